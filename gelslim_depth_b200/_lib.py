@@ -1,0 +1,80 @@
+"""ctypes binding of libgsd_b200.so (C ABI declared in include/gsd_b200.h).
+
+The library is the product: if it is missing or fails to load, importing this module raises --
+nothing in this package falls back to PyTorch or CPU arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgsd_b200.so")
+
+GSD_MAX_DIMS = 8
+DTYPE_BF16, DTYPE_FP32 = 0, 1
+MODE_INFER, MODE_TRAIN = 0, 1
+
+
+class Geometry(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("in_channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+                ("n_classes", C.c_int32), ("n_dims", C.c_int32), ("dims", C.c_int32 * GSD_MAX_DIMS),
+                ("dtype", C.c_int32), ("mode", C.c_int32)]
+
+
+class PrePost(C.Structure):
+    _fields_ = [("use_diff", C.c_int32), ("base_batch", C.c_int32), ("raw_height", C.c_int32), ("raw_width", C.c_int32),
+                ("out_height", C.c_int32), ("out_width", C.c_int32), ("in_scale", C.c_float * 8),
+                ("in_shift", C.c_float * 8), ("out_scale", C.c_float), ("out_shift", C.c_float)]
+
+
+# name -> (restype, argtypes): every symbol include/gsd_b200.h declares
+SYMBOLS = {
+    "gsd_abi_version": (C.c_int, []),
+    "gsd_last_error": (C.c_char_p, []),
+    "gsd_device_count": (C.c_int, []),
+    "gsd_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Geometry), C.c_int]),
+    "gsd_plan_destroy": (None, [C.c_void_p]),
+    "gsd_plan_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "gsd_plan_packed_bytes": (C.c_size_t, [C.c_void_p]),
+    "gsd_plan_num_params": (C.c_int, [C.c_void_p]),
+    "gsd_plan_num_bn_buffers": (C.c_int, [C.c_void_p]),
+    "gsd_plan_forward_launches": (C.c_int, [C.c_void_p]),
+    "gsd_plan_set_chunk": (C.c_int, [C.c_void_p, C.c_int]),
+    "gsd_plan_conv_flops": (C.c_double, [C.c_void_p]),
+    "gsd_pack_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "gsd_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p]),
+    "gsd_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsd_op_conv_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p]),
+    "gsd_op_image_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p,
+                                      C.c_int, C.c_void_p]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m gelslim_depth_b200.build` (needs nvcc). "
+        "gelslim_depth_b200 has no CPU / PyTorch fallback.")
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SYMBOLS.items():
+    _fn = getattr(lib, _name)          # AttributeError here == ABI mismatch, fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.gsd_abi_version() != 1:
+    raise ImportError("libgsd_b200.so ABI version mismatch")
+
+
+class GsdError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise GsdError(f"{what}: {lib.gsd_last_error().decode(errors='replace')} (rc={rc})")

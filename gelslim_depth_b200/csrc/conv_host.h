@@ -1,0 +1,169 @@
+// Host side of the tcgen05 conv: tile-shape / BN selection, tensor-map construction, launch.
+#pragma once
+#include <string.h>
+
+#include "conv_tc.cuh"
+#include "host_util.h"
+
+namespace gsd {
+
+struct ConvDesc {
+  const void* src0 = nullptr; int C0 = 0;                    // (B,H,W,C0) bf16
+  const void* src1 = nullptr; int C1 = 0, H1 = 0, W1 = 0;    // (B,H1,W1,C1) bf16, placed at (off_y, off_x)
+  int off_y = 0, off_x = 0;
+  int B = 0, H = 0, W = 0;
+  const void* w = nullptr;     // bf16 [groups*Cout][ntaps*(C0+C1)]
+  int Cout = 0;                // per output view
+  int groups = 1;              // 1: plain conv; 4: transposed-conv 2x2/s2 scatter
+  int ntaps = 1;
+  int8_t dy[kMaxTaps] = {0}, dx[kMaxTaps] = {0};
+  const float* scale = nullptr; const float* shift = nullptr;   // [groups*Cout]
+  int relu = 0;
+  void* out = nullptr;         // (B,H,W,Cout) or, groups==4, (B,2H,2W,Cout)
+  void* pooled = nullptr;      // (B,H/2,W/2,Cout) or null
+  int block_n = 0;             // 0 = choose
+};
+
+struct ConvLaunch {
+  ConvParams p;
+  int bn = 0, bkb = 0, grid = 0;
+  double flops = 0;            // 2*M*N*K of the real (unpadded) problem
+};
+
+inline void pick_tile(int H, int W, bool pool, int* th, int* tw) {
+  static const int cand[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
+  long best = -1;
+  for (auto& c : cand) {
+    if (pool && (c[0] & 1)) continue;
+    long covered = (long)((H + c[0] - 1) / c[0]) * c[0] * ((W + c[1] - 1) / c[1]) * c[1];
+    if (best < 0 || covered < best) { best = covered; *th = c[0]; *tw = c[1]; }
+  }
+}
+
+inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
+  memset(L, 0, sizeof *L);
+  GSD_CHECK(d.ntaps >= 1 && d.ntaps <= kMaxTaps, "conv: ntaps %d out of range", d.ntaps);
+  GSD_CHECK(d.groups == 1 || d.groups == 4, "conv: groups must be 1 or 4");
+  GSD_CHECK(d.Cout % 64 == 0 && d.Cout > 0, "conv: Cout %d must be a multiple of 64", d.Cout);
+  int bkb;
+  if (d.C0 % 64 == 0 && d.C1 % 64 == 0) bkb = 128;
+  else if (d.C0 == 16 && d.C1 == 0) bkb = 32;
+  else return fail(-1, "conv: unsupported input channels C0=%d C1=%d (need multiples of 64, or 16 for the first layer)", d.C0, d.C1);
+  const int kel = bkb / 2;
+  GSD_CHECK(!(d.pooled && d.groups != 1), "conv: pooling with the transposed-conv scatter is not supported");
+  GSD_CHECK(!d.pooled || (d.H >= 2 && d.W >= 2), "conv: pooled output needs H,W >= 2");
+
+  ConvParams& p = L->p;
+  int th = 8, tw = 16;
+  pick_tile(d.H, d.W, d.pooled != nullptr, &th, &tw);
+  p.th = th; p.tw = tw;
+  p.tiles_x = (d.W + tw - 1) / tw;
+  p.tiles_y = (d.H + th - 1) / th;
+  p.batch = d.B;
+  const int m_tiles = p.tiles_x * p.tiles_y * d.B;
+  const int ntot = d.groups * d.Cout;
+
+  int bn = d.block_n;
+  if (bn == 0) {
+    bn = 64;
+    const int cands[3] = {256, 128, 64};
+    for (int c : cands) {
+      if (d.Cout % c) continue;
+      if (bkb == 32 && c != 64) continue;
+      if ((long)m_tiles * (ntot / c) >= 2L * num_sms || c == 64) { bn = c; break; }
+    }
+  }
+  GSD_CHECK(bn == 64 || bn == 128 || bn == 256, "conv: block_n %d invalid", bn);
+  GSD_CHECK(d.Cout % bn == 0, "conv: block_n %d does not divide Cout %d", bn, d.Cout);
+  GSD_CHECK(!(bkb == 32 && bn != 64), "conv: first-layer path supports block_n 64 only");
+  L->bn = bn; L->bkb = bkb;
+  p.n_tiles = ntot / bn;
+  p.cout_per_group = d.Cout;
+  p.kb0 = d.C0 / kel;
+  p.kb1 = d.C1 / kel;
+  p.ntaps = d.ntaps;
+  for (int i = 0; i < d.ntaps; ++i) { p.tap_dy[i] = d.dy[i]; p.tap_dx[i] = d.dx[i]; }
+  p.off_x = d.off_x; p.off_y = d.off_y;
+  p.scale = d.scale; p.shift = d.shift;
+  p.relu = d.relu;
+  p.do_pool = d.pooled ? 1 : 0;
+
+  const CUtensorMapSwizzle swz = bkb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  {
+    uint64_t dims[4] = {(uint64_t)d.C0, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+    uint64_t str[3] = {(uint64_t)d.C0 * 2, (uint64_t)d.W * d.C0 * 2, (uint64_t)d.H * d.W * d.C0 * 2};
+    uint32_t box[4] = {(uint32_t)kel, (uint32_t)tw, (uint32_t)th, 1};
+    GSD_TRY(encode_bf16_map(&p.tm_src0, const_cast<void*>(d.src0), 4, dims, str, box, swz, false));
+  }
+  if (d.C1) {
+    uint64_t dims[4] = {(uint64_t)d.C1, (uint64_t)d.W1, (uint64_t)d.H1, (uint64_t)d.B};
+    uint64_t str[3] = {(uint64_t)d.C1 * 2, (uint64_t)d.W1 * d.C1 * 2, (uint64_t)d.H1 * d.W1 * d.C1 * 2};
+    uint32_t box[4] = {(uint32_t)kel, (uint32_t)tw, (uint32_t)th, 1};
+    GSD_TRY(encode_bf16_map(&p.tm_src1, const_cast<void*>(d.src1), 4, dims, str, box, swz, false));
+  } else {
+    p.tm_src1 = p.tm_src0;
+  }
+  {
+    const uint64_t ktot = (uint64_t)d.ntaps * (d.C0 + d.C1);
+    uint64_t dims[2] = {ktot, (uint64_t)ntot};
+    uint64_t str[1] = {ktot * 2};
+    uint32_t box[2] = {(uint32_t)kel, (uint32_t)bn};
+    GSD_TRY(encode_bf16_map(&p.tm_w, const_cast<void*>(d.w), 2, dims, str, box, swz, true));
+  }
+  if (d.groups == 1) {
+    uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+    uint64_t str[3] = {(uint64_t)d.Cout * 2, (uint64_t)d.W * d.Cout * 2, (uint64_t)d.H * d.W * d.Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
+    GSD_TRY(encode_bf16_map(&p.tm_out[0], d.out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
+    for (int g = 1; g < 4; ++g) p.tm_out[g] = p.tm_out[0];
+  } else {
+    // out is (B, 2H, 2W, Cout); view g = dy*2+dx selects pixels (2y+dy, 2x+dx)
+    const uint64_t W2 = 2ull * d.W, H2 = 2ull * d.H;
+    for (int g = 0; g < 4; ++g) {
+      const int gy = g >> 1, gx = g & 1;
+      char* base = static_cast<char*>(d.out) + ((uint64_t)gy * W2 + gx) * d.Cout * 2;
+      uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+      uint64_t str[3] = {2ull * d.Cout * 2, 2ull * W2 * d.Cout * 2, H2 * W2 * d.Cout * 2};
+      uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
+      GSD_TRY(encode_bf16_map(&p.tm_out[g], base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
+    }
+  }
+  if (d.pooled) {
+    const int ph = d.H / 2, pw = d.W / 2;
+    uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)pw, (uint64_t)ph, (uint64_t)d.B};
+    uint64_t str[3] = {(uint64_t)d.Cout * 2, (uint64_t)pw * d.Cout * 2, (uint64_t)ph * pw * d.Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)(tw / 2), (uint32_t)(th / 2), 1};
+    GSD_TRY(encode_bf16_map(&p.tm_pool, d.pooled, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
+  } else {
+    p.tm_pool = p.tm_out[0];
+  }
+  const long total = (long)m_tiles * p.n_tiles;
+  L->grid = (int)(total < num_sms ? total : num_sms);
+  L->flops = 2.0 * d.B * d.H * d.W * (double)ntot * d.ntaps * (d.C0 + d.C1);
+  return 0;
+}
+
+template <int BN, int BKB>
+inline int launch_conv_cfg(const ConvLaunch& L, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, BKB>;
+  static bool attr_set = false;   // per process; one device family
+  if (!attr_set) {
+    GSD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN, BKB><<<L.grid, kConvThreads, Cfg::SMEM_BYTES, st>>>(L.p);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+inline int run_conv_launch(const ConvLaunch& L, cudaStream_t st) {
+  if (L.bkb == 32) return launch_conv_cfg<64, 32>(L, st);
+  switch (L.bn) {
+    case 64: return launch_conv_cfg<64, 128>(L, st);
+    case 128: return launch_conv_cfg<128, 128>(L, st);
+    case 256: return launch_conv_cfg<256, 128>(L, st);
+  }
+  return fail(-1, "conv: no kernel for block_n %d", L.bn);
+}
+
+}  // namespace gsd

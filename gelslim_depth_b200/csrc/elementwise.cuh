@@ -1,0 +1,194 @@
+// Memory-bound kernels around the tensor-core convs: input prologue, 1x1 head, area resampling,
+// weight packing.  All are one-pass, coalesced, 128-bit vectorised where the layout allows.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gsd {
+
+struct PreParams {
+  const float* x;      // (B, C, Hr, Wr) fp32 NCHW raw frames
+  const float* base;   // (Bb, C, Hr, Wr) or null
+  int base_batch;
+  int use_diff;
+  int B, C, Hr, Wr, H, W;
+  float in_scale[8], in_shift[8];
+};
+
+// get_difference_image (image_utils.py:6-10) -> area down-sample (image_utils.py:12-15) ->
+// normalize_tactile_image (normalization_utils.py:29-34) -> NHWC bf16 with channels padded to 16
+// (the first conv's K-block).  One thread per output pixel; reads are coalesced along x per channel
+// plane, the 32-byte pixel record is written as two 16-byte stores.
+__global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_bfloat16* __restrict__ out) {
+  const long total = (long)p.B * p.H * p.W;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.W);
+    const int y = (int)((idx / p.W) % p.H);
+    const int b = (int)(idx / ((long)p.W * p.H));
+    // adaptive-average-pool bin: [floor(i*in/out), ceil((i+1)*in/out))
+    const int ys = (int)(((long)y * p.Hr) / p.H), ye = (int)((((long)y + 1) * p.Hr + p.H - 1) / p.H);
+    const int xs = (int)(((long)x * p.Wr) / p.W), xe = (int)((((long)x + 1) * p.Wr + p.W - 1) / p.W);
+    const float inv = 1.0f / (float)((ye - ys) * (xe - xs));
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < p.C) {
+        const float* px = p.x + ((long)b * p.C + c) * p.Hr * p.Wr;
+        const float* pb = p.base ? p.base + ((long)(p.base_batch == 1 ? 0 : b) * p.C + c) * p.Hr * p.Wr : nullptr;
+        float acc = 0.f;
+        for (int yy = ys; yy < ye; ++yy)
+          for (int xx = xs; xx < xe; ++xx) {
+            float t = __ldg(px + (long)yy * p.Wr + xx);
+            if (p.use_diff) t = (t - __ldg(pb + (long)yy * p.Wr + xx) + 255.0f) * 0.5f;
+            acc += t;
+          }
+        v[c] = p.in_scale[c] * (acc * inv) + p.in_shift[c];
+      }
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// OutConv 1x1 + bias (unet.py:54) + denormalize_depth_image (normalization_utils.py:129):
+// (B,H,W,64) bf16 NHWC -> (B,ncls,H,W) fp32 NCHW.  One thread per pixel: 128 contiguous bytes in,
+// ncls coalesced floats out.
+template <int CIN>
+__global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, int ncls, float out_scale,
+                                                   float out_shift, long npix_per_img, int B, float* __restrict__ y) {
+  __shared__ float sw[4 * CIN];
+  __shared__ float sb[4];
+  for (int i = threadIdx.x; i < ncls * CIN; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < ncls) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long total = npix_per_img * B;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const uint4* src = reinterpret_cast<const uint4*>(in + idx * CIN);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ch = 0; ch < CIN / 8; ++ch) {
+      const uint4 u = __ldg(src + ch);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[j]));
+        const int c = ch * 8 + 2 * j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < ncls) acc[k] += f.x * sw[k * CIN + c] + f.y * sw[k * CIN + c + 1];
+      }
+    }
+    const long b = idx / npix_per_img, pix = idx - b * npix_per_img;
+    for (int k = 0; k < ncls; ++k) y[(b * ncls + k) * npix_per_img + pix] = (acc[k] + sb[k]) * out_scale + out_shift;
+  }
+}
+
+// F.interpolate(mode='area') == adaptive average pooling, fp32 NCHW planes (complete_prediction.py:9).
+__global__ void __launch_bounds__(256) area_resample_kernel(const float* __restrict__ in, int planes, int Hi, int Wi,
+                                                            int Ho, int Wo, float* __restrict__ out) {
+  const long total = (long)planes * Ho * Wo;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % Wo);
+    const int y = (int)((idx / Wo) % Ho);
+    const long pl = idx / ((long)Wo * Ho);
+    const int ys = (int)(((long)y * Hi) / Ho), ye = (int)((((long)y + 1) * Hi + Ho - 1) / Ho);
+    const int xs = (int)(((long)x * Wi) / Wo), xe = (int)((((long)x + 1) * Wi + Wo - 1) / Wo);
+    const float* src = in + pl * Hi * Wi;
+    float acc = 0.f;
+    for (int yy = ys; yy < ye; ++yy)
+      for (int xx = xs; xx < xe; ++xx) acc += __ldg(src + (long)yy * Wi + xx);
+    out[idx] = acc / (float)((ye - ys) * (xe - xs));
+  }
+}
+
+// Stand-alone form of the processing helpers (image_utils.py:6-15, normalization_utils.py:4-130) for
+// callers that use them outside predict_depth_from_RGB: fp32 NCHW -> fp32 NCHW,
+//   out[c] = scale[c] * area_resample(use_diff ? (x - base + 255)/2 : x) + shift[c].
+__global__ void __launch_bounds__(256) image_affine_kernel(const PreParams p, float* __restrict__ out) {
+  const long total = (long)p.B * p.C * p.H * p.W;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.W);
+    const int y = (int)((idx / p.W) % p.H);
+    const int c = (int)((idx / ((long)p.W * p.H)) % p.C);
+    const int b = (int)(idx / ((long)p.W * p.H * p.C));
+    const int ys = (int)(((long)y * p.Hr) / p.H), ye = (int)((((long)y + 1) * p.Hr + p.H - 1) / p.H);
+    const int xs = (int)(((long)x * p.Wr) / p.W), xe = (int)((((long)x + 1) * p.Wr + p.W - 1) / p.W);
+    const float* px = p.x + ((long)b * p.C + c) * p.Hr * p.Wr;
+    const float* pb = p.base ? p.base + ((long)(p.base_batch == 1 ? 0 : b) * p.C + c) * p.Hr * p.Wr : nullptr;
+    float acc = 0.f;
+    for (int yy = ys; yy < ye; ++yy)
+      for (int xx = xs; xx < xe; ++xx) {
+        float t = __ldg(px + (long)yy * p.Wr + xx);
+        if (p.use_diff) t = (t - __ldg(pb + (long)yy * p.Wr + xx) + 255.0f) * 0.5f;
+        acc += t;
+      }
+    const int cc = c < 8 ? c : 7;
+    out[idx] = p.in_scale[cc] * (acc / (float)((ye - ys) * (xe - xs))) + p.in_shift[cc];
+  }
+}
+
+// ---------------------------------------------------------------- weight packing
+// Conv2d weight (O, I, kh, kw) fp32 -> bf16 [O][kh*kw][Ipad], zero for i >= I.
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int I, int taps, int Ipad,
+                                        __nv_bfloat16* __restrict__ out) {
+  const long total = (long)O * taps * Ipad;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % Ipad);
+    const int t = (int)((idx / Ipad) % taps);
+    const int o = (int)(idx / ((long)Ipad * taps));
+    out[idx] = __float2bfloat16_rn(i < I ? w[((long)o * I + i) * taps + t] : 0.f);
+  }
+}
+// ConvTranspose2d weight (I, O, 2, 2) fp32 -> bf16 [(dy*2+dx)*O + o][I]
+__global__ void pack_convt_weight_kernel(const float* __restrict__ w, int I, int O, __nv_bfloat16* __restrict__ out) {
+  const long total = 4L * O * I;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % I);
+    const int o = (int)((idx / I) % O);
+    const int g = (int)(idx / ((long)I * O));
+    out[idx] = __float2bfloat16_rn(w[((long)i * O + o) * 4 + g]);
+  }
+}
+// eval-mode BatchNorm folded to y = x*scale + shift (unet.py:12; eps 1e-5)
+__global__ void fold_bn_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, int C, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float s = gamma[c] * rsqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - mean[c] * s;
+  }
+}
+// transposed-conv epilogue constants: scale 1, shift = bias[o] for each of the 4 (dy,dx) groups
+__global__ void convt_bias_kernel(const float* __restrict__ bias, int O, float* __restrict__ scale,
+                                  float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * O) {
+    scale[i] = 1.f;
+    shift[i] = bias[i % O];
+  }
+}
+__global__ void copy_f32_kernel(const float* __restrict__ src, long n, float* __restrict__ dst) {
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x)
+    dst[idx] = src[idx];
+}
+
+inline int ew_grid(long total, int threads = 256, int cap = 148 * 16) {
+  long g = (total + threads - 1) / threads;
+  if (g < 1) g = 1;
+  return (int)(g > cap ? cap : g);
+}
+
+}  // namespace gsd

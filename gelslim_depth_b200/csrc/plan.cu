@@ -1,0 +1,463 @@
+// libgsd_b200.so -- plan construction, weight packing and the C ABI (include/gsd_b200.h).
+#include <vector>
+
+#include "../../include/gsd_b200.h"
+#include "conv_host.h"
+#include "elementwise.cuh"
+#include "host_util.h"
+
+using namespace gsd;
+
+namespace {
+
+struct ConvW {          // one packed conv3x3 (or the 2x2 transposed conv)
+  size_t w_off = 0, scale_off = 0, shift_off = 0;
+  int cin = 0, cin_pad = 0, cout = 0, taps = 0;
+};
+
+struct ChunkLaunches {
+  int b0 = 0, nb = 0;
+  std::vector<ConvLaunch> convs;
+};
+
+}  // namespace
+
+struct gsd_plan {
+  gsd_geometry g{};
+  int device = 0, num_sms = 148;
+  int depth = 0;
+  std::vector<int> Hs, Ws;
+  // packed arena
+  std::vector<ConvW> enc;     // inc.0, inc.3, down.i.0, down.i.3 ...   (2*(depth+1))
+  std::vector<ConvW> upT;     // up.i.up                                 (depth)
+  std::vector<ConvW> dec;     // up.i.conv.0, up.i.conv.3               (2*depth)
+  size_t head_w_off = 0, head_b_off = 0, packed_bytes = 0;
+  // workspace (element offsets are in bytes)
+  size_t in16_off = 0, head_tmp_off = 0, ws_bytes = 0;
+  std::vector<size_t> a_off, s_off, p_off, u_off, da_off, db_off;
+  // bound state
+  int chunk = 0;
+  void* bound_ws = nullptr;
+  const void* bound_packed = nullptr;
+  std::vector<ChunkLaunches> chunks;
+  // host-pipelined forward
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
+  cudaEvent_t ev_start = nullptr;
+  double conv_flops = 0;
+};
+
+static size_t bump(size_t* cur, size_t bytes) {
+  size_t off = align_up(*cur, 1024);
+  *cur = off + bytes;
+  return off;
+}
+
+extern "C" int gsd_abi_version(void) { return GSD_ABI_VERSION; }
+extern "C" const char* gsd_last_error(void) { return last_error_ref().c_str(); }
+
+extern "C" int gsd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+extern "C" int gsd_plan_create(gsd_plan** out, const gsd_geometry* g, int device) {
+  GSD_CHECK(out && g, "gsd_plan_create: null argument");
+  GSD_CHECK(g->dtype == GSD_DTYPE_BF16, "gsd_plan_create: dtype %d not implemented (bf16 only in this build)", g->dtype);
+  GSD_CHECK(g->mode == GSD_MODE_INFER, "gsd_plan_create: mode %d not implemented (inference only in this build)", g->mode);
+  GSD_CHECK(g->batch >= 1 && g->height >= 1 && g->width >= 1, "gsd_plan_create: bad shape");
+  GSD_CHECK(g->in_channels >= 1 && g->in_channels <= 8, "gsd_plan_create: in_channels %d not in 1..8", g->in_channels);
+  GSD_CHECK(g->n_classes >= 1 && g->n_classes <= 4, "gsd_plan_create: n_classes %d not in 1..4", g->n_classes);
+  GSD_CHECK(g->n_dims >= 2 && g->n_dims <= GSD_MAX_DIMS, "gsd_plan_create: n_dims %d not in 2..%d", g->n_dims, GSD_MAX_DIMS);
+  for (int i = 0; i < g->n_dims; ++i)
+    GSD_CHECK(g->dims[i] > 0 && g->dims[i] % 64 == 0, "gsd_plan_create: layer_dimensions[%d]=%d must be a multiple of 64", i, g->dims[i]);
+  for (int i = 0; i + 1 < g->n_dims; ++i)
+    GSD_CHECK(g->dims[i + 1] == 2 * g->dims[i],
+              "gsd_plan_create: layer_dimensions[%d]=%d must be 2x layer_dimensions[%d] (torch.cat in Up, unet.py:48)", i + 1,
+              g->dims[i + 1], i);
+  GSD_CHECK(g->dims[0] == 64, "gsd_plan_create: layer_dimensions[0] must be 64 (1x1 head kernel)");
+  int ndev = 0;
+  GSD_CUDA(cudaGetDeviceCount(&ndev));
+  GSD_CHECK(device >= 0 && device < ndev, "gsd_plan_create: device %d out of range (%d devices)", device, ndev);
+  int major = 0, sms = 0;
+  GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  GSD_CHECK(major == 10, "gsd_plan_create: device %d is sm_%d0; this library contains sm_100a code only (no fallback)", device, major);
+
+  gsd_plan* p = new gsd_plan();
+  p->g = *g;
+  p->device = device;
+  p->num_sms = sms;
+  p->depth = g->n_dims - 1;
+  p->Hs.push_back(g->height);
+  p->Ws.push_back(g->width);
+  for (int l = 0; l < p->depth; ++l) {
+    p->Hs.push_back(p->Hs.back() / 2);
+    p->Ws.push_back(p->Ws.back() / 2);
+  }
+  if (p->Hs.back() < 1 || p->Ws.back() < 1) {
+    delete p;
+    return fail(-1, "gsd_plan_create: %dx%d is too small for %d poolings", g->height, g->width, g->n_dims - 1);
+  }
+  // ---- packed arena
+  size_t cur = 0;
+  auto add_conv = [&](std::vector<ConvW>& v, int cin, int cin_pad, int cout, int taps, int ngroups) {
+    ConvW c;
+    c.cin = cin; c.cin_pad = cin_pad; c.cout = cout; c.taps = taps;
+    c.w_off = bump(&cur, (size_t)ngroups * cout * taps * cin_pad * 2);
+    c.scale_off = bump(&cur, (size_t)ngroups * cout * 4);
+    c.shift_off = bump(&cur, (size_t)ngroups * cout * 4);
+    v.push_back(c);
+  };
+  add_conv(p->enc, g->in_channels, 16, g->dims[0], 9, 1);
+  add_conv(p->enc, g->dims[0], g->dims[0], g->dims[0], 9, 1);
+  for (int l = 0; l < p->depth; ++l) {
+    add_conv(p->enc, g->dims[l], g->dims[l], g->dims[l + 1], 9, 1);
+    add_conv(p->enc, g->dims[l + 1], g->dims[l + 1], g->dims[l + 1], 9, 1);
+  }
+  for (int i = 0; i < p->depth; ++i) {
+    const int l = p->depth - 1 - i;
+    add_conv(p->upT, g->dims[l + 1], g->dims[l + 1], g->dims[l], 1, 4);
+    add_conv(p->dec, g->dims[l + 1], g->dims[l + 1], g->dims[l], 9, 1);
+    add_conv(p->dec, g->dims[l], g->dims[l], g->dims[l], 9, 1);
+  }
+  p->head_w_off = bump(&cur, (size_t)g->n_classes * g->dims[0] * 4);
+  p->head_b_off = bump(&cur, 16);
+  p->packed_bytes = align_up(cur, 1024);
+  // ---- workspace
+  cur = 0;
+  const size_t B = g->batch;
+  p->in16_off = bump(&cur, B * g->height * g->width * 16 * 2);
+  for (int l = 0; l <= p->depth; ++l) {
+    const size_t px = B * p->Hs[l] * p->Ws[l];
+    p->a_off.push_back(bump(&cur, px * g->dims[l] * 2));
+    p->s_off.push_back(bump(&cur, px * g->dims[l] * 2));
+    if (l < p->depth) p->p_off.push_back(bump(&cur, B * p->Hs[l + 1] * p->Ws[l + 1] * g->dims[l] * 2));
+  }
+  for (int i = 0; i < p->depth; ++i) {
+    const int l = p->depth - 1 - i;
+    p->u_off.push_back(bump(&cur, B * (2 * p->Hs[l + 1]) * (2 * p->Ws[l + 1]) * g->dims[l] * 2));
+    const size_t px = B * p->Hs[l] * p->Ws[l];
+    p->da_off.push_back(bump(&cur, px * g->dims[l] * 2));
+    p->db_off.push_back(bump(&cur, px * g->dims[l] * 2));
+  }
+  p->head_tmp_off = bump(&cur, B * g->n_classes * g->height * g->width * 4);
+  p->ws_bytes = align_up(cur, 1024);
+  p->chunk = g->batch;
+  *out = p;
+  return 0;
+}
+
+extern "C" void gsd_plan_destroy(gsd_plan* p) {
+  if (!p) return;
+  for (auto e : p->ev_in) cudaEventDestroy(e);
+  for (auto e : p->ev_done) cudaEventDestroy(e);
+  if (p->ev_start) cudaEventDestroy(p->ev_start);
+  if (p->copy_in) cudaStreamDestroy(p->copy_in);
+  if (p->copy_out) cudaStreamDestroy(p->copy_out);
+  delete p;
+}
+
+extern "C" size_t gsd_plan_workspace_bytes(const gsd_plan* p) { return p ? p->ws_bytes : 0; }
+extern "C" size_t gsd_plan_packed_bytes(const gsd_plan* p) { return p ? p->packed_bytes : 0; }
+extern "C" int gsd_plan_num_params(const gsd_plan* p) { return p ? 6 * (p->depth + 1) + 8 * p->depth + 2 : 0; }
+extern "C" int gsd_plan_num_bn_buffers(const gsd_plan* p) { return p ? 2 * (2 * (p->depth + 1) + 2 * p->depth) : 0; }
+extern "C" int gsd_plan_forward_launches(const gsd_plan* p) {
+  if (!p) return 0;
+  const int nchunks = (p->g.batch + p->chunk - 1) / p->chunk;
+  return nchunks * (1 + 2 * (p->depth + 1) + 3 * p->depth + 1);   // + area resample when sizes differ (runtime)
+}
+extern "C" int gsd_plan_set_chunk(gsd_plan* p, int frames_per_chunk) {
+  GSD_CHECK(p && frames_per_chunk >= 1, "gsd_plan_set_chunk: bad argument");
+  p->chunk = frames_per_chunk > p->g.batch ? p->g.batch : frames_per_chunk;
+  p->bound_ws = nullptr;   // force re-binding
+  return 0;
+}
+extern "C" double gsd_plan_conv_flops(const gsd_plan* p) { return p ? p->conv_flops : 0; }
+
+extern "C" int gsd_pack_weights(gsd_plan* p, const void* const* params, const void* const* bn, void* packed,
+                                void* stream) {
+  GSD_CHECK(p && params && bn && packed, "gsd_pack_weights: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GSD_CUDA(cudaSetDevice(p->device));
+  char* base = static_cast<char*>(packed);
+  int pi = 0, bi = 0;
+  auto F = [](const void* q) { return static_cast<const float*>(q); };
+  auto pack_conv_bn = [&](const ConvW& c) -> int {
+    const float* w = F(params[pi++]);
+    const float* gamma = F(params[pi++]);
+    const float* beta = F(params[pi++]);
+    const float* mean = F(bn[bi++]);
+    const float* var = F(bn[bi++]);
+    const long total = (long)c.cout * c.taps * c.cin_pad;
+    pack_conv_weight_kernel<<<ew_grid(total), 256, 0, st>>>(w, c.cout, c.cin, c.taps, c.cin_pad,
+                                                             reinterpret_cast<__nv_bfloat16*>(base + c.w_off));
+    fold_bn_kernel<<<(c.cout + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, c.cout, 1e-5f,
+                                                         reinterpret_cast<float*>(base + c.scale_off),
+                                                         reinterpret_cast<float*>(base + c.shift_off));
+    GSD_CUDA(cudaGetLastError());
+    return 0;
+  };
+  for (size_t i = 0; i < p->enc.size(); ++i) GSD_TRY(pack_conv_bn(p->enc[i]));
+  for (int i = 0; i < p->depth; ++i) {
+    const ConvW& u = p->upT[i];
+    const float* w = F(params[pi++]);
+    const float* b = F(params[pi++]);
+    pack_convt_weight_kernel<<<ew_grid(4L * u.cout * u.cin), 256, 0, st>>>(w, u.cin, u.cout,
+                                                                           reinterpret_cast<__nv_bfloat16*>(base + u.w_off));
+    convt_bias_kernel<<<(4 * u.cout + 127) / 128, 128, 0, st>>>(b, u.cout, reinterpret_cast<float*>(base + u.scale_off),
+                                                                reinterpret_cast<float*>(base + u.shift_off));
+    GSD_CUDA(cudaGetLastError());
+    GSD_TRY(pack_conv_bn(p->dec[2 * i]));
+    GSD_TRY(pack_conv_bn(p->dec[2 * i + 1]));
+  }
+  const long hw = (long)p->g.n_classes * p->g.dims[0];
+  copy_f32_kernel<<<1, 256, 0, st>>>(F(params[pi++]), hw, reinterpret_cast<float*>(base + p->head_w_off));
+  copy_f32_kernel<<<1, 32, 0, st>>>(F(params[pi++]), p->g.n_classes, reinterpret_cast<float*>(base + p->head_b_off));
+  GSD_CUDA(cudaGetLastError());
+  GSD_CHECK(pi == gsd_plan_num_params(p) && bi == gsd_plan_num_bn_buffers(p), "gsd_pack_weights: internal count mismatch");
+  return 0;
+}
+
+static void taps3x3(ConvDesc* d) {
+  d->ntaps = 9;
+  for (int t = 0; t < 9; ++t) { d->dy[t] = (int8_t)(t / 3 - 1); d->dx[t] = (int8_t)(t % 3 - 1); }
+}
+
+// (Re)build every tensor map / launch record for the given workspace + packed-weight addresses.
+static int bind(gsd_plan* p, void* ws, const void* packed) {
+  if (p->bound_ws == ws && p->bound_packed == packed && !p->chunks.empty()) return 0;
+  p->chunks.clear();
+  p->conv_flops = 0;
+  const gsd_geometry& g = p->g;
+  char* W = static_cast<char*>(ws);
+  const char* P = static_cast<const char*>(packed);
+  auto fptr = [&](size_t off) { return reinterpret_cast<const float*>(P + off); };
+  for (int b0 = 0; b0 < g.batch; b0 += p->chunk) {
+    ChunkLaunches ch;
+    ch.b0 = b0;
+    ch.nb = (b0 + p->chunk <= g.batch) ? p->chunk : g.batch - b0;
+    auto act = [&](size_t off, int l_h, int l_w, int c) {   // address of frame b0 inside a (B,h,w,c) bf16 tensor
+      return static_cast<void*>(W + off + (size_t)b0 * l_h * l_w * c * 2);
+    };
+    auto add = [&](ConvDesc& d) -> int {
+      ConvLaunch L;
+      GSD_TRY(build_conv_launch(d, p->num_sms, &L));
+      p->conv_flops += L.flops;
+      ch.convs.push_back(L);
+      return 0;
+    };
+    // encoder
+    for (int l = 0; l <= p->depth; ++l) {
+      const int h = p->Hs[l], w = p->Ws[l];
+      ConvDesc d0;
+      taps3x3(&d0);
+      d0.B = ch.nb; d0.H = h; d0.W = w;
+      if (l == 0) { d0.src0 = act(p->in16_off, h, w, 16); d0.C0 = 16; }
+      else { d0.src0 = act(p->p_off[l - 1], h, w, g.dims[l - 1]); d0.C0 = g.dims[l - 1]; }
+      const ConvW& c0 = p->enc[2 * l];
+      d0.w = P + c0.w_off; d0.scale = fptr(c0.scale_off); d0.shift = fptr(c0.shift_off);
+      d0.Cout = g.dims[l]; d0.relu = 1;
+      d0.out = act(p->a_off[l], h, w, g.dims[l]);
+      GSD_TRY(add(d0));
+      ConvDesc d1;
+      taps3x3(&d1);
+      d1.B = ch.nb; d1.H = h; d1.W = w;
+      d1.src0 = d0.out; d1.C0 = g.dims[l];
+      const ConvW& c1 = p->enc[2 * l + 1];
+      d1.w = P + c1.w_off; d1.scale = fptr(c1.scale_off); d1.shift = fptr(c1.shift_off);
+      d1.Cout = g.dims[l]; d1.relu = 1;
+      d1.out = act(p->s_off[l], h, w, g.dims[l]);
+      if (l < p->depth) d1.pooled = act(p->p_off[l], p->Hs[l + 1], p->Ws[l + 1], g.dims[l]);
+      GSD_TRY(add(d1));
+    }
+    // decoder
+    for (int i = 0; i < p->depth; ++i) {
+      const int l = p->depth - 1 - i;
+      const int hs = p->Hs[l + 1], wsz = p->Ws[l + 1], h = p->Hs[l], w = p->Ws[l];
+      ConvDesc t;
+      t.ntaps = 1; t.groups = 4;
+      t.B = ch.nb; t.H = hs; t.W = wsz;
+      t.src0 = (i == 0) ? act(p->s_off[p->depth], hs, wsz, g.dims[l + 1]) : act(p->db_off[i - 1], hs, wsz, g.dims[l + 1]);
+      t.C0 = g.dims[l + 1];
+      const ConvW& u = p->upT[i];
+      t.w = P + u.w_off; t.scale = fptr(u.scale_off); t.shift = fptr(u.shift_off);
+      t.Cout = g.dims[l]; t.relu = 0;
+      t.out = act(p->u_off[i], 2 * hs, 2 * wsz, g.dims[l]);
+      GSD_TRY(add(t));
+      ConvDesc d0;
+      taps3x3(&d0);
+      d0.B = ch.nb; d0.H = h; d0.W = w;
+      d0.src0 = act(p->s_off[l], h, w, g.dims[l]); d0.C0 = g.dims[l];
+      d0.src1 = t.out; d0.C1 = g.dims[l]; d0.H1 = 2 * hs; d0.W1 = 2 * wsz;
+      d0.off_y = (h - 2 * hs) / 2; d0.off_x = (w - 2 * wsz) / 2;       // F.pad left/top = diff // 2 (unet.py:46-47)
+      const ConvW& c0 = p->dec[2 * i];
+      d0.w = P + c0.w_off; d0.scale = fptr(c0.scale_off); d0.shift = fptr(c0.shift_off);
+      d0.Cout = g.dims[l]; d0.relu = 1;
+      d0.out = act(p->da_off[i], h, w, g.dims[l]);
+      GSD_TRY(add(d0));
+      ConvDesc d1;
+      taps3x3(&d1);
+      d1.B = ch.nb; d1.H = h; d1.W = w;
+      d1.src0 = d0.out; d1.C0 = g.dims[l];
+      const ConvW& c1 = p->dec[2 * i + 1];
+      d1.w = P + c1.w_off; d1.scale = fptr(c1.scale_off); d1.shift = fptr(c1.shift_off);
+      d1.Cout = g.dims[l]; d1.relu = 1;
+      d1.out = act(p->db_off[i], h, w, g.dims[l]);
+      GSD_TRY(add(d1));
+    }
+    p->chunks.push_back(std::move(ch));
+  }
+  p->bound_ws = ws;
+  p->bound_packed = packed;
+  return 0;
+}
+
+static int check_prepost(const gsd_plan* p, const gsd_prepost* pp, const float* base) {
+  GSD_CHECK(pp != nullptr, "gsd_forward: gsd_prepost is required");
+  GSD_CHECK(pp->raw_height >= p->g.height && pp->raw_width >= p->g.width,
+            "gsd_forward: raw frames (%dx%d) smaller than the network input (%dx%d) are not supported", pp->raw_height,
+            pp->raw_width, p->g.height, p->g.width);
+  GSD_CHECK(pp->out_height >= 1 && pp->out_width >= 1, "gsd_forward: bad output size");
+  GSD_CHECK(!pp->use_diff || base != nullptr, "gsd_forward: use_diff set but base is NULL");
+  GSD_CHECK(!pp->use_diff || pp->base_batch == 1 || pp->base_batch == p->g.batch,
+            "gsd_forward: base_batch must be 1 or batch");
+  return 0;
+}
+
+// one chunk of frames through the whole network on `st`
+static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const float* base, const gsd_prepost* pp,
+                     float* y, void* ws, const void* packed, cudaStream_t st) {
+  const gsd_geometry& g = p->g;
+  char* W = static_cast<char*>(ws);
+  const char* P = static_cast<const char*>(packed);
+  PreParams pre;
+  const size_t raw_frame = (size_t)g.in_channels * pp->raw_height * pp->raw_width;
+  pre.x = x + (size_t)ch.b0 * raw_frame;
+  pre.base = pp->use_diff ? (pp->base_batch == 1 ? base : base + (size_t)ch.b0 * raw_frame) : nullptr;
+  pre.base_batch = pp->base_batch;
+  pre.use_diff = pp->use_diff;
+  pre.B = ch.nb; pre.C = g.in_channels; pre.Hr = pp->raw_height; pre.Wr = pp->raw_width; pre.H = g.height; pre.W = g.width;
+  for (int c = 0; c < 8; ++c) { pre.in_scale[c] = pp->in_scale[c]; pre.in_shift[c] = pp->in_shift[c]; }
+  __nv_bfloat16* in16 = reinterpret_cast<__nv_bfloat16*>(W + p->in16_off + (size_t)ch.b0 * g.height * g.width * 16 * 2);
+  prologue_kernel<<<ew_grid((long)ch.nb * g.height * g.width), 256, 0, st>>>(pre, in16);
+  GSD_CUDA(cudaGetLastError());
+  for (const ConvLaunch& L : ch.convs) GSD_TRY(run_conv_launch(L, st));
+  // head
+  const long npix = (long)g.height * g.width;
+  const __nv_bfloat16* last = reinterpret_cast<const __nv_bfloat16*>(W + p->db_off[p->depth - 1] + (size_t)ch.b0 * npix * 64 * 2);
+  const bool resample = pp->out_height != g.height || pp->out_width != g.width;
+  float* head_out = resample ? reinterpret_cast<float*>(W + p->head_tmp_off) + (size_t)ch.b0 * g.n_classes * npix
+                             : y + (size_t)ch.b0 * g.n_classes * npix;
+  head_kernel<64><<<ew_grid(npix * ch.nb), 256, 0, st>>>(last, reinterpret_cast<const float*>(P + p->head_w_off),
+                                                         reinterpret_cast<const float*>(P + p->head_b_off), g.n_classes,
+                                                         pp->out_scale, pp->out_shift, npix, ch.nb, head_out);
+  GSD_CUDA(cudaGetLastError());
+  if (resample) {
+    const long opix = (long)pp->out_height * pp->out_width;
+    area_resample_kernel<<<ew_grid(opix * ch.nb * g.n_classes), 256, 0, st>>>(
+        head_out, ch.nb * g.n_classes, g.height, g.width, pp->out_height, pp->out_width,
+        y + (size_t)ch.b0 * g.n_classes * opix);
+    GSD_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int gsd_forward(gsd_plan* p, const float* x, const float* base, const gsd_prepost* pp, float* y,
+                           void* workspace, const void* packed, void* stream) {
+  GSD_CHECK(p && x && y && workspace && packed, "gsd_forward: null argument");
+  GSD_TRY(check_prepost(p, pp, base));
+  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_TRY(bind(p, workspace, packed));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (const ChunkLaunches& ch : p->chunks) GSD_TRY(run_chunk(p, ch, x, base, pp, y, workspace, packed, st));
+  return 0;
+}
+
+extern "C" int gsd_forward_host(gsd_plan* p, const float* x_host, const float* base, const gsd_prepost* pp,
+                                float* y_host, float* x_dev, float* y_dev, void* workspace, const void* packed,
+                                void* stream) {
+  GSD_CHECK(p && x_host && y_host && x_dev && y_dev && workspace && packed, "gsd_forward_host: null argument");
+  GSD_TRY(check_prepost(p, pp, base));
+  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_TRY(bind(p, workspace, packed));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!p->copy_in) {
+    GSD_CUDA(cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking));
+    GSD_CUDA(cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking));
+    GSD_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+  }
+  while (p->ev_in.size() < p->chunks.size()) {
+    cudaEvent_t a, b;
+    GSD_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    GSD_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    p->ev_in.push_back(a);
+    p->ev_done.push_back(b);
+  }
+  const gsd_geometry& g = p->g;
+  const size_t raw_frame = (size_t)g.in_channels * pp->raw_height * pp->raw_width;
+  const size_t out_frame = (size_t)g.n_classes * pp->out_height * pp->out_width;
+  // work already queued on the caller's stream (e.g. weight packing) precedes the first copy
+  GSD_CUDA(cudaEventRecord(p->ev_start, st));
+  GSD_CUDA(cudaStreamWaitEvent(p->copy_in, p->ev_start, 0));
+  GSD_CUDA(cudaStreamWaitEvent(p->copy_out, p->ev_start, 0));
+  for (size_t c = 0; c < p->chunks.size(); ++c) {
+    const ChunkLaunches& ch = p->chunks[c];
+    GSD_CUDA(cudaMemcpyAsync(x_dev + ch.b0 * raw_frame, x_host + ch.b0 * raw_frame, ch.nb * raw_frame * 4,
+                             cudaMemcpyHostToDevice, p->copy_in));
+    GSD_CUDA(cudaEventRecord(p->ev_in[c], p->copy_in));
+    GSD_CUDA(cudaStreamWaitEvent(st, p->ev_in[c], 0));
+    GSD_TRY(run_chunk(p, ch, x_dev, base, pp, y_dev, workspace, packed, st));
+    GSD_CUDA(cudaEventRecord(p->ev_done[c], st));
+    GSD_CUDA(cudaStreamWaitEvent(p->copy_out, p->ev_done[c], 0));
+    GSD_CUDA(cudaMemcpyAsync(y_host + ch.b0 * out_frame, y_dev + ch.b0 * out_frame, ch.nb * out_frame * 4,
+                             cudaMemcpyDeviceToHost, p->copy_out));
+  }
+  GSD_CUDA(cudaStreamSynchronize(p->copy_out));
+  GSD_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int gsd_op_conv_bf16(const void* src0, int C0, const void* src1, int C1, int H1, int W1, int off_y,
+                                int off_x, int B, int H, int W, const void* w, int Cout, int ntaps,
+                                const int8_t* tap_dy, const int8_t* tap_dx, int out_groups, const float* scale,
+                                const float* shift, int relu, void* out, void* pooled, int block_n, int device,
+                                void* stream) {
+  GSD_CHECK(src0 && w && scale && shift && out && tap_dy && tap_dx, "gsd_op_conv_bf16: null argument");
+  GSD_CUDA(cudaSetDevice(device));
+  int sms = 0, major = 0;
+  GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  GSD_CHECK(major == 10, "gsd_op_conv_bf16: device %d is not sm_100 (no fallback)", device);
+  ConvDesc d;
+  d.src0 = src0; d.C0 = C0; d.src1 = src1; d.C1 = src1 ? C1 : 0; d.H1 = H1; d.W1 = W1; d.off_y = off_y; d.off_x = off_x;
+  d.B = B; d.H = H; d.W = W; d.w = w; d.Cout = Cout; d.groups = out_groups; d.ntaps = ntaps;
+  GSD_CHECK(ntaps >= 1 && ntaps <= kMaxTaps, "gsd_op_conv_bf16: ntaps out of range");
+  for (int t = 0; t < ntaps; ++t) { d.dy[t] = tap_dy[t]; d.dx[t] = tap_dx[t]; }
+  d.scale = scale; d.shift = shift; d.relu = relu; d.out = out; d.pooled = pooled; d.block_n = block_n;
+  ConvLaunch L;
+  GSD_TRY(build_conv_launch(d, sms, &L));
+  return run_conv_launch(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gsd_op_image_affine(const float* x, const float* base, int base_batch, int use_diff, int B, int Cc,
+                                   int Hr, int Wr, int H, int W, const float* scale8, const float* shift8, float* out,
+                                   int device, void* stream) {
+  GSD_CHECK(x && out && scale8 && shift8, "gsd_op_image_affine: null argument");
+  GSD_CHECK(!use_diff || base, "gsd_op_image_affine: use_diff without base");
+  GSD_CHECK(B >= 1 && Cc >= 1 && H >= 1 && W >= 1 && Hr >= 1 && Wr >= 1, "gsd_op_image_affine: bad shape");
+  GSD_CUDA(cudaSetDevice(device));
+  PreParams p;
+  p.x = x; p.base = use_diff ? base : nullptr; p.base_batch = base_batch; p.use_diff = use_diff;
+  p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W;
+  for (int c = 0; c < 8; ++c) { p.in_scale[c] = scale8[c]; p.in_shift[c] = shift8[c]; }
+  image_affine_kernel<<<ew_grid((long)B * Cc * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, out);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}

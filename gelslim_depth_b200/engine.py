@@ -1,0 +1,138 @@
+"""Host-side driver of libgsd_b200.so: plan cache, torch-owned workspaces, packed-weight cache.
+
+PyTorch is the allocator and stream provider only; every FLOP happens inside the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def make_prepost(in_channels: int, raw_hw: Tuple[int, int], out_hw: Tuple[int, int], use_diff: bool = False,
+                 base_batch: int = 1, in_scale: Sequence[float] = (1.0,), in_shift: Sequence[float] = (0.0,),
+                 out_scale: float = 1.0, out_shift: float = 0.0) -> _lib.PrePost:
+    pp = _lib.PrePost()
+    pp.use_diff = int(use_diff)
+    pp.base_batch = int(base_batch)
+    pp.raw_height, pp.raw_width = int(raw_hw[0]), int(raw_hw[1])
+    pp.out_height, pp.out_width = int(out_hw[0]), int(out_hw[1])
+    for c in range(8):
+        pp.in_scale[c] = float(in_scale[min(c, len(in_scale) - 1)])
+        pp.in_shift[c] = float(in_shift[min(c, len(in_shift) - 1)])
+    pp.out_scale, pp.out_shift = float(out_scale), float(out_shift)
+    return pp
+
+
+class Plan:
+    """One gsd_plan + the torch tensors that back its workspace."""
+
+    def __init__(self, batch, in_channels, height, width, n_classes, dims, device: torch.device,
+                 dtype=_lib.DTYPE_BF16, mode=_lib.MODE_INFER):
+        g = _lib.Geometry()
+        g.batch, g.in_channels, g.height, g.width, g.n_classes = batch, in_channels, height, width, n_classes
+        g.n_dims = len(dims)
+        for i, d in enumerate(dims):
+            g.dims[i] = int(d)
+        g.dtype, g.mode = dtype, mode
+        self.geometry = g
+        self.device = device
+        self.handle = C.c_void_p()
+        check(lib.gsd_plan_create(C.byref(self.handle), C.byref(g), device.index or 0), "gsd_plan_create")
+        self.workspace = torch.empty(lib.gsd_plan_workspace_bytes(self.handle), dtype=torch.uint8, device=device)
+        self.packed_bytes = lib.gsd_plan_packed_bytes(self.handle)
+
+    def set_chunk(self, frames: int):
+        check(lib.gsd_plan_set_chunk(self.handle, int(frames)), "gsd_plan_set_chunk")
+
+    @property
+    def launches(self) -> int:
+        return lib.gsd_plan_forward_launches(self.handle)
+
+    @property
+    def conv_flops(self) -> float:
+        return lib.gsd_plan_conv_flops(self.handle)
+
+    def pack(self, params, bn_buffers, packed: torch.Tensor):
+        n_p, n_b = lib.gsd_plan_num_params(self.handle), lib.gsd_plan_num_bn_buffers(self.handle)
+        if len(params) != n_p or len(bn_buffers) != n_b:
+            raise ValueError(f"expected {n_p} params / {n_b} BN buffers, got {len(params)} / {len(bn_buffers)}")
+        for t in list(params) + list(bn_buffers):
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("parameters must be contiguous fp32 tensors on the plan's device")
+        pa = (C.c_void_p * n_p)(*[t.data_ptr() for t in params])
+        ba = (C.c_void_p * n_b)(*[t.data_ptr() for t in bn_buffers])
+        check(lib.gsd_pack_weights(self.handle, pa, ba, _ptr(packed), _stream(self.device)), "gsd_pack_weights")
+
+    def forward(self, x, base, pp, y, packed):
+        check(lib.gsd_forward(self.handle, _ptr(x), _ptr(base), C.byref(pp), _ptr(y), _ptr(self.workspace),
+                              _ptr(packed), _stream(self.device)), "gsd_forward")
+
+    def forward_host(self, x_host, base, pp, y_host, x_dev, y_dev, packed):
+        check(lib.gsd_forward_host(self.handle, _ptr(x_host), _ptr(base), C.byref(pp), _ptr(y_host), _ptr(x_dev),
+                                   _ptr(y_dev), _ptr(self.workspace), _ptr(packed), _stream(self.device)),
+              "gsd_forward_host")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.gsd_plan_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+class PlanCache:
+    def __init__(self, capacity: int = 4):
+        self.capacity = capacity
+        self._plans: "OrderedDict[tuple, Plan]" = OrderedDict()
+
+    def get(self, key, factory) -> Plan:
+        if key in self._plans:
+            self._plans.move_to_end(key)
+            return self._plans[key]
+        plan = factory()
+        self._plans[key] = plan
+        while len(self._plans) > self.capacity:
+            self._plans.popitem(last=False)
+        return plan
+
+    def clear(self):
+        self._plans.clear()
+
+
+def conv_op(src0, w, scale, shift, taps, relu=True, src1=None, off=(0, 0), cout=None, groups=1, pool=False,
+            block_n=0):
+    """Single tcgen05 conv (gsd_op_conv_bf16) on NHWC bf16 torch tensors -- used by the parity tests."""
+    B, H, W, C0 = src0.shape
+    dev = src0.device
+    ntaps = len(taps)
+    dy = (C.c_int8 * ntaps)(*[t[0] for t in taps])
+    dx = (C.c_int8 * ntaps)(*[t[1] for t in taps])
+    cout = cout if cout is not None else w.shape[0] // groups
+    if groups == 1:
+        out = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device=dev)
+    else:
+        out = torch.empty(B, 2 * H, 2 * W, cout, dtype=torch.bfloat16, device=dev)
+    pooled = torch.empty(B, H // 2, W // 2, cout, dtype=torch.bfloat16, device=dev) if pool else None
+    C1 = H1 = W1 = 0
+    if src1 is not None:
+        _, H1, W1, C1 = src1.shape
+    check(lib.gsd_op_conv_bf16(_ptr(src0), C0, _ptr(src1), C1, H1, W1, off[0], off[1], B, H, W, _ptr(w), cout, ntaps,
+                               C.cast(dy, C.c_void_p), C.cast(dx, C.c_void_p), groups, _ptr(scale), _ptr(shift),
+                               int(relu), _ptr(out), _ptr(pooled), block_n, dev.index or 0, _stream(dev)),
+          "gsd_op_conv_bf16")
+    return (out, pooled) if pool else out

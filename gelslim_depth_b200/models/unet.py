@@ -1,0 +1,152 @@
+"""Drop-in replacement of gelslim_depth.models.unet.UNet (reference: gelslim_depth/models/unet.py:60-88).
+
+Same constructor, same `forward(x)` keyword, same parameter / buffer names, registration order and
+default initialisation (so `torch.manual_seed(s); UNet(...)` yields the reference's weights and
+`unet_bigdata.pth` loads unchanged) -- but `forward` never touches torch.nn arithmetic: the module
+tree below is only a *parameter container*; the computation is one call into libgsd_b200.so
+(hand-written sm_100a kernels, see csrc/).  There is no CPU or cuDNN fallback: a CPU tensor, an
+unsupported configuration or a missing library raises.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..engine import Plan, PlanCache, make_prepost
+
+_DEFAULT_DIMS = (64, 128, 256, 512, 1024)
+
+
+class _Params(nn.Module):
+    """A node of the parameter tree; it owns sub-modules but is never called."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container -- the computation lives in libgsd_b200.so")
+
+
+def _conv_bn_pair(cin: int, cout: int, k: int) -> nn.Sequential:
+    # indices 0..5 must match nn.Sequential numbering of the reference DoubleConv (unet.py:10-17)
+    layers = []
+    for a, b in ((cin, cout), (cout, cout)):
+        layers += [nn.Conv2d(a, b, kernel_size=k, padding=1, bias=False), nn.BatchNorm2d(b), nn.ReLU(inplace=True)]
+    return nn.Sequential(*layers)
+
+
+def _double_conv(cin: int, cout: int, k: int) -> _Params:
+    node = _Params()
+    node.double_conv = _conv_bn_pair(cin, cout, k)
+    return node
+
+
+class UNet(nn.Module):
+    def __init__(self, n_channels, n_classes, layer_dimensions=list(_DEFAULT_DIMS), kernel_size=3, maxpool_size=2,
+                 upconv_stride=2, bilinear=False):
+        super().__init__()
+        dims = [int(d) for d in layer_dimensions]
+        self._validate(n_channels, n_classes, dims, kernel_size, maxpool_size, upconv_stride)
+        self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear   # unet.py:63-65
+        self.layer_dimensions = dims
+
+        # Construction order == reference (unet.py:67-77) so the default-init RNG stream is identical.
+        self.inc = _double_conv(n_channels, dims[0], kernel_size)
+        self.down = nn.ModuleList()
+        for lo, hi in zip(dims[:-1], dims[1:]):
+            stage = _Params()
+            stage.maxpool_conv = nn.Sequential(nn.MaxPool2d(maxpool_size), _double_conv(lo, hi, kernel_size))
+            self.down.append(stage)
+        self.up = nn.ModuleList()
+        for hi, lo in zip(dims[:0:-1], dims[-2::-1]):
+            stage = _Params()
+            stage.up = nn.ConvTranspose2d(hi, hi // 2, kernel_size=kernel_size - 1, stride=upconv_stride)
+            stage.conv = _double_conv(hi, lo, 3)
+            self.up.append(stage)
+        self.outc = _Params()
+        self.outc.conv = nn.Conv2d(dims[0], n_classes, kernel_size=1)
+
+        self._plans = PlanCache(capacity=4)
+        self._packed = None          # torch.uint8 arena of bf16 GEMM operands + folded BN
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ validation
+    @staticmethod
+    def _validate(n_channels, n_classes, dims, kernel_size, maxpool_size, upconv_stride):
+        problems = []
+        if kernel_size != 3:
+            problems.append("kernel_size must be 3 (padding is fixed at 1 in the reference, unet.py:11)")
+        if maxpool_size != 2 or upconv_stride != 2:
+            problems.append("maxpool_size and upconv_stride must be 2")
+        if not 2 <= len(dims) <= _lib.GSD_MAX_DIMS:
+            problems.append(f"len(layer_dimensions) must be in 2..{_lib.GSD_MAX_DIMS}")
+        if dims and dims[0] != 64:
+            problems.append("layer_dimensions[0] must be 64")
+        if any(b != 2 * a for a, b in zip(dims[:-1], dims[1:])):
+            problems.append("layer_dimensions must double at every level (torch.cat in Up, unet.py:48)")
+        if not 1 <= n_channels <= 8 or not 1 <= n_classes <= 4:
+            problems.append("n_channels must be 1..8 and n_classes 1..4")
+        if problems:
+            raise NotImplementedError("gelslim_depth_b200.UNet: unsupported configuration (no fallback path): "
+                                      + "; ".join(problems))
+
+    # ------------------------------------------------------------------ weights
+    def _bn_buffers(self) -> List[torch.Tensor]:
+        out = []
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                out += [m.running_mean, m.running_var]
+        return out
+
+    def _weights_key(self):
+        ts = list(self.parameters()) + self._bn_buffers()
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def packed_weights(self, plan: Plan) -> torch.Tensor:
+        """bf16 K-major GEMM operands + folded eval-mode BatchNorm; re-packed whenever any parameter or
+        running statistic changed (optimizer.step, ema.average_parameters(), load_state_dict, .to())."""
+        key = self._weights_key()
+        if self._packed is None or self._packed_key != key or self._packed.device != plan.device \
+                or self._packed.numel() != plan.packed_bytes:
+            if self._packed is None or self._packed.device != plan.device or self._packed.numel() != plan.packed_bytes:
+                self._packed = torch.empty(plan.packed_bytes, dtype=torch.uint8, device=plan.device)
+            plan.pack([p.detach() for p in self.parameters()], self._bn_buffers(), self._packed)
+            self._packed_key = key
+        return self._packed
+
+    def plan_for(self, batch: int, height: int, width: int, device: torch.device) -> Plan:
+        key = (batch, height, width, device)
+        return self._plans.get(key, lambda: Plan(batch, self.n_channels, height, width, self.n_classes,
+                                                 self.layer_dimensions, device))
+
+    def _apply(self, fn, *a, **k):          # .to()/.cuda()/.float(): drop device-specific caches
+        self._plans.clear()
+        self._packed, self._packed_key = None, None
+        return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------ forward
+    def run(self, x: torch.Tensor, pp=None, base: torch.Tensor = None, net_hw=None) -> torch.Tensor:
+        """x: fp32 NCHW CUDA tensor.  With `pp` (a gsd_prepost) the difference image, resampling,
+        normalisation and depth de-normalisation are fused around the network."""
+        if not x.is_cuda:
+            raise RuntimeError("gelslim_depth_b200.UNet runs on a B200 only; got a CPU tensor (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != self.n_channels:
+            raise ValueError(f"expected (N, {self.n_channels}, H, W), got {tuple(x.shape)}")
+        if self.training:
+            raise NotImplementedError("train-mode forward (batch-statistics BatchNorm + backward) is not part of "
+                                      "this build yet; call .eval()")
+        x = x.contiguous().float()
+        n, _, h, w = x.shape
+        nh, nw = net_hw if net_hw is not None else (h, w)
+        if pp is None:
+            pp = make_prepost(self.n_channels, (h, w), (h, w))
+        plan = self.plan_for(n, nh, nw, x.device)
+        packed = self.packed_weights(plan)
+        y = torch.empty(n, self.n_classes, pp.out_height, pp.out_width, dtype=torch.float32, device=x.device)
+        if base is not None:
+            base = base.contiguous().float()
+        plan.forward(x, base, pp, y, packed)
+        return y
+
+    def forward(self, x):
+        return self.run(x)

@@ -1,0 +1,145 @@
+/*
+ * gsd_b200.h -- C ABI of libgsd_b200.so, the B200 (sm_100a) implementation of the
+ * gelslim_depth U-Net hot path.
+ *
+ * The reference (MMintLab/gelslim_depth) has NO FFI / plugin interface of its own: the seam is
+ * Python duck typing.  Each entry point below therefore cites the reference
+ * *Python* interface it replaces (paths relative to the reference checkout); the Python-side binding
+ * a maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter name ends in `_host`; PyTorch (or any other allocator) stays the owner of all memory;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, performs
+ *     no allocation and no synchronisation, and is therefore CUDA-graph capturable;
+ *   - return value 0 = success, negative = error (gsd_last_error() gives the message); nothing is
+ *     thrown across the boundary;
+ *   - one plan per (geometry, device); a plan is not thread-safe, distinct plans are.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute call fails.
+ */
+#ifndef GSD_B200_H
+#define GSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSD_ABI_VERSION 1
+#define GSD_MAX_DIMS 8
+
+enum { GSD_DTYPE_BF16 = 0, GSD_DTYPE_FP32 = 1 };
+enum { GSD_MODE_INFER = 0, GSD_MODE_TRAIN = 1 };
+
+/* Geometry of one U-Net instance: the arguments of
+ * gelslim_depth/models/unet.py:61  UNet(n_channels, n_classes, layer_dimensions, kernel_size=3,
+ * maxpool_size=2, upconv_stride=2) plus the tensor shape of `forward(x)` (unet.py:79). */
+typedef struct gsd_geometry {
+  int32_t batch;        /* N of x                                     */
+  int32_t in_channels;  /* n_channels (3 or 6)                        */
+  int32_t height;       /* H of x (network resolution)                */
+  int32_t width;        /* W of x                                     */
+  int32_t n_classes;    /* 1 or 2                                     */
+  int32_t n_dims;       /* len(layer_dimensions), 2..GSD_MAX_DIMS     */
+  int32_t dims[GSD_MAX_DIMS]; /* layer_dimensions, each a multiple of 64 */
+  int32_t dtype;        /* GSD_DTYPE_*: arithmetic of the conv path   */
+  int32_t mode;         /* GSD_MODE_*                                 */
+} gsd_geometry;
+
+/* Pre/post-processing fused around the network, i.e. everything
+ * gelslim_depth/processing_utils/complete_prediction.py:4-10 does besides `model(x=...)`, plus the
+ * caller-side difference image (image_utils.py:6-10):
+ *   x_net[c] = in_scale[c] * area_resample( use_diff ? (raw - base + 255)/2 : raw ) + in_shift[c]
+ *   depth    = area_resample( y_net * out_scale + out_shift )
+ * With raw_height == geometry.height (etc.) the resampling is the identity. */
+typedef struct gsd_prepost {
+  int32_t use_diff;             /* 1: subtract `base` (image_utils.py:7-9)                     */
+  int32_t base_batch;           /* 1 (broadcast) or batch                                       */
+  int32_t raw_height, raw_width;/* size of the raw frames (e.g. 320 x 427)                      */
+  int32_t out_height, out_width;/* `output_size` of predict_depth_from_RGB                     */
+  float in_scale[8];            /* normalize_tactile_image: scale/denominator, per channel      */
+  float in_shift[8];            /*                         -scale*bias/denominator              */
+  float out_scale;              /* denormalize_depth_image: denominator/scale                   */
+  float out_shift;              /*                          bias                                */
+} gsd_prepost;
+
+typedef struct gsd_plan gsd_plan;
+
+int gsd_abi_version(void);
+const char* gsd_last_error(void);
+/* Number of CUDA devices with compute capability 10.x; 0 means every compute call will fail. */
+int gsd_device_count(void);
+
+/* --- plan ------------------------------------------------------------------------------------ */
+/* Replaces: UNet.__init__ (unet.py:61-77) + the implicit shape specialisation of the first call. */
+int gsd_plan_create(gsd_plan** out, const gsd_geometry* g, int device);
+void gsd_plan_destroy(gsd_plan* p);
+/* Bytes of activation workspace / packed weights the caller must allocate (256-byte aligned). */
+size_t gsd_plan_workspace_bytes(const gsd_plan* p);
+size_t gsd_plan_packed_bytes(const gsd_plan* p);
+/* Number of parameter tensors / BatchNorm buffer tensors gsd_pack_weights expects. */
+int gsd_plan_num_params(const gsd_plan* p);
+int gsd_plan_num_bn_buffers(const gsd_plan* p);
+/* Kernel launches one gsd_forward issues (for bench.py's gpu_launches). */
+int gsd_plan_forward_launches(const gsd_plan* p);
+/* Process the batch as independent chunks of `frames_per_chunk` frames (default: the whole batch).
+ * Chunks are what gsd_forward_host pipelines against the host<->device copies. */
+int gsd_plan_set_chunk(gsd_plan* p, int frames_per_chunk);
+/* 2*M*N*K summed over the conv / transposed-conv GEMMs of one gsd_forward (valid after the first
+ * forward); the denominator-free numerator of bench.py's tensor roofline. */
+double gsd_plan_conv_flops(const gsd_plan* p);
+
+/* Replaces: model.load_state_dict / .to(device) on the reference module (test_depth_estimation.py:61-65).
+ * params: fp32 device pointers in nn.Module.parameters() order of the reference UNet
+ *         (inc.double_conv.0.weight, inc.double_conv.1.weight, inc.double_conv.1.bias, ...).
+ * bn_buffers: fp32 device pointers, (running_mean, running_var) per BatchNorm in module order.
+ * Folds eval-mode BatchNorm into a per-channel (scale, shift) applied in the conv epilogue and
+ * re-lays conv weights as K-major bf16 GEMM operands. */
+int gsd_pack_weights(gsd_plan* p, const void* const* params, const void* const* bn_buffers,
+                     void* packed, void* stream);
+
+/* Replaces: UNet.forward (unet.py:79-88) and, with a non-trivial gsd_prepost, the whole of
+ * predict_depth_from_RGB (complete_prediction.py:4-10).
+ * x:    fp32 NCHW (batch, in_channels, raw_height, raw_width)
+ * base: fp32 NCHW (base_batch, in_channels, raw_height, raw_width) or NULL
+ * y:    fp32 NCHW (batch, n_classes, out_height, out_width) */
+int gsd_forward(gsd_plan* p, const float* x, const float* base, const gsd_prepost* pp, float* y,
+                void* workspace, const void* packed, void* stream);
+
+/* Same computation with HOST buffers (pinned or pageable): copies the frames host->device in
+ * `chunk`-frame pieces on a copy stream overlapped with compute, and the depth maps back.
+ * `x_dev`/`y_dev` are caller-owned device staging buffers of the full batch size.
+ * Blocks until y_host is complete. */
+int gsd_forward_host(gsd_plan* p, const float* x_host, const float* base, const gsd_prepost* pp,
+                     float* y_host, float* x_dev, float* y_dev, void* workspace, const void* packed,
+                     void* stream);
+
+/* --- single operators (used by the parity tests; the plan is built from exactly these) ---------- */
+/* conv KxK (taps given explicitly) as implicit GEMM on tcgen05, NHWC bf16.
+ *   src0:(B,H,W,C0) [+ src1:(B,H1,W1,C1) placed at offset (off_y, off_x), zero elsewhere -> virtual
+ *   F.pad + torch.cat of unet.py:43-48];  w: bf16 [Cout_total][ntaps*(C0+C1)] K-major;
+ *   out = relu?(acc*scale[n] + shift[n]) as bf16 NHWC (B,H,W,Cout); optional 2x2 max-pooled copy.
+ *   out_groups == 4 selects the transposed-conv scatter (unet.py:36): w rows are
+ *   [(dy*2+dx)*Cout + co], out is (B,2H,2W,Cout). */
+int gsd_op_conv_bf16(const void* src0, int C0, const void* src1, int C1, int H1, int W1, int off_y,
+                     int off_x, int B, int H, int W, const void* w, int Cout, int ntaps,
+                     const int8_t* tap_dy, const int8_t* tap_dx, int out_groups, const float* scale,
+                     const float* shift, int relu, void* out, void* pooled, int block_n, int device,
+                     void* stream);
+
+/* Stand-alone processing helper: fp32 NCHW -> fp32 NCHW,
+ *   out[:, c] = scale8[min(c,7)] * area_resample(use_diff ? (x - base + 255)/2 : x) + shift8[min(c,7)]
+ * Replaces (when called outside the fused forward): get_difference_image (image_utils.py:6-10),
+ * sample_multi_channel_image_to_desired_size(..., 'area') (image_utils.py:12-15),
+ * normalize_tactile_image / normalize_depth_image / denormalize_depth_image
+ * (normalization_utils.py:4-35, 70-130).  scale8/shift8 are HOST arrays of 8 floats. */
+int gsd_op_image_affine(const float* x, const float* base, int base_batch, int use_diff, int B, int C,
+                        int Hr, int Wr, int H, int W, const float* scale8_host, const float* shift8_host,
+                        float* out, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSD_B200_H */

@@ -1,0 +1,261 @@
+"""GPU parity tests (run with `-m gpu` on a B200): every CUDA path is called through the C ABI and
+compared with the CPU oracle / the reference-generated golden fixtures.
+
+Stated tolerances (bf16 mode): operands are rounded to bf16, products accumulate in fp32 (TMEM) and
+each layer's output is rounded to bf16 once.  Single op vs an fp32 CPU conv on the SAME bf16-rounded
+operands: |err| <= 2^-8 * |y| + 1e-3 (one output rounding).  Whole network (23 layers) vs the fp32
+reference: per-tensor relative L2 <= 2e-2, max-abs depth error <= 5e-2 in network units on
+conditioned O(1) activations."""
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TAPS3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch.device("cuda:0")
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def pack_w3(w, cin_pad=None):
+    """(O,I,3,3) -> bf16 [O][9][Ipad] == csrc/elementwise.cuh pack_conv_weight_kernel"""
+    O, I = w.shape[:2]
+    cin_pad = cin_pad or I
+    out = torch.zeros(O, 9, cin_pad)
+    out[:, :, :I] = w.reshape(O, I, 9).permute(0, 2, 1)
+    return out.reshape(O, 9 * cin_pad).to(torch.bfloat16)
+
+
+def check_close(got, ref, what):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    tol = ref.abs() * 2 ** -8 + 1e-3
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{what}: {bad}/{err.numel()} beyond tolerance, max err {float(err.max()):.4g}, rel_l2 {rel_l2(got, ref):.3g}"
+
+
+@pytest.mark.parametrize("cin,cout,h,w,b,bn", [(64, 64, 19, 23, 2, 0), (64, 128, 16, 32, 1, 128), (128, 64, 9, 150, 1, 64),
+                                               (256, 256, 10, 13, 3, 256), (128, 256, 20, 26, 1, 64), (64, 64, 40, 53, 2, 64)])
+def test_conv3x3_op(cin, cout, h, w, b, bn):
+    from gelslim_depth_b200.engine import conv_op
+    g = torch.Generator().manual_seed(cin * 7 + cout + h)
+    x = bf16r(torch.randn(b, cin, h, w, generator=g))
+    wt = bf16r(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    scale = 0.5 + torch.rand(cout, generator=g)
+    shift = torch.randn(cout, generator=g) * 0.3
+    ref = torch.relu(F.conv2d(x, wt, padding=1) * scale[None, :, None, None] + shift[None, :, None, None])
+    d = dev()
+    out = conv_op(nhwc(x).to(torch.bfloat16).to(d), pack_w3(wt).to(d), scale.to(d), shift.to(d), TAPS3, relu=True, block_n=bn)
+    torch.cuda.synchronize()
+    check_close(out.permute(0, 3, 1, 2), ref, f"conv3x3 {cin}->{cout} {h}x{w}")
+
+
+def test_first_layer_op_padded_channels():
+    from gelslim_depth_b200.engine import conv_op
+    g = torch.Generator().manual_seed(5)
+    for cin in (3, 6):
+        x = bf16r(torch.rand(2, cin, 21, 37, generator=g))
+        wt = bf16r(torch.randn(64, cin, 3, 3, generator=g) * 0.3)
+        ref = torch.relu(F.conv2d(x, wt, padding=1))
+        x16 = torch.zeros(2, 21, 37, 16)
+        x16[..., :cin] = nhwc(x)
+        d = dev()
+        out = conv_op(x16.to(torch.bfloat16).to(d), pack_w3(wt, 16).to(d), torch.ones(64, device=d),
+                      torch.zeros(64, device=d), TAPS3, relu=True)
+        torch.cuda.synchronize()
+        check_close(out.permute(0, 3, 1, 2), ref, f"first layer cin={cin}")
+
+
+@pytest.mark.parametrize("h,w", [(16, 32), (21, 27), (40, 53)])
+def test_conv_with_fused_maxpool(h, w):
+    from gelslim_depth_b200.engine import conv_op
+    g = torch.Generator().manual_seed(h + w)
+    x = bf16r(torch.randn(2, 64, h, w, generator=g))
+    wt = bf16r(torch.randn(128, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5)
+    ref = bf16r(torch.relu(F.conv2d(x, wt, padding=1)))
+    d = dev()
+    out, pooled = conv_op(nhwc(x).to(torch.bfloat16).to(d), pack_w3(wt).to(d), torch.ones(128, device=d),
+                          torch.zeros(128, device=d), TAPS3, relu=True, pool=True)
+    torch.cuda.synchronize()
+    check_close(out.permute(0, 3, 1, 2), ref, "conv before pool")
+    # the pooled tensor must be EXACTLY max_pool2d (floor mode, unet.py:26) of the stored bf16 tensor
+    want = F.max_pool2d(out.permute(0, 3, 1, 2).float().cpu(), 2)
+    assert torch.equal(pooled.permute(0, 3, 1, 2).float().cpu(), want)
+
+
+@pytest.mark.parametrize("hs,ws,h,w", [(5, 6, 10, 13), (10, 13, 20, 26), (8, 8, 17, 17)])
+def test_virtual_concat_with_pad(hs, ws, h, w):
+    """conv over torch.cat([skip, F.pad(up)], 1) without materialising it (unet.py:43-48)."""
+    from gelslim_depth_b200.engine import conv_op
+    g = torch.Generator().manual_seed(hs * 31 + w)
+    skip = bf16r(torch.randn(2, 64, h, w, generator=g))
+    up = bf16r(torch.randn(2, 64, 2 * hs, 2 * ws, generator=g))
+    dy, dx = h - 2 * hs, w - 2 * ws
+    cat = torch.cat([skip, F.pad(up, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])], dim=1)
+    wt = bf16r(torch.randn(64, 128, 3, 3, generator=g) * (2.0 / 1152) ** 0.5)
+    ref = torch.relu(F.conv2d(cat, wt, padding=1))
+    d = dev()
+    out = conv_op(nhwc(skip).to(torch.bfloat16).to(d), pack_w3(wt).to(d), torch.ones(64, device=d), torch.zeros(64, device=d),
+                  TAPS3, relu=True, src1=nhwc(up).to(torch.bfloat16).to(d), off=(dy // 2, dx // 2))
+    torch.cuda.synchronize()
+    check_close(out.permute(0, 3, 1, 2), ref, "virtual concat")
+
+
+@pytest.mark.parametrize("cin,h,w,bn", [(128, 10, 13, 64), (256, 20, 26, 128), (512, 5, 6, 0)])
+def test_transposed_conv_scatter(cin, h, w, bn):
+    """ConvTranspose2d(k=2, s=2) + bias as a GEMM with a strided 4-view TMA scatter (unet.py:36)."""
+    from gelslim_depth_b200.engine import conv_op
+    cout = cin // 2
+    g = torch.Generator().manual_seed(cin + h)
+    x = bf16r(torch.randn(2, cin, h, w, generator=g))
+    wt = bf16r(torch.randn(cin, cout, 2, 2, generator=g) * (1.0 / cin) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.2
+    ref = F.conv_transpose2d(x, wt, bias, stride=2)
+    packed = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin).to(torch.bfloat16)     # [(dy*2+dx)*O + o][I]
+    d = dev()
+    out = conv_op(nhwc(x).to(torch.bfloat16).to(d), packed.to(d), torch.ones(4 * cout, device=d), bias.repeat(4).to(d),
+                  [(0, 0)], relu=False, groups=4, cout=cout, block_n=bn)
+    torch.cuda.synchronize()
+    check_close(out.permute(0, 3, 1, 2), ref, "transposed conv")
+
+
+def build_net(g, device):
+    from gelslim_depth_b200.models.unet import UNet
+    torch.manual_seed(g["module_seed"])
+    net = UNet(g["cin"], g["ncls"], layer_dimensions=g["dims"])
+    init = oracle.conditioned_state_dict if g["init"] == "conditioned" else oracle.trainer_init_state_dict
+    sd = init(net.state_dict(), seed=g["init_seed"])
+    assert oracle.state_dict_digest(sd) == g["digest"]
+    net.load_state_dict(sd)
+    return net.to(device).eval(), sd
+
+
+@pytest.mark.parametrize("tag", ["g2_eval", "g3_eval"])
+def test_unet_forward_vs_reference_golden(golden_full, tag):
+    g = golden_full[tag]
+    net, sd = build_net(g, dev())
+    y = net(x=g["x"].to(dev()))
+    torch.cuda.synchronize()
+    assert y.shape == g["y"].shape and y.dtype == torch.float32
+    ref = g["y"]
+    assert float(ref.std()) > 0.05, "fixture must not be degenerate"
+    assert rel_l2(y, ref) < 2e-2, rel_l2(y, ref)
+    assert float((y.cpu() - ref).abs().max()) < 5e-2 * max(1.0, float(ref.abs().max()))
+
+
+def test_unet_forward_vs_oracle_odd_geometry():
+    """Geometry that exercises floor pooling and the right/bottom zero pad at every level (427-like)."""
+    from gelslim_depth_b200.models.unet import UNet
+    torch.manual_seed(1)
+    net = UNet(6, 2)
+    sd = oracle.conditioned_state_dict(net.state_dict(), seed=3)
+    net.load_state_dict(sd)
+    net = net.to(dev()).eval()
+    x = torch.rand(3, 6, 53, 75, generator=torch.Generator().manual_seed(2))
+    ref = oracle.unet_forward(sd, x)
+    y = net(x=x.to(dev()))
+    assert rel_l2(y, ref) < 2e-2
+    # weight-cache invalidation: in-place parameter update (what Adam / ema.average_parameters() do)
+    with torch.no_grad():
+        net.outc.conv.bias.add_(1.0)
+    y2 = net(x=x.to(dev()))
+    assert torch.allclose(y2, y + 1.0, atol=1e-5)
+
+
+def shipped_cfg(size, tactile_spelling=False):
+    c = types.SimpleNamespace(input_tactile_image_size=size, interp_method="area", norm_scale=0.9,
+                              depth_normalization_method="min_max_to_0_-1",
+                              depth_normalization_parameters=(-1.9180814027786255, 0.0))
+    pre = "tactile" if tactile_spelling else "image"
+    setattr(c, pre + "_normalization_method", "0_255_to_0_1")
+    setattr(c, pre + "_normalization_parameters", None)
+    return c
+
+
+@pytest.mark.parametrize("spelling", [False, True])
+def test_predict_depth_pipeline_g3(spelling):
+    """predict_depth_from_RGB with area down/up-sampling (G3 pipeline, complete_prediction.py:4-10)."""
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.processing_utils.complete_prediction import predict_depth_from_RGB, predict_depth_from_frames
+    torch.manual_seed(4)
+    net = UNet(3, 1)
+    sd = oracle.conditioned_state_dict(net.state_dict(), seed=8)
+    net.load_state_dict(sd)
+    net = net.to(dev()).eval()
+    g = torch.Generator().manual_seed(6)
+    raw = torch.randint(0, 256, (2, 6, 64, 85), generator=g).float()
+    base = torch.randint(0, 256, (1, 6, 64, 85), generator=g).float()
+    cfg = shipped_cfg((32, 43), spelling)
+    fingers = oracle.split_fingers(oracle.get_difference_image(raw, base))
+    ref = oracle.predict_depth_from_RGB(fingers, lambda t: oracle.unet_forward(sd, t), (64, 85), cfg)
+    got = predict_depth_from_RGB(fingers.to(dev()), net, (64, 85), cfg)
+    assert got.shape == ref.shape
+    scale_mm = 1.9180814027786255 / 0.9
+    assert float((got.cpu() - ref).abs().max()) < 5e-2 * scale_mm * max(1.0, float((ref / scale_mm).abs().max()))
+    assert rel_l2(got, ref) < 2e-2
+    # raw frames + base: difference image fused too (Left finger = channels 0:3)
+    got2 = predict_depth_from_frames(raw[:, 0:3].contiguous().to(dev()), base[:, 0:3].contiguous().to(dev()), net, (64, 85), cfg)
+    assert rel_l2(got2, ref[:2]) < 2e-2
+
+
+def test_processing_helpers_vs_golden(golden_processing):
+    from gelslim_depth_b200.processing_utils import image_utils, normalization_utils
+    p = golden_processing
+    d = dev()
+    diff = image_utils.get_difference_image(p["raw"].to(d), p["base"].to(d))
+    assert torch.equal(diff.cpu(), p["diff"])
+    g = torch.Generator().manual_seed(9)
+    torch.randint(0, 256, (2, 6, 64, 85), generator=g)
+    torch.randint(0, 256, (1, 6, 64, 85), generator=g)
+    img = torch.rand(1, 1, 320, 427, generator=g)
+    down = image_utils.sample_multi_channel_image_to_desired_size(img.to(d), (160, 213), "area")
+    assert torch.allclose(down.cpu(), p["area_down"], rtol=1e-5, atol=1e-6)
+    p4 = ([1.0, 2.0, 3.0], [200.0, 210.0, 220.0], [100.0, 110.0, 120.0], [50.0, 60.0, 70.0])
+    for m in ("mean_std", "0_255_to_-1_1", "0_255_to_0_1"):
+        got = normalization_utils.normalize_tactile_image(p["norm_in"].to(d), m, 0.9, p4)
+        assert torch.allclose(got.cpu(), p["norm_img_" + m], rtol=1e-5, atol=1e-5), m
+    dp = (-1.9180814027786255, 0.0, -0.4, 0.3)
+    for m in ("min_max_to_-1_1", "mean_std", "min_max_to_0_1", "min_max_to_0_-1"):
+        got = normalization_utils.denormalize_depth_image(p["depth_in"].to(d), m, 0.9, dp)
+        assert torch.allclose(got.cpu(), p["denorm_depth_" + m], rtol=1e-5, atol=1e-5), m
+        got = normalization_utils.normalize_depth_image(p["depth_in"].to(d), m, 0.9, dp)
+        assert torch.allclose(got.cpu(), p["norm_depth_" + m], rtol=1e-5, atol=1e-5), m
+
+
+def test_forward_host_pipelined_matches_device_path():
+    import ctypes as C
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.engine import make_prepost
+    torch.manual_seed(2)
+    net = UNet(6, 2)
+    net.load_state_dict(oracle.conditioned_state_dict(net.state_dict(), seed=1))
+    net = net.to(dev()).eval()
+    x = torch.rand(5, 6, 32, 43, generator=torch.Generator().manual_seed(3))
+    y_ref = net(x=x.to(dev())).cpu()
+    plan = net.plan_for(5, 32, 43, dev())
+    plan.set_chunk(2)
+    pp = make_prepost(6, (32, 43), (32, 43))
+    xh, yh = x.pin_memory(), torch.empty(5, 2, 32, 43).pin_memory()
+    xd, yd = torch.empty_like(x, device=dev()), torch.empty(5, 2, 32, 43, device=dev())
+    plan.forward_host(xh, None, pp, yh, xd, yd, net.packed_weights(plan))
+    assert torch.equal(yh, y_ref)
