@@ -3,7 +3,7 @@ compared with the CPU oracle / the reference-generated golden fixtures.
 
 Stated tolerances (bf16 mode): operands are rounded to bf16, products accumulate in fp32 (TMEM) and
 each layer's output is rounded to bf16 once.  Single op vs an fp32 CPU conv on the SAME bf16-rounded
-operands: |err| <= 2^-8 * |y| + 1e-3 (one output rounding).  Whole network (23 layers) vs the fp32
+operands: |err| <= 2^-7 * |y| + 1e-3 (one bf16 ulp: fp32 summation order can flip the output rounding).  Whole network (23 layers) vs the fp32
 reference: per-tensor relative L2 <= 2e-2, max-abs depth error <= 5e-2 in network units on
 conditioned O(1) activations."""
 import types
@@ -49,7 +49,7 @@ def pack_w3(w, cin_pad=None):
 def check_close(got, ref, what):
     got, ref = got.float().cpu(), ref.float().cpu()
     err = (got - ref).abs()
-    tol = ref.abs() * 2 ** -8 + 1e-3
+    tol = ref.abs() * 2 ** -7 + 1e-3
     bad = int((err > tol).sum())
     assert bad == 0, f"{what}: {bad}/{err.numel()} beyond tolerance, max err {float(err.max()):.4g}, rel_l2 {rel_l2(got, ref):.3g}"
 
