@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- U-Net frames/s @6x320x427 (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference algorithm on the host CPU cores
+
+A "step" is one pass of the hot path (gsd_forward: input prologue -> 22 tcgen05 conv GEMMs -> 1x1 head)
+over one batch of synthetic frame pairs.  Workload at every N: BASELINE.json configs[1] -- UNet(6,2),
+bf16, batch 64 frames of 6x320x427 PER GPU (weak scaling; inference shards by frame with no collective).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, CIN, NCLS = 320, 427, 6, 2
+GFLOP_PER_FRAME = 200.117          # 2*MAC over the 23 conv / transposed-conv layers (G2)
+DIMS = [64, 128, 256, 512, 1024]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1386.1), d.get("bf16_tflops", 1634.5), d.get("hbm_gbs", 6541.5), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_frames(torch, batch, seed):
+    """raw = randint(0,256) frames, base = randint(0,256) undeformed image."""
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.randint(0, 256, (batch, CIN, H, W), generator=g, dtype=torch.uint8).float()
+    base = torch.randint(0, 256, (1, CIN, H, W), generator=torch.Generator().manual_seed(1), dtype=torch.uint8).float()
+    return raw, base
+
+
+def cpu_reference_fps(torch, seconds_budget=20.0, max_iters=8, threads=None):
+    """The reference algorithm (oracle port of gelslim_depth UNet.forward + get_difference_image +
+    normalisation) on the host cores, fp32, on a bounded sample: single 6x320x427 frame pairs."""
+    import oracle
+    from gelslim_depth_b200.models.unet import UNet
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in UNet(CIN, NCLS, layer_dimensions=DIMS).state_dict().items()}
+    raw, base = synthetic_frames(torch, 1, 0)
+    times = []
+    t_all = time.perf_counter()
+    with torch.no_grad():
+        for i in range(max_iters + 1):
+            t0 = time.perf_counter()
+            x = oracle.normalize_tactile_image(oracle.get_difference_image(raw, base), "0_255_to_0_1", 0.9, None)
+            y = oracle.unet_forward(sd, x)
+            y = oracle.denormalize_depth_image(y, "min_max_to_0_-1", 0.9, (-1.9180814027786255, 0.0))
+            dt = time.perf_counter() - t0
+            if i > 0:                       # first call = warm-up (oneDNN primitive creation)
+                times.append(dt)
+            if time.perf_counter() - t_all > seconds_budget and len(times) >= 2:
+                break
+    med = statistics.median(times)
+    return 1.0 / med, threads, f"{len(times)} single-frame (1x6x320x427) fp32 forwards of the oracle port, median {med:.3f} s, 1 warm-up"
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    import oracle
+    from gelslim_depth_b200.models.unet import UNet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in UNet(CIN, NCLS, layer_dimensions=DIMS).state_dict().items()}
+    raw, base = synthetic_frames(torch, 1, 0)
+
+    def step():
+        with torch.no_grad():
+            x = oracle.normalize_tactile_image(oracle.get_difference_image(raw, base), "0_255_to_0_1", 0.9, None)
+            y = oracle.unet_forward(sd, x)
+            return oracle.denormalize_depth_image(y, "min_max_to_0_-1", 0.9, (-1.9180814027786255, 0.0))
+
+    for _ in range(args.warmup):
+        step()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t1
+    fps = args.steps / dt
+    sample = f"each step = ONE 6x320x427 frame pair (bounded sample of the batch-64 workload), fp32, {threads} host threads"
+    line = {"impl": "reference", "metric": "unet_frames_per_s_6x320x427", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: UNet(6,2) inference 6x320x427, batch 64 per GPU (reference arm: 1-frame sample per step)",
+                       "geometry": "G2"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per pipelined chunk of the host path (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="print the per-launch table to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.engine import make_prepost
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    torch.manual_seed(0)
+    net = UNet(CIN, NCLS, layer_dimensions=DIMS).to(dev).eval()      # random init (no checkpoints offline)
+    raw, base = synthetic_frames(torch, B, seed=rank)
+    raw_h = raw.pin_memory()
+    x_dev, base_dev = raw.to(dev), base.to(dev)
+    y_dev = torch.empty(B, NCLS, H, W, device=dev)
+    y_host = torch.empty(B, NCLS, H, W).pin_memory()
+    # get_difference_image + '0_255_to_0_1' + 'min_max_to_0_-1' (config_unet_bigdata.py:39-43) fused around the net
+    pp = make_prepost(CIN, (H, W), (H, W), use_diff=True, base_batch=1, in_scale=[1 / 255.0], in_shift=[0.0],
+                      out_scale=1.9180814027786255 / -0.9, out_shift=-1.9180814027786255)
+    plan = net.plan_for(B, H, W, dev)
+    packed = net.packed_weights(plan)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput (value)
+    for _ in range(args.warmup):
+        plan.forward(x_dev, base_dev, pp, y_dev, packed)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        plan.forward(x_dev, base_dev, pp, y_dev, packed)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---------------- end to end through the C ABI with HOST buffers (e2e)
+    chunk = args.chunk or max(1, B // 8)
+    plan.set_chunk(chunk)
+    for _ in range(2):
+        plan.forward_host(raw_h, base_dev, pp, y_host, x_dev, y_dev, packed)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        plan.forward_host(raw_h, base_dev, pp, y_host, x_dev, y_dev, packed)   # blocks until y_host is complete
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)     # forward_host blocks until the last D2H landed, so the events bracket it all
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t)
+    e2e = world * B * e2e_steps / (e2e_ms / 1e3)
+    plan.set_chunk(B)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- live roofline of the dominant kernel (conv_tc_kernel) + per-launch table
+    sustained, burst, hbm, src = measured_peaks()
+    prof = None
+    for _ in range(3):
+        prof = plan.forward_profiled(x_dev, base_dev, pp, y_dev, packed)
+    conv_ms = sum(m for m, f in prof if f > 0)
+    conv_flops = sum(f for m, f in prof if f > 0)
+    other_ms = sum(m for m, f in prof if f == 0)
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    names = ["prologue"] + ["inc.0", "inc.3"] + [f"down.{i}.{j}" for i in range(4) for j in (0, 3)] + \
+            [f"up.{i}.{n}" for i in range(4) for n in ("up", "conv.0", "conv.3")] + ["head"]
+    table = [{"launch": n, "ms": round(m, 4), "tflops": round(f / (m * 1e-3) / 1e12, 1) if f else None}
+             for n, (m, f) in zip(names, prof)]
+    if args.layers:
+        for r in table:
+            print(r, file=sys.stderr)
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (22 launches/step: 18 conv3x3 + 4 convT as implicit GEMM)",
+                "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
+                "frac_of_burst": achieved / burst, "traffic": None,
+                "conv_share_of_step": conv_ms / (conv_ms + other_ms),
+                "flops_per_launch_set": conv_flops, "algorithmic_gflop_per_frame": GFLOP_PER_FRAME}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        fps, cores, sample = cpu_reference_fps(torch)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+
+    line = {"metric": "unet_frames_per_s_6x320x427", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: UNet(6,2) inference bf16, batch 64 frames of 6x320x427 per GPU, "
+                                   "difference image + normalisation + depth de-normalisation fused",
+                       "geometry": "G2", "batch_per_gpu": B, "l2": "inputs_larger_than_l2 (210 MB frames, 22 GB activations per step)",
+                       "weights": "random init seed 0"},
+            "tensor_frac_whole_step": value / world * GFLOP_PER_FRAME / 1e3 / sustained,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * CIN * H * W * 4,
+                    "d2h_bytes_per_step": B * NCLS * H * W * 4, "steps": e2e_steps, "chunk_frames": chunk,
+                    "api": "gsd_forward_host (pinned fp32 frames in, fp32 depth maps out, copies inside the timed region)"},
+            "gpu_launches": plan.launches * args.steps, "clocks": clocks, "layers": table}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

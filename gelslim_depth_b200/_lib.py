@@ -47,10 +47,16 @@ SYMBOLS = {
                               C.c_void_p, C.c_void_p]),
     "gsd_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsd_forward_profiled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int,
+                                       C.POINTER(C.c_int)]),
     "gsd_op_conv_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p]),
+    "gsd_op_conv3x3_halo_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gsd_op_image_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p,
                                       C.c_int, C.c_void_p]),

@@ -1,5 +1,6 @@
 // Host side of the tcgen05 conv: tile-shape / BN selection, tensor-map construction, launch.
 #pragma once
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_tc.cuh"
@@ -32,6 +33,10 @@ struct ConvLaunch {
 
 inline void pick_tile(int H, int W, bool pool, int* th, int* tw) {
   static const int cand[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
+  if (const char* e = getenv("GSD_FORCE_TILE")) {   // tuning experiments only: "THxTW"
+    int a = 0, b = 0;
+    if (sscanf(e, "%dx%d", &a, &b) == 2 && a * b == 128 && !(pool && ((a | b) & 1))) { *th = a; *tw = b; return; }
+  }
   long best = -1;
   for (auto& c : cand) {
     if (pool && (c[0] & 1)) continue;
@@ -164,6 +169,115 @@ inline int run_conv_launch(const ConvLaunch& L, cudaStream_t st) {
     case 256: return launch_conv_cfg<256, 128>(L, st);
   }
   return fail(-1, "conv: no kernel for block_n %d", L.bn);
+}
+
+}  // namespace gsd
+
+// ------------------------------------------------------------------------------------------------
+// Halo kernel (conv_halo.cuh) host side
+#include "conv_halo.cuh"
+
+namespace gsd {
+
+struct HaloLaunch {
+  HaloParams p;
+  int bn = 0, mt = 0, wres = 0, grid = 0, smem = 0;
+  double flops = 0;
+};
+
+// fraction of MMA rows that are real pixels with 16x8 tiles
+inline double halo_tile_efficiency(int H, int W) {
+  return (double)H * W / ((double)((H + 15) / 16) * 16 * ((W + 7) / 8) * 8);
+}
+
+inline bool halo_supported(const ConvDesc& d) {
+  if (d.ntaps != 9 || d.groups != 1) return false;
+  if (d.C0 % 64 || d.C1 % 64 || d.Cout % 64 || d.Cout > 1024) return false;
+  if (d.Cout != 64 && d.Cout % 128) return false;
+  for (int t = 0; t < 9; ++t)
+    if (d.dy[t] != t / 3 - 1 || d.dx[t] != t % 3 - 1) return false;
+  return true;
+}
+
+inline int build_halo_launch(const ConvDesc& d, int num_sms, int base_off_mode, HaloLaunch* L) {
+  memset(L, 0, sizeof *L);
+  GSD_CHECK(halo_supported(d), "halo conv: unsupported shape (C0=%d C1=%d Cout=%d taps=%d groups=%d)", d.C0, d.C1, d.Cout,
+            d.ntaps, d.groups);
+  HaloParams& p = L->p;
+  p.cb0 = d.C0 / 64; p.cb1 = d.C1 / 64;
+  const int cbt = p.cb0 + p.cb1;
+  p.off_x = d.off_x; p.off_y = d.off_y;
+  p.tiles_x = (d.W + 7) / 8; p.tiles_y = (d.H + 15) / 16; p.batch = d.B;
+  p.H = d.H; p.W = d.W; p.Cout = d.Cout;
+  p.scale = d.scale; p.shift = d.shift; p.relu = d.relu;
+  p.out = static_cast<__nv_bfloat16*>(d.out);
+  p.pooled = static_cast<__nv_bfloat16*>(d.pooled);
+  p.base_off_mode = base_off_mode;
+  const int budget = 227 * 1024 - 1024;
+  const int aux = 2 * d.Cout * 4 + 512;
+  int bn, mt, wres;
+  if (d.Cout == 64 && 9 * cbt * 64 * 128 <= 150 * 1024) { bn = 64; mt = 1; wres = 1; }
+  else if (d.Cout == 128 && cbt == 1) { bn = 128; mt = 1; wres = 1; }
+  else if (d.Cout == 64) { bn = 64; mt = 2; wres = 0; }
+  else { bn = 128; mt = 2; wres = 0; }
+  if (d.block_n == 64 && d.Cout % 64 == 0 && !wres) bn = 64;
+  const int b_bytes = bn * 128;
+  if (wres) {
+    p.nb = 0;
+    p.na = (budget - aux - 9 * cbt * b_bytes) / kHaloBufBytes;
+    if (p.na > 6) p.na = 6;
+    GSD_CHECK(p.na >= 2, "halo conv: resident weights leave no room for the halo ring");
+    L->smem = p.na * kHaloBufBytes + 9 * cbt * b_bytes + aux + 1024;
+  } else {
+    p.na = 4;
+    p.nb = (budget - aux - p.na * kHaloBufBytes) / b_bytes;
+    if (p.nb > 9) p.nb = 9;
+    GSD_CHECK(p.nb >= 3, "halo conv: no room for the weight ring");
+    L->smem = p.na * kHaloBufBytes + p.nb * b_bytes + aux + 1024;
+  }
+  p.n_tiles = d.Cout / bn;
+  L->bn = bn; L->mt = mt; L->wres = wres;
+  auto src_map = [&](CUtensorMap* m, const void* base, int C, int H, int W) -> int {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)d.B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {64, 10, 18, 1};
+    return encode_bf16_map(m, const_cast<void*>(base), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false);
+  };
+  GSD_TRY(src_map(&p.tm_src0, d.src0, d.C0, d.H, d.W));
+  if (d.C1) GSD_TRY(src_map(&p.tm_src1, d.src1, d.C1, d.H1, d.W1));
+  else p.tm_src1 = p.tm_src0;
+  {
+    const uint64_t ktot = 9ull * (d.C0 + d.C1);
+    uint64_t dims[2] = {ktot, (uint64_t)d.Cout};
+    uint64_t str[1] = {ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    GSD_TRY(encode_bf16_map(&p.tm_w, const_cast<void*>(d.w), 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  const long m_tiles = (long)p.tiles_x * p.tiles_y * d.B;
+  const long items = ((m_tiles + mt - 1) / mt) * p.n_tiles;
+  L->grid = (int)(items < num_sms ? items : num_sms);
+  L->flops = 2.0 * d.B * d.H * d.W * (double)d.Cout * 9 * (d.C0 + d.C1);
+  return 0;
+}
+
+template <int BN, int MT, bool WRES>
+inline int launch_halo_cfg(const HaloLaunch& L, cudaStream_t st) {
+  static int attr_smem = 0;
+  if (attr_smem < L.smem) {
+    GSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
+    attr_smem = L.smem;
+  }
+  conv_halo_kernel<BN, MT, WRES><<<L.grid, kHaloThreads, L.smem, st>>>(L.p);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+inline int run_halo_launch(const HaloLaunch& L, cudaStream_t st) {
+  if (L.bn == 64 && L.mt == 1 && L.wres) return launch_halo_cfg<64, 1, true>(L, st);
+  if (L.bn == 128 && L.mt == 1 && L.wres) return launch_halo_cfg<128, 1, true>(L, st);
+  if (L.bn == 64 && L.mt == 2 && !L.wres) return launch_halo_cfg<64, 2, false>(L, st);
+  if (L.bn == 128 && L.mt == 2 && !L.wres) return launch_halo_cfg<128, 2, false>(L, st);
+  return fail(-1, "halo conv: no kernel for bn=%d mt=%d wres=%d", L.bn, L.mt, L.wres);
 }
 
 }  // namespace gsd

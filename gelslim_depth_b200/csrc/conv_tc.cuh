@@ -166,33 +166,35 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+    // ===================================================== MMA issuer (warp converged; one elected lane issues)
+    constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
+    constexpr uint32_t desc_hi = ((8u * BKB) >> 4) | (1u << 14) | ((BKB == 128 ? 2u : 6u) << 29);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t sa = s_stage + stage * Cfg::STAGE_BYTES;
-          const uint64_t a_desc = make_kmajor_desc<BKB>(sa);
-          const uint64_t b_desc = make_kmajor_desc<BKB>(sa + Cfg::A_BYTES);
+        const uint32_t sa = s_stage + stage * Cfg::STAGE_BYTES;
+        const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo = (((sa + Cfg::A_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < KSTEPS; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle span: +2 in the >>4 address field
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (k != 0) ? 1u : (uint32_t)(kb != 0));
           }
           umma_commit(bar_empty + 8 * stage);   // frees the smem stage once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) umma_commit(bar_acc_full + 8 * acc);
         }
-        umma_commit(bar_acc_full + 8 * acc);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {

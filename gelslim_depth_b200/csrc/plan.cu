@@ -15,9 +15,16 @@ struct ConvW {          // one packed conv3x3 (or the 2x2 transposed conv)
   int cin = 0, cin_pad = 0, cout = 0, taps = 0;
 };
 
+struct AnyLaunch {      // one GEMM launch of the network: tap-streaming kernel or halo-resident kernel
+  int halo = 0;
+  ConvLaunch tc;
+  HaloLaunch hl;
+  double flops = 0;
+};
+
 struct ChunkLaunches {
   int b0 = 0, nb = 0;
-  std::vector<ConvLaunch> convs;
+  std::vector<AnyLaunch> convs;
 };
 
 }  // namespace
@@ -247,10 +254,18 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       return static_cast<void*>(W + off + (size_t)b0 * l_h * l_w * c * 2);
     };
     auto add = [&](ConvDesc& d) -> int {
-      ConvLaunch L;
-      GSD_TRY(build_conv_launch(d, p->num_sms, &L));
-      p->conv_flops += L.flops;
-      ch.convs.push_back(L);
+      AnyLaunch A;
+      // halo-resident kernel wherever its fixed 16x8 tiling wastes < 25 % of the MMA rows
+      if (!getenv("GSD_NO_HALO") && halo_supported(d) && halo_tile_efficiency(d.H, d.W) >= 0.75) {
+        A.halo = 1;
+        GSD_TRY(build_halo_launch(d, p->num_sms, 0, &A.hl));
+        A.flops = A.hl.flops;
+      } else {
+        GSD_TRY(build_conv_launch(d, p->num_sms, &A.tc));
+        A.flops = A.tc.flops;
+      }
+      p->conv_flops += A.flops;
+      ch.convs.push_back(A);
       return 0;
     };
     // encoder
@@ -333,7 +348,17 @@ static int check_prepost(const gsd_plan* p, const gsd_prepost* pp, const float* 
 
 // one chunk of frames through the whole network on `st`
 static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const float* base, const gsd_prepost* pp,
-                     float* y, void* ws, const void* packed, cudaStream_t st) {
+                     float* y, void* ws, const void* packed, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
+  auto mark = [&]() -> int {
+    if (evs) {
+      cudaEvent_t e;
+      GSD_CUDA(cudaEventCreate(&e));
+      GSD_CUDA(cudaEventRecord(e, st));
+      evs->push_back(e);
+    }
+    return 0;
+  };
+  GSD_TRY(mark());
   const gsd_geometry& g = p->g;
   char* W = static_cast<char*>(ws);
   const char* P = static_cast<const char*>(packed);
@@ -348,7 +373,12 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const
   __nv_bfloat16* in16 = reinterpret_cast<__nv_bfloat16*>(W + p->in16_off + (size_t)ch.b0 * g.height * g.width * 16 * 2);
   prologue_kernel<<<ew_grid((long)ch.nb * g.height * g.width), 256, 0, st>>>(pre, in16);
   GSD_CUDA(cudaGetLastError());
-  for (const ConvLaunch& L : ch.convs) GSD_TRY(run_conv_launch(L, st));
+  GSD_TRY(mark());
+  for (const AnyLaunch& L : ch.convs) {
+    if (L.halo) GSD_TRY(run_halo_launch(L.hl, st));
+    else GSD_TRY(run_conv_launch(L.tc, st));
+    GSD_TRY(mark());
+  }
   // head
   const long npix = (long)g.height * g.width;
   const __nv_bfloat16* last = reinterpret_cast<const __nv_bfloat16*>(W + p->db_off[p->depth - 1] + (size_t)ch.b0 * npix * 64 * 2);
@@ -366,6 +396,7 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const
         y + (size_t)ch.b0 * g.n_classes * opix);
     GSD_CUDA(cudaGetLastError());
   }
+  GSD_TRY(mark());
   return 0;
 }
 
@@ -460,4 +491,55 @@ extern "C" int gsd_op_image_affine(const float* x, const float* base, int base_b
   image_affine_kernel<<<ew_grid((long)B * Cc * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, out);
   GSD_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Instrumented forward: CUDA events between consecutive launches of chunk 0.. (bench.py's live roofline).
+// ms_host[i] = duration of launch i (prologue, convs in network order, head[+resample]) summed over chunks;
+// flops_host[i] = 2*M*N*K of that launch (0 for the memory-bound ones).  Synchronises the stream.
+extern "C" int gsd_forward_profiled(gsd_plan* p, const float* x, const float* base, const gsd_prepost* pp, float* y,
+                                    void* workspace, const void* packed, void* stream, float* ms_host,
+                                    double* flops_host, int capacity, int* n_out) {
+  GSD_CHECK(p && x && y && workspace && packed && ms_host && flops_host && n_out, "gsd_forward_profiled: null argument");
+  GSD_TRY(check_prepost(p, pp, base));
+  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_TRY(bind(p, workspace, packed));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int per_chunk = (int)p->chunks[0].convs.size() + 2;
+  GSD_CHECK(capacity >= per_chunk, "gsd_forward_profiled: capacity %d < %d", capacity, per_chunk);
+  for (int i = 0; i < per_chunk; ++i) { ms_host[i] = 0.f; flops_host[i] = 0.0; }
+  for (const ChunkLaunches& ch : p->chunks) {
+    std::vector<cudaEvent_t> evs;
+    GSD_TRY(run_chunk(p, ch, x, base, pp, y, workspace, packed, st, &evs));
+    GSD_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i + 1 < (int)evs.size() && i < per_chunk; ++i) {
+      float ms = 0.f;
+      GSD_CUDA(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+      ms_host[i] += ms;
+      if (i >= 1 && i - 1 < (int)ch.convs.size()) flops_host[i] += ch.convs[i - 1].flops;
+    }
+    for (auto e : evs) cudaEventDestroy(e);
+  }
+  *n_out = per_chunk;
+  return 0;
+}
+
+// conv3x3 (pad 1) through the halo kernel (conv_halo.cuh); same tensor conventions as gsd_op_conv_bf16.
+extern "C" int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* src1, int C1, int H1, int W1, int off_y,
+                                        int off_x, int B, int H, int W, const void* w, int Cout, const float* scale,
+                                        const float* shift, int relu, void* out, void* pooled, int block_n,
+                                        int base_off_mode, int device, void* stream) {
+  GSD_CHECK(src0 && w && scale && shift && out, "gsd_op_conv3x3_halo_bf16: null argument");
+  GSD_CUDA(cudaSetDevice(device));
+  int sms = 0, major = 0;
+  GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  GSD_CHECK(major == 10, "gsd_op_conv3x3_halo_bf16: device %d is not sm_100 (no fallback)", device);
+  ConvDesc d;
+  d.src0 = src0; d.C0 = C0; d.src1 = src1; d.C1 = src1 ? C1 : 0; d.H1 = H1; d.W1 = W1; d.off_y = off_y; d.off_x = off_x;
+  d.B = B; d.H = H; d.W = W; d.w = w; d.Cout = Cout; d.groups = 1;
+  taps3x3(&d);
+  d.scale = scale; d.shift = shift; d.relu = relu; d.out = out; d.pooled = pooled; d.block_n = block_n;
+  HaloLaunch L;
+  GSD_TRY(build_halo_launch(d, sms, base_off_mode, &L));
+  return run_halo_launch(L, static_cast<cudaStream_t>(stream));
 }

@@ -81,6 +81,17 @@ class Plan:
         check(lib.gsd_forward(self.handle, _ptr(x), _ptr(base), C.byref(pp), _ptr(y), _ptr(self.workspace),
                               _ptr(packed), _stream(self.device)), "gsd_forward")
 
+    def forward_profiled(self, x, base, pp, y, packed):
+        """-> list of (ms, flops) per launch in network order (prologue, convs..., head)."""
+        cap = 64
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        n = C.c_int(0)
+        check(lib.gsd_forward_profiled(self.handle, _ptr(x), _ptr(base), C.byref(pp), _ptr(y), _ptr(self.workspace),
+                                       _ptr(packed), _stream(self.device), ms, fl, cap, C.byref(n)),
+              "gsd_forward_profiled")
+        return [(ms[i], fl[i]) for i in range(n.value)]
+
     def forward_host(self, x_host, base, pp, y_host, x_dev, y_dev, packed):
         check(lib.gsd_forward_host(self.handle, _ptr(x_host), _ptr(base), C.byref(pp), _ptr(y_host), _ptr(x_dev),
                                    _ptr(y_dev), _ptr(self.workspace), _ptr(packed), _stream(self.device)),
@@ -135,4 +146,20 @@ def conv_op(src0, w, scale, shift, taps, relu=True, src1=None, off=(0, 0), cout=
                                C.cast(dy, C.c_void_p), C.cast(dx, C.c_void_p), groups, _ptr(scale), _ptr(shift),
                                int(relu), _ptr(out), _ptr(pooled), block_n, dev.index or 0, _stream(dev)),
           "gsd_op_conv_bf16")
+    return (out, pooled) if pool else out
+
+
+def conv3x3_halo_op(src0, w, scale, shift, relu=True, src1=None, off=(0, 0), pool=False, block_n=0, base_off_mode=0):
+    """conv3x3 through the halo-resident kernel (gsd_op_conv3x3_halo_bf16); NHWC bf16 torch tensors."""
+    B, H, W, C0 = src0.shape
+    dev = src0.device
+    cout = w.shape[0]
+    out = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device=dev)
+    pooled = torch.empty(B, H // 2, W // 2, cout, dtype=torch.bfloat16, device=dev) if pool else None
+    C1 = H1 = W1 = 0
+    if src1 is not None:
+        _, H1, W1, C1 = src1.shape
+    check(lib.gsd_op_conv3x3_halo_bf16(_ptr(src0), C0, _ptr(src1), C1, H1, W1, off[0], off[1], B, H, W, _ptr(w), cout,
+                                       _ptr(scale), _ptr(shift), int(relu), _ptr(out), _ptr(pooled), block_n,
+                                       base_off_mode, dev.index or 0, _stream(dev)), "gsd_op_conv3x3_halo_bf16")
     return (out, pooled) if pool else out

@@ -116,6 +116,14 @@ int gsd_forward_host(gsd_plan* p, const float* x_host, const float* base, const 
                      float* y_host, float* x_dev, float* y_dev, void* workspace, const void* packed,
                      void* stream);
 
+/* gsd_forward with CUDA events recorded between consecutive launches (synchronises `stream`):
+ * ms_host[i] / flops_host[i] = device time and 2*M*N*K of launch i in network order (index 0 = input
+ * prologue, 1..n-2 = conv / transposed-conv GEMMs, n-1 = 1x1 head [+ area resample]).  Measurement aid
+ * for bench.py's live roofline; not on the product path. */
+int gsd_forward_profiled(gsd_plan* p, const float* x, const float* base, const gsd_prepost* pp, float* y,
+                         void* workspace, const void* packed, void* stream, float* ms_host,
+                         double* flops_host, int capacity, int* n_out);
+
 /* --- single operators (used by the parity tests; the plan is built from exactly these) ---------- */
 /* conv KxK (taps given explicitly) as implicit GEMM on tcgen05, NHWC bf16.
  *   src0:(B,H,W,C0) [+ src1:(B,H1,W1,C1) placed at offset (off_y, off_x), zero elsewhere -> virtual
@@ -128,6 +136,14 @@ int gsd_op_conv_bf16(const void* src0, int C0, const void* src1, int C1, int H1,
                      const int8_t* tap_dy, const int8_t* tap_dx, int out_groups, const float* scale,
                      const float* shift, int relu, void* out, void* pooled, int block_n, int device,
                      void* stream);
+
+/* conv3x3 / pad 1 through the halo-resident kernel (csrc/conv_halo.cuh): same tensors as
+ * gsd_op_conv_bf16 with the 9 taps implied.  base_off_mode selects how the UMMA descriptor encodes the
+ * swizzle phase of the shifted tap views (1 = PTX-ISA base-offset field; 0 = experiment). */
+int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* src1, int C1, int H1, int W1, int off_y,
+                             int off_x, int B, int H, int W, const void* w, int Cout, const float* scale,
+                             const float* shift, int relu, void* out, void* pooled, int block_n,
+                             int base_off_mode, int device, void* stream);
 
 /* Stand-alone processing helper: fp32 NCHW -> fp32 NCHW,
  *   out[:, c] = scale8[min(c,7)] * area_resample(use_diff ? (x - base + 255)/2 : x) + shift8[min(c,7)]

@@ -259,3 +259,30 @@ def test_forward_host_pipelined_matches_device_path():
     xd, yd = torch.empty_like(x, device=dev()), torch.empty(5, 2, 32, 43, device=dev())
     plan.forward_host(xh, None, pp, yh, xd, yd, net.packed_weights(plan))
     assert torch.equal(yh, y_ref)
+
+
+@pytest.mark.parametrize("cin,cin1,cout,h,w,b,pool", [(64, 0, 64, 19, 23, 2, False), (64, 0, 64, 40, 53, 2, True),
+                                                       (64, 0, 128, 33, 20, 1, False), (128, 0, 128, 21, 27, 2, True),
+                                                       (256, 0, 256, 16, 24, 3, False), (64, 64, 64, 20, 26, 2, False),
+                                                       (128, 128, 128, 10, 13, 1, False), (64, 0, 64, 16, 8, 1, True)])
+def test_conv3x3_halo_kernel(cin, cin1, cout, h, w, b, pool):
+    """Halo-resident conv3x3 (csrc/conv_halo.cuh): shifted-descriptor tap views, resident / streamed weights,
+    two-source virtual concat, shuffle max-pool."""
+    from gelslim_depth_b200.engine import conv3x3_halo_op
+    g = torch.Generator().manual_seed(cin + cout + h)
+    ct = cin + cin1
+    x = bf16r(torch.randn(b, ct, h, w, generator=g))
+    wt = bf16r(torch.randn(cout, ct, 3, 3, generator=g) * (2.0 / (9 * ct)) ** 0.5)
+    sc, sh = 0.5 + torch.rand(cout, generator=g), 0.3 * torch.randn(cout, generator=g)
+    ref = torch.relu(F.conv2d(x, wt, padding=1) * sc[None, :, None, None] + sh[None, :, None, None])
+    d = dev()
+    xs = nhwc(x).to(torch.bfloat16).to(d)
+    s0 = xs[..., :cin].contiguous()
+    s1 = xs[..., cin:].contiguous() if cin1 else None
+    r = conv3x3_halo_op(s0, pack_w3(wt).to(d), sc.to(d), sh.to(d), relu=True, src1=s1, pool=pool)
+    torch.cuda.synchronize()
+    out = r[0] if pool else r
+    check_close(out.permute(0, 3, 1, 2), ref, "halo conv3x3")
+    if pool:
+        want = F.max_pool2d(out.permute(0, 3, 1, 2).float().cpu(), 2)
+        assert torch.equal(r[1].permute(0, 3, 1, 2).float().cpu(), want)
