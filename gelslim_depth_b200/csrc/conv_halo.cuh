@@ -5,9 +5,10 @@
 // the tensor pipe.  Here one TMA box per 64-channel block brings the (16+2) x (8+2) pixel halo of a
 // 16 x 8 output tile into smem ONCE; the A operand of filter tap (dy,dx) is the SAME smem buffer read
 // through a UMMA descriptor whose start address is shifted by (dy*10+dx) rows: the 16 eight-row core
-// groups (one per image row of the tile) are 10 rows = 1280 bytes apart (stride-byte-offset), and the
-// descriptor's base-offset field carries the 128B-swizzle phase of the unaligned start row.  A-operand
-// traffic from L2 drops 6.4x.  Weights are either RESIDENT in smem for the whole persistent CTA (64/128
+// groups (one per image row of the tile) are 10 rows = 1280 bytes apart (stride-byte-offset).  The start
+// row is NOT 8-row aligned; measured on B200 the tensor core applies the 128B-swizzle XOR on absolute
+// shared-memory address bits (as TMA does when it writes), so the descriptor base-offset stays 0.
+// A-operand traffic from L2 drops 6.4x.  Weights are either RESIDENT in smem for the whole persistent CTA (64/128
 // output channels with small K) or streamed through a ring and shared by MT=2 output tiles (M = 256
 // per CTA), which halves their traffic.
 //
@@ -17,47 +18,55 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "epilogue.cuh"
 #include "gsd_ptx.cuh"
 
 namespace gsd {
 
-constexpr int kHaloThreads = 192;
 constexpr int kHaloRows = 18 * 10;                 // halo pixels per tile
-constexpr int kHaloBoxBytes = kHaloRows * 128;     // 23040: bytes one TMA box delivers
-constexpr int kHaloBufBytes = 23 * 1024;           // buffer pitch (1024-aligned)
 
 struct HaloParams {
-  CUtensorMap tm_src0;   // (C0, W, H, B) bf16, box (64, 10, 18, 1)
+  CUtensorMap tm_src0;   // (C0, W, H, B) bf16, box (BKB/2, 10, 18, 1)
   CUtensorMap tm_src1;   // second source of the virtual concat
-  CUtensorMap tm_w;      // (9*(C0+C1), Cout) bf16, box (64, BN)
+  CUtensorMap tm_w;      // (9*(C0+C1), Cout) bf16, box (BKB/2, BN)
   const float* scale;    // [Cout]
   const float* shift;    // [Cout]
-  __nv_bfloat16* out;    // (B, H, W, Cout)
+  __nv_bfloat16* out;    // (B, H, W, Cout) or null (head-only)
   __nv_bfloat16* pooled; // (B, H/2, W/2, Cout) or null
-  int cb0, cb1;          // 64-channel blocks of source 0 / 1
+  // fused OutConv 1x1 + bias + depth de-normalisation (unet.py:54, normalization_utils.py:129); Cout == BN == 64
+  const float* head_w;   // [ncls][64] or null
+  const float* head_b;   // [ncls]
+  float* head_y;         // (B, ncls, H, W) fp32 NCHW
+  float head_scale, head_shift;
+  int head_ncls;
+  int cb0, cb1;          // channel blocks (BKB/2 channels each) of source 0 / 1
   int off_x, off_y;      // F.pad left/top of source 1
   int tiles_x, tiles_y, batch;
   int H, W, Cout;
   int n_tiles;           // Cout / BN
   int relu;
   int na, nb;            // ring depths (A halo buffers, B weight stages)
-  int base_off_mode;     // 1: descriptor base-offset = (start >> 7) & 7 (PTX ISA); 0: leave it 0 (experiment)
 };
 
-// high words of the two smem descriptors (constant): version 1 @bit 46, SW128 @bits 61..63, SBO >> 4 @bits 32..45
-constexpr uint32_t kHaloDescHi = (1280u >> 4) | (1u << 14) | (2u << 29);
-constexpr uint32_t kKmajor128DescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+template <int BKB>
+struct HaloGeom {
+  static constexpr int BOX_BYTES = kHaloRows * BKB;                       // bytes one TMA halo box delivers
+  static constexpr int BUF_BYTES = (BOX_BYTES + 1023) / 1024 * 1024;      // ring pitch
+  static constexpr uint32_t LAYOUT = (BKB == 128) ? 2u : 6u;              // SWIZZLE_128B / SWIZZLE_32B
+  // descriptor high words: SBO >> 4 @bits 32..45, version 1 @bit 46, swizzle @bits 61..63
+  static constexpr uint32_t A_HI = ((10u * BKB) >> 4) | (1u << 14) | (LAYOUT << 29);   // image rows are 10 halo pixels apart
+  static constexpr uint32_t B_HI = ((8u * BKB) >> 4) | (1u << 14) | (LAYOUT << 29);
+  static constexpr int KSTEPS = BKB / 32;                                 // UMMA K = 16 bf16 = 32 bytes
+  static constexpr int ROW16 = BKB / 16;                                  // one halo pixel in descriptor address units
+};
 
-// smem descriptor for the shifted-halo A operand
-__device__ __forceinline__ uint64_t make_halo_desc(uint32_t saddr, int base_off_mode) {
-  const uint64_t bo = base_off_mode ? (uint64_t)((saddr >> 7) & 7u) : 0ull;
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1280 >> 4) << 32) | (1ull << 46) | (bo << 49) |
-         (2ull << 61);
-}
-
-template <int BN, int MT, bool WRES>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
-  constexpr int B_BYTES = BN * 128;
+// NEPI = epilogue warps (4: one per TMEM lane quadrant; 8: two per quadrant on alternate 32-column units)
+template <int BN, int MT, bool WRES, int BKB, int NEPI>
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  constexpr int kHaloThreads = 64 + 32 * NEPI;
+  using G = HaloGeom<BKB>;
+  constexpr int B_BYTES = BN * BKB;
+  constexpr int KEL = BKB / 2;
   constexpr int TMEM_COLS = (2 * MT * BN <= 128) ? 128 : (2 * MT * BN <= 256) ? 256 : 512;
   static_assert(2 * MT * BN <= 512, "accumulators exceed TMEM");
 
@@ -69,11 +78,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const int nkb = 9 * cbt;
   const int na = p.na, nb = WRES ? 0 : p.nb;
   const uint32_t s_a = smem_base;
-  const uint32_t s_b = s_a + na * kHaloBufBytes;                       // B ring, or the resident weights
+  const uint32_t s_b = s_a + na * G::BUF_BYTES;                        // B ring, or the resident weights
   const uint32_t s_aux = s_b + (WRES ? nkb : nb) * B_BYTES;
   float* g_scale = reinterpret_cast<float*>(smem_gen + (s_aux - smem_base));   // [Cout] (<= 1024)
   float* g_shift = g_scale + p.Cout;
-  const uint32_t s_bar = s_aux + 2 * p.Cout * 4;
+  float* g_head = g_shift + p.Cout;                                    // [4][64] + [4]
+  const uint32_t s_epi = s_aux + 2 * p.Cout * 4 + (4 * 64 + 4) * 4 + 16;   // per-warp 2 KB epilogue transpose patches
+  const uint32_t s_hx = s_epi + NEPI * kEpiStageBytesPerWarp;         // head partial-sum exchange [4 quadrants][32][4]
+  float* g_hx = reinterpret_cast<float*>(smem_gen + (s_hx - smem_base));
+  const uint32_t s_bar = s_hx + 4 * 32 * 4 * 4;
   const uint32_t bar_fullA = s_bar;                    // [na]
   const uint32_t bar_emptyA = bar_fullA + 8 * na;      // [na]
   const uint32_t bar_fullB = bar_emptyA + 8 * na;      // [nb] (or [1] = resident weights landed)
@@ -94,13 +107,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < na; ++i) { mbar_init(bar_fullA + 8 * i, 1); mbar_init(bar_emptyA + 8 * i, 1); }
     for (int i = 0; i < (WRES ? 1 : nb); ++i) { mbar_init(bar_fullB + 8 * i, 1); mbar_init(bar_emptyB + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, NEPI); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(s_tmem_slot);
   for (int i = threadIdx.x; i < p.Cout; i += kHaloThreads) {
     g_scale[i] = __ldg(p.scale + i);
     g_shift[i] = __ldg(p.shift + i);
+  }
+  if (p.head_w) {
+    for (int i = threadIdx.x; i < p.head_ncls * 64; i += kHaloThreads) g_head[i] = __ldg(p.head_w + i);
+    if (threadIdx.x < p.head_ncls) g_head[256 + threadIdx.x] = __ldg(p.head_b + threadIdx.x);
   }
   tc_fence_before();
   __syncthreads();
@@ -116,7 +133,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (lane == 0) {
       if (WRES) {
         mbar_arrive_expect_tx(bar_fullB, (uint32_t)(nkb * B_BYTES));
-        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(s_b + kb * B_BYTES, &p.tm_w, bar_fullB, kb * 64, 0);
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(s_b + kb * B_BYTES, &p.tm_w, bar_fullB, kb * KEL, 0);
       }
       int ia = 0, ib = 0;
       uint32_t pa = 0, pb = 0;
@@ -133,11 +150,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const int b = mt / (p.tiles_x * p.tiles_y);
             const int xs = tx * 8 - 1, ys = ty * 16 - 1;
             mbar_wait(bar_emptyA + 8 * ia, pa ^ 1);
-            mbar_arrive_expect_tx(bar_fullA + 8 * ia, kHaloBoxBytes);
+            mbar_arrive_expect_tx(bar_fullA + 8 * ia, G::BOX_BYTES);
             if (cb < p.cb0)
-              tma_load_4d(s_a + ia * kHaloBufBytes, &p.tm_src0, bar_fullA + 8 * ia, cb * 64, xs, ys, b);
+              tma_load_4d(s_a + ia * G::BUF_BYTES, &p.tm_src0, bar_fullA + 8 * ia, cb * KEL, xs, ys, b);
             else
-              tma_load_4d(s_a + ia * kHaloBufBytes, &p.tm_src1, bar_fullA + 8 * ia, (cb - p.cb0) * 64, xs - p.off_x,
+              tma_load_4d(s_a + ia * G::BUF_BYTES, &p.tm_src1, bar_fullA + 8 * ia, (cb - p.cb0) * KEL, xs - p.off_x,
                           ys - p.off_y, b);
             if (++ia == na) { ia = 0; pa ^= 1; }
           }
@@ -145,7 +162,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(bar_emptyB + 8 * ib, pb ^ 1);
               mbar_arrive_expect_tx(bar_fullB + 8 * ib, B_BYTES);
-              tma_load_2d(s_b + ib * B_BYTES, &p.tm_w, bar_fullB + 8 * ib, (tap * cbt + cb) * 64, nt * BN);
+              tma_load_2d(s_b + ib * B_BYTES, &p.tm_w, bar_fullB + 8 * ib, (tap * cbt + cb) * KEL, nt * BN);
               if (++ib == nb) { ib = 0; pb ^= 1; }
             }
           }
@@ -169,7 +186,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
           mbar_wait(bar_fullA + 8 * ia, pa);
-          a_lo[j] = ((s_a + ia * kHaloBufBytes) & 0x3FFFFu) >> 4;
+          a_lo[j] = ((s_a + ia * G::BUF_BYTES) & 0x3FFFFu) >> 4;
           a_slot[j] = ia;
           if (++ia == na) { ia = 0; pa ^= 1; }
         }
@@ -191,11 +208,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < MT; ++j) {
                 const uint32_t d_tmem = tmem_base + (buf * MT + j) * BN;
-                const uint32_t a0 = a_lo[j] + (ty3 * 10 + tx3) * 8;     // +128 bytes per halo row (>>4)
+                // tap view = same halo buffer, start shifted by (ty3*10 + tx3) halo pixels; the hardware applies
+                // the swizzle XOR on absolute smem address bits, so no base-offset is needed (verified on B200)
+                const uint32_t a0 = a_lo[j] + (ty3 * 10 + tx3) * G::ROW16;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_lohi(d_tmem, (a0 + 2 * k) | (1u << 16), kHaloDescHi, (b_lo + 2 * k) | (1u << 16), kKmajor128DescHi,
-                                 idesc, (k != 0) ? 1u : (uint32_t)((cb | tap) != 0));
+                for (int k = 0; k < G::KSTEPS; ++k)
+                  umma_bf16_lohi(d_tmem, (a0 + 2 * k) | (1u << 16), G::A_HI, (b_lo + 2 * k) | (1u << 16), G::B_HI, idesc,
+                                 (k != 0) ? 1u : (uint32_t)((cb | tap) != 0));
               }
               if (!WRES) umma_commit(bar_emptyB + 8 * ib);
             }
@@ -213,10 +232,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       __syncwarp();
     }
   } else {
-    // ===================================================== epilogue (warps 2..5)
+    // ===================================================== epilogue (warps 2..9): quadrant q = warp % 4, column half = (warp-2)/4
     const int q = warp & 3;
+    const int half = (NEPI == 8) ? ((warp - 2) >> 2) : 0;
+    const int ew = warp - 2;
     const int ly = 4 * q + (lane >> 3), lx = lane & 7;
     const int Hp = p.H >> 1, Wp = p.W >> 1;
+    const bool hx = lane & 1, hy = (lane >> 3) & 1;   // which half of a pooling exchange this lane keeps
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -232,48 +254,47 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int ty = (mt / p.tiles_x) % p.tiles_y;
         const int b = mt / (p.tiles_x * p.tiles_y);
         const int y = ty * 16 + ly, x = tx * 8 + lx;
+        EpiPixel px;
         const bool valid = (y < p.H) && (x < p.W);
-        const bool pvalid = p.pooled && !(lane & 9) && ((y >> 1) < Hp) && ((x >> 1) < Wp);
-        __nv_bfloat16* orow = p.out + (((size_t)b * p.H + y) * p.W + x) * p.Cout + nt * BN;
-        __nv_bfloat16* prow = p.pooled ? p.pooled + (((size_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout + nt * BN : nullptr;
+        px.store_out = p.out != nullptr;
+        px.pvalid = ((y >> 1) < Hp) && ((x >> 1) < Wp);
+        px.hx = hx; px.hy = hy; px.ypart = 8;
+        px.prow = p.pooled ? p.pooled + (((size_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout + nt * BN + (hx ? 16 : 0) + (hy ? 8 : 0)
+                           : nullptr;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = 8 * i + (lane >> 2);
+          const int yy = ty * 16 + 4 * q + (r >> 3), xx = tx * 8 + (r & 7);
+          px.rp[i] = (p.out && yy < p.H && xx < p.W) ? p.out + (((size_t)b * p.H + yy) * p.W + xx) * p.Cout + nt * BN : nullptr;
+        }
         const uint32_t t_row = tmem_base + (buf * MT + j) * BN + ((uint32_t)(q * 32) << 16);
+        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-          const float* sc = g_scale + nt * BN + c0;
-          const float* sh = g_shift + nt * BN + c0;
+        for (int c0 = 32 * half; c0 < BN; c0 += 8 * NEPI)
+          epilogue_32cols(t_row, c0, g_scale + nt * BN, g_shift + nt * BN, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc,
+                          p.head_w ? g_head : nullptr, p.head_ncls);
+        if (p.head_w) {
+          // the two warps of a quadrant hold the two channel halves of the same 32 pixels: combine through smem
+          float* slot = g_hx + (q * 32 + lane) * 4;
+          if (NEPI == 8) {
+            if (half == 1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(v[2 * i]) * sc[2 * i] + sh[2 * i];
-            float c = __uint_as_float(v[2 * i + 1]) * sc[2 * i + 1] + sh[2 * i + 1];
-            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          if (valid) {
-            uint4* o = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-          }
-          if (p.pooled) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
-              __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[i]), *reinterpret_cast<__nv_bfloat162*>(&o1));
-              uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
-              uint32_t o8 = __shfl_xor_sync(0xffffffffu, mu, 8);
-              m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o8));
-              pk[i] = *reinterpret_cast<uint32_t*>(&m);
+              for (int k = 0; k < 4; ++k) slot[k] = hacc[k];
             }
-            if (pvalid) {
-              uint4* o = reinterpret_cast<uint4*>(prow + c0);
+            named_bar_sync(1 + q, 64);
+            if (half == 0) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) o[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+              for (int k = 0; k < 4; ++k) hacc[k] += slot[k];
             }
           }
+          if (half == 0 && valid) {
+            const size_t plane = (size_t)p.H * p.W;
+            float* yo = p.head_y + (size_t)b * p.head_ncls * plane + (size_t)y * p.W + x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < p.head_ncls) yo[k * plane] = (hacc[k] + g_head[256 + k]) * p.head_scale + p.head_shift;
+          }
+          if (NEPI == 8) named_bar_sync(1 + q, 64);
         }
       }
       tc_fence_before();

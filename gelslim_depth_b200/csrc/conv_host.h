@@ -23,6 +23,9 @@ struct ConvDesc {
   void* out = nullptr;         // (B,H,W,Cout) or, groups==4, (B,2H,2W,Cout)
   void* pooled = nullptr;      // (B,H/2,W/2,Cout) or null
   int block_n = 0;             // 0 = choose
+  // fused OutConv 1x1 + bias + depth de-normalisation (halo kernel only, Cout == 64)
+  const float* head_w = nullptr; const float* head_b = nullptr; float* head_y = nullptr;
+  float head_scale = 1.f, head_shift = 0.f; int head_ncls = 0;
 };
 
 struct ConvLaunch {
@@ -32,14 +35,14 @@ struct ConvLaunch {
 };
 
 inline void pick_tile(int H, int W, bool pool, int* th, int* tw) {
-  static const int cand[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
+  static const int cand[5][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}};
   if (const char* e = getenv("GSD_FORCE_TILE")) {   // tuning experiments only: "THxTW"
     int a = 0, b = 0;
-    if (sscanf(e, "%dx%d", &a, &b) == 2 && a * b == 128 && !(pool && ((a | b) & 1))) { *th = a; *tw = b; return; }
+    if (sscanf(e, "%dx%d", &a, &b) == 2 && a * b == 128 && !(pool && b != 8 && b != 16)) { *th = a; *tw = b; return; }
   }
   long best = -1;
   for (auto& c : cand) {
-    if (pool && (c[0] & 1)) continue;
+    if (pool && c[1] != 8 && c[1] != 16) continue;   // the shuffle max-pool needs both window rows in one warp
     long covered = (long)((H + c[0] - 1) / c[0]) * c[0] * ((W + c[1] - 1) / c[1]) * c[1];
     if (best < 0 || covered < best) { best = covered; *th = c[0]; *tw = c[1]; }
   }
@@ -73,13 +76,15 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
     bn = 64;
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
-      if (d.Cout % c) continue;
+      // a tile may span several (dy,dx) groups of the transposed-conv scatter (A is then loaded once for all of them)
+      if (d.groups == 1 ? (d.Cout % c != 0) : (ntot % c != 0 || (c % d.Cout != 0 && d.Cout % c != 0))) continue;
       if (bkb == 32 && c != 64) continue;
       if ((long)m_tiles * (ntot / c) >= 2L * num_sms || c == 64) { bn = c; break; }
     }
   }
   GSD_CHECK(bn == 64 || bn == 128 || bn == 256, "conv: block_n %d invalid", bn);
-  GSD_CHECK(d.Cout % bn == 0, "conv: block_n %d does not divide Cout %d", bn, d.Cout);
+  GSD_CHECK(ntot % bn == 0 && (d.Cout % bn == 0 || (d.groups == 4 && bn % d.Cout == 0)),
+            "conv: block_n %d incompatible with Cout %d (groups %d)", bn, d.Cout, d.groups);
   GSD_CHECK(!(bkb == 32 && bn != 64), "conv: first-layer path supports block_n 64 only");
   L->bn = bn; L->bkb = bkb;
   p.n_tiles = ntot / bn;
@@ -115,33 +120,10 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
     uint32_t box[2] = {(uint32_t)kel, (uint32_t)bn};
     GSD_TRY(encode_bf16_map(&p.tm_w, const_cast<void*>(d.w), 2, dims, str, box, swz, true));
   }
-  if (d.groups == 1) {
-    uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
-    uint64_t str[3] = {(uint64_t)d.Cout * 2, (uint64_t)d.W * d.Cout * 2, (uint64_t)d.H * d.W * d.Cout * 2};
-    uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
-    GSD_TRY(encode_bf16_map(&p.tm_out[0], d.out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
-    for (int g = 1; g < 4; ++g) p.tm_out[g] = p.tm_out[0];
-  } else {
-    // out is (B, 2H, 2W, Cout); view g = dy*2+dx selects pixels (2y+dy, 2x+dx)
-    const uint64_t W2 = 2ull * d.W, H2 = 2ull * d.H;
-    for (int g = 0; g < 4; ++g) {
-      const int gy = g >> 1, gx = g & 1;
-      char* base = static_cast<char*>(d.out) + ((uint64_t)gy * W2 + gx) * d.Cout * 2;
-      uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
-      uint64_t str[3] = {2ull * d.Cout * 2, 2ull * W2 * d.Cout * 2, H2 * W2 * d.Cout * 2};
-      uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
-      GSD_TRY(encode_bf16_map(&p.tm_out[g], base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
-    }
-  }
-  if (d.pooled) {
-    const int ph = d.H / 2, pw = d.W / 2;
-    uint64_t dims[4] = {(uint64_t)d.Cout, (uint64_t)pw, (uint64_t)ph, (uint64_t)d.B};
-    uint64_t str[3] = {(uint64_t)d.Cout * 2, (uint64_t)pw * d.Cout * 2, (uint64_t)ph * pw * d.Cout * 2};
-    uint32_t box[4] = {64, (uint32_t)(tw / 2), (uint32_t)(th / 2), 1};
-    GSD_TRY(encode_bf16_map(&p.tm_pool, d.pooled, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
-  } else {
-    p.tm_pool = p.tm_out[0];
-  }
+  p.out = static_cast<__nv_bfloat16*>(d.out);
+  p.pooled = static_cast<__nv_bfloat16*>(d.pooled);
+  p.H = d.H; p.W = d.W; p.groups = d.groups; p.ntot = ntot;
+  GSD_CHECK(ntot <= 2048, "conv: more than 2048 output channels per launch are not supported");
   const long total = (long)m_tiles * p.n_tiles;
   L->grid = (int)(total < num_sms ? total : num_sms);
   L->flops = 2.0 * d.B * d.H * d.W * (double)ntot * d.ntaps * (d.C0 + d.C1);
@@ -181,7 +163,7 @@ namespace gsd {
 
 struct HaloLaunch {
   HaloParams p;
-  int bn = 0, mt = 0, wres = 0, grid = 0, smem = 0;
+  int bn = 0, mt = 0, wres = 0, bkb = 0, nepi = 8, grid = 0, smem = 0;
   double flops = 0;
 };
 
@@ -192,19 +174,23 @@ inline double halo_tile_efficiency(int H, int W) {
 
 inline bool halo_supported(const ConvDesc& d) {
   if (d.ntaps != 9 || d.groups != 1) return false;
-  if (d.C0 % 64 || d.C1 % 64 || d.Cout % 64 || d.Cout > 1024) return false;
+  const bool first = (d.C0 == 16 && d.C1 == 0 && d.Cout == 64);
+  if (!first && (d.C0 % 64 || d.C1 % 64)) return false;
+  if (d.Cout % 64 || d.Cout > 1024) return false;
   if (d.Cout != 64 && d.Cout % 128) return false;
   for (int t = 0; t < 9; ++t)
     if (d.dy[t] != t / 3 - 1 || d.dx[t] != t % 3 - 1) return false;
   return true;
 }
 
-inline int build_halo_launch(const ConvDesc& d, int num_sms, int base_off_mode, HaloLaunch* L) {
+inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   memset(L, 0, sizeof *L);
   GSD_CHECK(halo_supported(d), "halo conv: unsupported shape (C0=%d C1=%d Cout=%d taps=%d groups=%d)", d.C0, d.C1, d.Cout,
             d.ntaps, d.groups);
   HaloParams& p = L->p;
-  p.cb0 = d.C0 / 64; p.cb1 = d.C1 / 64;
+  const int bkb = (d.C0 == 16) ? 32 : 128;
+  const int kel = bkb / 2;
+  p.cb0 = d.C0 / kel; p.cb1 = d.C1 / kel;
   const int cbt = p.cb0 + p.cb1;
   p.off_x = d.off_x; p.off_y = d.off_y;
   p.tiles_x = (d.W + 7) / 8; p.tiles_y = (d.H + 15) / 16; p.batch = d.B;
@@ -212,36 +198,43 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, int base_off_mode, 
   p.scale = d.scale; p.shift = d.shift; p.relu = d.relu;
   p.out = static_cast<__nv_bfloat16*>(d.out);
   p.pooled = static_cast<__nv_bfloat16*>(d.pooled);
-  p.base_off_mode = base_off_mode;
+  p.head_w = d.head_w; p.head_b = d.head_b; p.head_y = d.head_y;
+  p.head_scale = d.head_scale; p.head_shift = d.head_shift; p.head_ncls = d.head_ncls;
+  GSD_CHECK(!d.head_w || (d.Cout == 64 && d.head_ncls >= 1 && d.head_ncls <= 4 && d.head_y && d.head_b),
+            "halo conv: fused 1x1 head needs Cout == 64 and 1..4 classes");
+  GSD_CHECK(d.out || d.head_w, "halo conv: no output requested");
   const int budget = 227 * 1024 - 1024;
-  const int aux = 2 * d.Cout * 4 + 512;
-  int bn, mt, wres;
-  if (d.Cout == 64 && 9 * cbt * 64 * 128 <= 150 * 1024) { bn = 64; mt = 1; wres = 1; }
-  else if (d.Cout == 128 && cbt == 1) { bn = 128; mt = 1; wres = 1; }
+  const int buf_bytes = (kHaloRows * bkb + 1023) / 1024 * 1024;
+  int bn, mt, wres, nepi = 8;
+  // 64 output channels: the whole weight matrix stays resident in smem for the life of the persistent CTA
+  // (4 epilogue warps instead of 8 when that leaves too little room for the halo ring)
+  if (d.Cout == 64 && 9 * cbt * 64 * bkb <= 150 * 1024) { bn = 64; mt = 1; wres = 1; nepi = (9 * cbt * 64 * bkb > 80 * 1024) ? 4 : 8; }
   else if (d.Cout == 64) { bn = 64; mt = 2; wres = 0; }
   else { bn = 128; mt = 2; wres = 0; }
-  if (d.block_n == 64 && d.Cout % 64 == 0 && !wres) bn = 64;
-  const int b_bytes = bn * 128;
+  GSD_CHECK(bkb == 128 || wres, "halo conv: first-layer path needs resident weights");
+  const int aux = 2 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
+  const int b_bytes = bn * bkb;
   if (wres) {
     p.nb = 0;
-    p.na = (budget - aux - 9 * cbt * b_bytes) / kHaloBufBytes;
+    p.na = (budget - aux - 9 * cbt * b_bytes) / buf_bytes;
     if (p.na > 6) p.na = 6;
     GSD_CHECK(p.na >= 2, "halo conv: resident weights leave no room for the halo ring");
-    L->smem = p.na * kHaloBufBytes + 9 * cbt * b_bytes + aux + 1024;
+    L->smem = p.na * buf_bytes + 9 * cbt * b_bytes + aux + 1024;
   } else {
     p.na = 4;
-    p.nb = (budget - aux - p.na * kHaloBufBytes) / b_bytes;
+    p.nb = (budget - aux - p.na * buf_bytes) / b_bytes;
     if (p.nb > 9) p.nb = 9;
     GSD_CHECK(p.nb >= 3, "halo conv: no room for the weight ring");
-    L->smem = p.na * kHaloBufBytes + p.nb * b_bytes + aux + 1024;
+    L->smem = p.na * buf_bytes + p.nb * b_bytes + aux + 1024;
   }
   p.n_tiles = d.Cout / bn;
-  L->bn = bn; L->mt = mt; L->wres = wres;
+  L->bn = bn; L->mt = mt; L->wres = wres; L->bkb = bkb; L->nepi = nepi;
+  const CUtensorMapSwizzle swz = bkb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   auto src_map = [&](CUtensorMap* m, const void* base, int C, int H, int W) -> int {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)d.B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    uint32_t box[4] = {64, 10, 18, 1};
-    return encode_bf16_map(m, const_cast<void*>(base), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false);
+    uint32_t box[4] = {(uint32_t)kel, 10, 18, 1};
+    return encode_bf16_map(m, const_cast<void*>(base), 4, dims, str, box, swz, false);
   };
   GSD_TRY(src_map(&p.tm_src0, d.src0, d.C0, d.H, d.W));
   if (d.C1) GSD_TRY(src_map(&p.tm_src1, d.src1, d.C1, d.H1, d.W1));
@@ -250,8 +243,8 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, int base_off_mode, 
     const uint64_t ktot = 9ull * (d.C0 + d.C1);
     uint64_t dims[2] = {ktot, (uint64_t)d.Cout};
     uint64_t str[1] = {ktot * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
-    GSD_TRY(encode_bf16_map(&p.tm_w, const_cast<void*>(d.w), 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+    uint32_t box[2] = {(uint32_t)kel, (uint32_t)bn};
+    GSD_TRY(encode_bf16_map(&p.tm_w, const_cast<void*>(d.w), 2, dims, str, box, swz, true));
   }
   const long m_tiles = (long)p.tiles_x * p.tiles_y * d.B;
   const long items = ((m_tiles + mt - 1) / mt) * p.n_tiles;
@@ -260,24 +253,25 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, int base_off_mode, 
   return 0;
 }
 
-template <int BN, int MT, bool WRES>
+template <int BN, int MT, bool WRES, int BKB, int NEPI>
 inline int launch_halo_cfg(const HaloLaunch& L, cudaStream_t st) {
   static int attr_smem = 0;
   if (attr_smem < L.smem) {
-    GSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
+    GSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, WRES, BKB, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
     attr_smem = L.smem;
   }
-  conv_halo_kernel<BN, MT, WRES><<<L.grid, kHaloThreads, L.smem, st>>>(L.p);
+  conv_halo_kernel<BN, MT, WRES, BKB, NEPI><<<L.grid, 64 + 32 * NEPI, L.smem, st>>>(L.p);
   GSD_CUDA(cudaGetLastError());
   return 0;
 }
 
 inline int run_halo_launch(const HaloLaunch& L, cudaStream_t st) {
-  if (L.bn == 64 && L.mt == 1 && L.wres) return launch_halo_cfg<64, 1, true>(L, st);
-  if (L.bn == 128 && L.mt == 1 && L.wres) return launch_halo_cfg<128, 1, true>(L, st);
-  if (L.bn == 64 && L.mt == 2 && !L.wres) return launch_halo_cfg<64, 2, false>(L, st);
-  if (L.bn == 128 && L.mt == 2 && !L.wres) return launch_halo_cfg<128, 2, false>(L, st);
-  return fail(-1, "halo conv: no kernel for bn=%d mt=%d wres=%d", L.bn, L.mt, L.wres);
+  if (L.bkb == 32) return launch_halo_cfg<64, 1, true, 32, 8>(L, st);
+  if (L.bn == 64 && L.mt == 1 && L.wres && L.nepi == 8) return launch_halo_cfg<64, 1, true, 128, 8>(L, st);
+  if (L.bn == 64 && L.mt == 1 && L.wres && L.nepi == 4) return launch_halo_cfg<64, 1, true, 128, 4>(L, st);
+  if (L.bn == 64 && L.mt == 2 && !L.wres) return launch_halo_cfg<64, 2, false, 128, 8>(L, st);
+  if (L.bn == 128 && L.mt == 2 && !L.wres) return launch_halo_cfg<128, 2, false, 128, 8>(L, st);
+  return fail(-1, "halo conv: no kernel for bn=%d mt=%d wres=%d nepi=%d", L.bn, L.mt, L.wres, L.nepi);
 }
 
 }  // namespace gsd

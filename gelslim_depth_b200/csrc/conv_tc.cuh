@@ -11,29 +11,31 @@
 // activation source makes torch.cat([skip, up], 1) (unet.py:48) virtual: its channels are just more
 // K-blocks.  Nothing is im2col-materialised.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0    : TMA producer (one elected lane)
 //   warp 1    : tcgen05.mma issuer (one elected lane); accumulators double-buffered in TMEM so the
 //               epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 2-5 : epilogue: tcgen05.ld -> per-channel scale/shift (folded BatchNorm or bias) -> ReLU ->
-//               bf16 -> swizzled smem staging -> TMA store (hardware clips ragged edges);
-//               optionally a fused 2x2 max-pool of the staged tile -> second TMA store.
+//   warps 2-9 : epilogue (epilogue.cuh): tcgen05.ld -> per-channel scale/shift (folded BatchNorm or bias) ->
+//               ReLU -> bf16 -> 16-byte global stores from registers; optional fused 2x2 max-pool by warp
+//               shuffles; the transposed-conv variant scatters to (2y+dy, 2x+dx).
 #pragma once
 #include <cuda_bf16.h>
 
+#include "epilogue.cuh"
 #include "gsd_ptx.cuh"
 
 namespace gsd {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kMaxTaps = 9;
 
 struct ConvParams {
   CUtensorMap tm_src0;    // (C0, W, H, B) bf16
   CUtensorMap tm_src1;    // (C1, W1, H1, B) bf16 -- second half of the virtual concat (unused if kb1 == 0)
   CUtensorMap tm_w;       // (Ktot, Ntot) bf16, K-major weights
-  CUtensorMap tm_out[4];  // (Cout, W, H, B) bf16; 4 strided views for the transposed-conv scatter
-  CUtensorMap tm_pool;    // (Cout, W/2, H/2, B) bf16
+  __nv_bfloat16* out;     // (B, H, W, Cout), or (B, 2H, 2W, Cout) for the transposed-conv scatter (groups == 4)
+  __nv_bfloat16* pooled;  // (B, H/2, W/2, Cout) or null
+  int H, W, groups, ntot;
   const float* scale;     // [Ntot]
   const float* shift;     // [Ntot]
   int kb0, kb1;           // channel blocks per tap of source 0 / 1
@@ -54,17 +56,12 @@ struct ConvCfg {
   static constexpr int A_BYTES = 128 * BKB;
   static constexpr int B_BYTES = BN * BKB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int GROUPS = BN / 64;                   // 64-channel (128-byte) output groups
-  static constexpr int PASS_GROUPS = GROUPS > 2 ? 2 : GROUPS;   // groups staged per epilogue pass
-  static constexpr int PASSES = GROUPS / PASS_GROUPS;
-  static constexpr int PASS_N = PASS_GROUPS * 64;
-  static constexpr int OUT_BYTES = PASS_GROUPS * 128 * 128;     // staged bf16 tile (one pass)
-  static constexpr int POOL_BYTES = PASS_GROUPS * 32 * 128;     // staged pooled tile (one pass)
-  static constexpr int AUX_BYTES = 2 * BN * 4 + 256;       // scale/shift + barriers + tmem slot
+  static constexpr int MAX_NTOT = 2048;                    // scale/shift of the whole layer live in smem
+  static constexpr int AUX_BYTES = 2 * MAX_NTOT * 4 + kEpiWarps * kEpiStageBytesPerWarp + 256;   // scale/shift + epilogue patches + barriers
   static constexpr int BUDGET = 227 * 1024 - 1024;         // minus manual 1024-byte alignment slack
-  static constexpr int STAGES_RAW = (BUDGET - OUT_BYTES - POOL_BYTES - AUX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (BUDGET - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + POOL_BYTES + AUX_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
@@ -87,12 +84,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const uint32_t s_stage = smem_base;
-  const uint32_t s_out = s_stage + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t s_pool = s_out + Cfg::OUT_BYTES;
-  const uint32_t s_aux = s_pool + Cfg::POOL_BYTES;
+  const uint32_t s_aux = s_stage + STAGES * Cfg::STAGE_BYTES;
   float* g_scale = reinterpret_cast<float*>(smem_gen + (s_aux - smem_base));
-  float* g_shift = g_scale + BN;
-  const uint32_t s_bar = s_aux + 2 * BN * 4;
+  float* g_shift = g_scale + Cfg::MAX_NTOT;
+  const uint32_t s_epi = s_aux + 2 * Cfg::MAX_NTOT * 4;
+  const uint32_t s_bar = s_epi + kEpiWarps * kEpiStageBytesPerWarp;
   // barrier slots (8 bytes each): full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
   const uint32_t bar_full = s_bar;
   const uint32_t bar_empty = s_bar + 8 * STAGES;
@@ -107,7 +103,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_src0);
     tma_prefetch_desc(&p.tm_w);
-    tma_prefetch_desc(&p.tm_out[0]);
     if (p.kb1) tma_prefetch_desc(&p.tm_src1);
   }
   if (warp == 1 && lane == 0) {
@@ -117,11 +112,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 4);   // one arrive per epilogue warp
+      mbar_init(bar_acc_empty + 8 * i, kEpiWarps);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(s_tmem_slot);
+  for (int i = threadIdx.x; i < p.ntot; i += kConvThreads) {
+    g_scale[i] = __ldg(p.scale + i);
+    g_shift[i] = __ldg(p.shift + i);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -198,10 +197,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5, 128 threads)
+    // ===================================================== epilogue (warps 2..9): quadrant q = warp % 4, column half = (warp-2)/4
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    const int tw_shift = 31 - __clz(p.tw);          // tile width is a power of two
     const int row = q * 32 + lane;        // accumulator row == pixel index inside the tile
-    const int et = threadIdx.x - 64;      // 0..127
+    const int ly = row >> tw_shift, lx = row & (p.tw - 1);
+    const int Hp = p.H >> 1, Wp = p.W >> 1;
+    const bool hx = lane & 1, hy = (lane & p.tw) != 0;   // pooling needs tw in {8, 16}: both window rows in one warp
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -212,99 +216,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
       const int b = mt / p.tiles_y;
-      const int x0 = tx * p.tw, y0 = ty * p.th;
+      const int y = ty * p.th + ly, x = tx * p.tw + lx;
       const int n0 = nt * BN;
-
-      const int grp_idx = n0 / p.cout_per_group;            // which output view (transposed-conv scatter)
-      const int ch0 = n0 - grp_idx * p.cout_per_group;
-      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-        // staging buffers are free once the previous TMA stores have finished reading them
-        if (et == 0) tma_store_wait_read<0>();
-        if (pass == 0) {
-          for (int i = et; i < BN; i += 128) {
-            g_scale[i] = __ldg(p.scale + n0 + i);
-            g_shift[i] = __ldg(p.shift + n0 + i);
-          }
-        }
-        named_bar_sync(1, 128);
-        if (pass == 0) {
-          mbar_wait(bar_acc_full + 8 * acc, acc_phase);
-          tc_fence_after();
-        }
-#pragma unroll 1
-        for (int cc = 0; cc < Cfg::PASS_N; cc += 32) {
-          const int c0 = pass * Cfg::PASS_N + cc;
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);
-          tmem_ld_wait();
-          uint32_t packed[16];
+      EpiPixel px;
+      px.store_out = true;
+      px.pvalid = ((y >> 1) < Hp) && ((x >> 1) < Wp);
+      px.hx = hx; px.hy = hy; px.ypart = p.tw;
+      // pixel index (in units of one output pixel record) of the 4 rows this lane stores after the transpose
+      long pix[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(v[2 * j]) * g_scale[c0 + 2 * j] + g_shift[c0 + 2 * j];
-            float c = __uint_as_float(v[2 * j + 1]) * g_scale[c0 + 2 * j + 1] + g_shift[c0 + 2 * j + 1];
-            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
-            packed[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          const uint32_t grp = s_out + (cc >> 6) * (128 * 128);
-          const int chunk0 = (cc & 63) >> 3;   // 0 or 4
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t addr = grp + sw128_off(row, chunk0 + j);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j]),
-                         "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
-                         : "memory");
-          }
-        }
-        if (pass == Cfg::PASSES - 1) {
-          // accumulator fully read -> hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
-        }
-
-        if (p.do_pool) {
-          named_bar_sync(1, 128);   // whole staged tile visible to all epilogue threads
-          const int pw = p.tw >> 1;
-          for (int item = et; item < Cfg::PASS_GROUPS * 32 * 8; item += 128) {
-            const int chunk = item & 7;
-            const int prow = (item >> 3) & 31;
-            const int g = item >> 8;
-            const int py = prow / pw, px = prow - py * pw;
-            const int r00 = (2 * py) * p.tw + 2 * px;
-            const uint32_t gb = s_out + g * (128 * 128);
-            uint4 a, c, d, e;
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(gb + sw128_off(r00, chunk)));
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "r"(gb + sw128_off(r00 + 1, chunk)));
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(gb + sw128_off(r00 + p.tw, chunk)));
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(gb + sw128_off(r00 + p.tw + 1, chunk)));
-            auto mx = [](uint32_t u0, uint32_t u1, uint32_t u2, uint32_t u3) {
-              __nv_bfloat162 m = __hmax2(__hmax2(*reinterpret_cast<__nv_bfloat162*>(&u0), *reinterpret_cast<__nv_bfloat162*>(&u1)),
-                                         __hmax2(*reinterpret_cast<__nv_bfloat162*>(&u2), *reinterpret_cast<__nv_bfloat162*>(&u3)));
-              return *reinterpret_cast<uint32_t*>(&m);
-            };
-            const uint32_t o0 = mx(a.x, c.x, d.x, e.x), o1 = mx(a.y, c.y, d.y, e.y);
-            const uint32_t o2 = mx(a.z, c.z, d.z, e.z), o3 = mx(a.w, c.w, d.w, e.w);
-            const uint32_t addr = s_pool + g * (32 * 128) + sw128_off(prow, chunk);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
-          }
-        }
-        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, 128);
-        if (et == 0) {
-#pragma unroll
-          for (int g = 0; g < Cfg::PASS_GROUPS; ++g) {
-            const int ch = ch0 + pass * Cfg::PASS_N + g * 64;
-            tma_store_4d(&p.tm_out[grp_idx], s_out + g * (128 * 128), ch, x0, y0, b);
-            if (p.do_pool) tma_store_4d(&p.tm_pool, s_pool + g * (32 * 128), ch, x0 >> 1, y0 >> 1, b);
-          }
-          tma_store_commit();
-        }
+      for (int i = 0; i < 4; ++i) {
+        const int rr = q * 32 + 8 * i + (lane >> 2);
+        const int yy = ty * p.th + (rr >> tw_shift), xx = tx * p.tw + (rr & (p.tw - 1));
+        if (yy >= p.H || xx >= p.W) pix[i] = -1;
+        else if (p.groups == 1) pix[i] = ((long)b * p.H + yy) * p.W + xx;
+        else pix[i] = ((long)b * 2 * p.H + 2 * yy) * (2 * p.W) + 2 * xx;
       }
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      float hacc[4];
+#pragma unroll 1
+      for (int c0 = 32 * half; c0 < BN; c0 += 64) {
+        // a 32-column unit lies inside ONE (dy,dx) group of the transposed-conv scatter (Cout % 32 == 0)
+        const int grp_idx = (n0 + c0) / p.cout_per_group;
+        const int ch0 = n0 + c0 - grp_idx * p.cout_per_group;        // channel of column c0 inside its group
+        const long goff = (p.groups == 1) ? 0 : (long)(grp_idx >> 1) * (2 * p.W) + (grp_idx & 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          px.rp[i] = pix[i] < 0 ? nullptr : p.out + (pix[i] + goff) * p.cout_per_group + ch0 - c0;
+        px.prow = p.pooled ? p.pooled + (((size_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout_per_group + ch0 - c0 + (hx ? 16 : 0) + (hy ? 8 : 0)
+                           : nullptr;
+        epilogue_32cols(t_row, c0, g_scale + n0, g_shift + n0, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc, nullptr, 0);
+      }
+      // accumulator fully read -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
     }
-    if (et == 0) tma_store_wait_all<0>();   // global writes complete before the CTA exits
   }
 
   tc_fence_before();

@@ -1,0 +1,126 @@
+// Shared conv epilogue: TMEM accumulator -> scale/shift (folded BatchNorm / bias) -> ReLU -> bf16 ->
+// global memory, optional fused 2x2 max-pool (warp shuffles) and optional fused OutConv 1x1 head.
+// One thread owns one pixel (= one TMEM lane = one accumulator row).  EIGHT epilogue warps share a tile:
+// two per TMEM lane quadrant, taking alternate 32-column units, so that two warps per SM sub-partition
+// hide each other's tcgen05.ld / store latency.
+//
+// Stores: a thread holds 64 contiguous bytes (32 channels) of ITS pixel, so storing straight from registers
+// makes every lane of a warp-wide 16-byte store hit a different 128-byte line (32 LSU wavefronts per
+// instruction; measured LSU-bound).  Instead each warp transposes through a private 2 KB swizzled smem
+// patch (no block-level barrier): afterwards 4 consecutive lanes write one pixel's 64 bytes, i.e. a
+// warp-wide store covers 8 pixels x 64 B with full sectors.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gsd_ptx.cuh"
+
+namespace gsd {
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiStageBytesPerWarp = 32 * 64;   // 32 pixels x 32 channels bf16
+
+struct EpiPixel {
+  __nv_bfloat16* prow;    // &pooled[window][channel base + this lane's 8-channel piece] or null
+  __nv_bfloat16* rp[4];   // &out[pixel of warp row 8*i + lane/4][tile channel base] (null: outside the image)
+  bool store_out;         // warp-uniform: the bf16 activation is written
+  bool pvalid;            // pooling window inside the pooled image
+  bool hx, hy;            // which half this lane keeps in the x / y pooling exchange
+  int ypart;              // lane xor mask of the vertical pooling partner (= tile width)
+};
+
+// Processes the 32 accumulator columns [c0, c0+32) of this thread's row.
+//   sc/sh  : smem scale/shift already offset to the tile's first channel
+//   stage  : this warp's private staging patch (shared-window address)
+//   hacc/g_head/ncls: fused 1x1 head partial sums / smem weights [ncls][64] (g_head == nullptr: no head)
+__device__ __forceinline__ void epilogue_32cols(uint32_t t_row, int c0, const float* sc, const float* sh, int relu,
+                                                const EpiPixel& px, uint32_t stage, int lane, float (&hacc)[4],
+                                                const float* g_head, int ncls) {
+  uint32_t v[32];
+  tmem_ld32(t_row + c0, v);
+  tmem_ld_wait();
+  // per-channel constants are warp-uniform smem reads: fetch them as 128-bit broadcasts (one smem wavefront per
+  // 4 channels) -- the smem data pipe is shared with the tensor core's operand reads and is the scarce resource.
+  float f[32];
+  const float4* sc4 = reinterpret_cast<const float4*>(sc + c0);
+  const float4* sh4 = reinterpret_cast<const float4*>(sh + c0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a = sc4[i], b = sh4[i];
+    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) * a.x + b.x;
+    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) * a.y + b.y;
+    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) * a.z + b.z;
+    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) * a.w + b.w;
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+  if (g_head) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < ncls) {           // warp-uniform
+        const float4* w4 = reinterpret_cast<const float4*>(g_head + k * 64 + c0);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w = w4[i];
+          s = fmaf(f[4 * i + 0], w.x, s);
+          s = fmaf(f[4 * i + 1], w.y, s);
+          s = fmaf(f[4 * i + 2], w.z, s);
+          s = fmaf(f[4 * i + 3], w.w, s);
+        }
+        hacc[k] += s;
+      }
+    }
+  }
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  if (px.store_out) {
+    // lane -> row `lane` of the patch; 16-byte chunk j lives at (j ^ ((row >> 1) & 3)): conflict-free both ways
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t addr = stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                   "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 8 * i + (lane >> 2), c = lane & 3;
+      uint4 val;
+      const uint32_t addr = stage + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(addr));
+      if (px.rp[i]) *reinterpret_cast<uint4*>(px.rp[i] + c0 + c * 8) = val;
+    }
+    __syncwarp();
+  }
+  if (px.prow) {
+    // 2x2 max over lanes {l, l^1, l^ypart, l^1^ypart}; every exchange halves the channels a lane keeps, so the
+    // window's 4 lanes end up with 8 distinct channels each (12 shuffles instead of 32, 1 store per lane).
+    uint32_t m8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t send = px.hx ? pk[i] : pk[i + 8];
+      const uint32_t keep = px.hx ? pk[i + 8] : pk[i];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv));
+      m8[i] = *reinterpret_cast<uint32_t*>(&m);
+    }
+    uint32_t m4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t send = px.hy ? m8[i] : m8[i + 4];
+      const uint32_t keep = px.hy ? m8[i + 4] : m8[i];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, px.ypart);
+      __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv));
+      m4[i] = *reinterpret_cast<uint32_t*>(&m);
+    }
+    if (px.pvalid) *reinterpret_cast<uint4*>(px.prow + c0) = make_uint4(m4[0], m4[1], m4[2], m4[3]);
+  }
+}
+
+}  // namespace gsd

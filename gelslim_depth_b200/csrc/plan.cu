@@ -52,6 +52,7 @@ struct gsd_plan {
   std::vector<cudaEvent_t> ev_in, ev_done;
   cudaEvent_t ev_start = nullptr;
   double conv_flops = 0;
+  int head_fused = 0;          // 1x1 head + de-normalisation folded into the last conv's epilogue
 };
 
 static size_t bump(size_t* cur, size_t bytes) {
@@ -178,7 +179,7 @@ extern "C" int gsd_plan_num_bn_buffers(const gsd_plan* p) { return p ? 2 * (2 * 
 extern "C" int gsd_plan_forward_launches(const gsd_plan* p) {
   if (!p) return 0;
   const int nchunks = (p->g.batch + p->chunk - 1) / p->chunk;
-  return nchunks * (1 + 2 * (p->depth + 1) + 3 * p->depth + 1);   // + area resample when sizes differ (runtime)
+  return nchunks * (1 + 2 * (p->depth + 1) + 3 * p->depth + (p->head_fused ? 0 : 1));   // + area resample when sizes differ
 }
 extern "C" int gsd_plan_set_chunk(gsd_plan* p, int frames_per_chunk) {
   GSD_CHECK(p && frames_per_chunk >= 1, "gsd_plan_set_chunk: bad argument");
@@ -253,12 +254,15 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
     auto act = [&](size_t off, int l_h, int l_w, int c) {   // address of frame b0 inside a (B,h,w,c) bf16 tensor
       return static_cast<void*>(W + off + (size_t)b0 * l_h * l_w * c * 2);
     };
+    auto use_halo = [&](const ConvDesc& d) {
+      // halo-resident kernel wherever its fixed 16x8 tiling wastes < 25 % of the MMA rows
+      return !getenv("GSD_NO_HALO") && halo_supported(d) && halo_tile_efficiency(d.H, d.W) >= 0.75;
+    };
     auto add = [&](ConvDesc& d) -> int {
       AnyLaunch A;
-      // halo-resident kernel wherever its fixed 16x8 tiling wastes < 25 % of the MMA rows
-      if (!getenv("GSD_NO_HALO") && halo_supported(d) && halo_tile_efficiency(d.H, d.W) >= 0.75) {
+      if (use_halo(d)) {
         A.halo = 1;
-        GSD_TRY(build_halo_launch(d, p->num_sms, 0, &A.hl));
+        GSD_TRY(build_halo_launch(d, p->num_sms, &A.hl));
         A.flops = A.hl.flops;
       } else {
         GSD_TRY(build_conv_launch(d, p->num_sms, &A.tc));
@@ -325,6 +329,15 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       d1.w = P + c1.w_off; d1.scale = fptr(c1.scale_off); d1.shift = fptr(c1.shift_off);
       d1.Cout = g.dims[l]; d1.relu = 1;
       d1.out = act(p->db_off[i], h, w, g.dims[l]);
+      if (i == p->depth - 1 && use_halo(d1) && g.dims[0] == 64 && !getenv("GSD_NO_HEAD_FUSION")) {
+        // OutConv + bias + denormalize_depth_image ride in this conv's epilogue; its bf16 output is never written
+        d1.head_w = fptr(p->head_w_off); d1.head_b = fptr(p->head_b_off); d1.head_ncls = g.n_classes;
+        d1.head_y = reinterpret_cast<float*>(W + p->head_tmp_off);   // patched per call in run_chunk
+        d1.out = nullptr;
+        p->head_fused = 1;
+      } else if (i == p->depth - 1) {
+        p->head_fused = 0;
+      }
       GSD_TRY(add(d1));
     }
     p->chunks.push_back(std::move(ch));
@@ -374,21 +387,31 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const
   prologue_kernel<<<ew_grid((long)ch.nb * g.height * g.width), 256, 0, st>>>(pre, in16);
   GSD_CUDA(cudaGetLastError());
   GSD_TRY(mark());
-  for (const AnyLaunch& L : ch.convs) {
-    if (L.halo) GSD_TRY(run_halo_launch(L.hl, st));
-    else GSD_TRY(run_conv_launch(L.tc, st));
-    GSD_TRY(mark());
-  }
-  // head
   const long npix = (long)g.height * g.width;
-  const __nv_bfloat16* last = reinterpret_cast<const __nv_bfloat16*>(W + p->db_off[p->depth - 1] + (size_t)ch.b0 * npix * 64 * 2);
   const bool resample = pp->out_height != g.height || pp->out_width != g.width;
   float* head_out = resample ? reinterpret_cast<float*>(W + p->head_tmp_off) + (size_t)ch.b0 * g.n_classes * npix
                              : y + (size_t)ch.b0 * g.n_classes * npix;
-  head_kernel<64><<<ew_grid(npix * ch.nb), 256, 0, st>>>(last, reinterpret_cast<const float*>(P + p->head_w_off),
-                                                         reinterpret_cast<const float*>(P + p->head_b_off), g.n_classes,
-                                                         pp->out_scale, pp->out_shift, npix, ch.nb, head_out);
-  GSD_CUDA(cudaGetLastError());
+  for (const AnyLaunch& L : ch.convs) {
+    if (L.halo && L.hl.p.head_w) {
+      HaloLaunch t = L.hl;
+      t.p.head_y = head_out;
+      t.p.head_scale = pp->out_scale;
+      t.p.head_shift = pp->out_shift;
+      GSD_TRY(run_halo_launch(t, st));
+    } else if (L.halo) {
+      GSD_TRY(run_halo_launch(L.hl, st));
+    } else {
+      GSD_TRY(run_conv_launch(L.tc, st));
+    }
+    GSD_TRY(mark());
+  }
+  if (!p->head_fused) {
+    const __nv_bfloat16* last = reinterpret_cast<const __nv_bfloat16*>(W + p->db_off[p->depth - 1] + (size_t)ch.b0 * npix * 64 * 2);
+    head_kernel<64><<<ew_grid(npix * ch.nb), 256, 0, st>>>(last, reinterpret_cast<const float*>(P + p->head_w_off),
+                                                           reinterpret_cast<const float*>(P + p->head_b_off), g.n_classes,
+                                                           pp->out_scale, pp->out_shift, npix, ch.nb, head_out);
+    GSD_CUDA(cudaGetLastError());
+  }
   if (resample) {
     const long opix = (long)pp->out_height * pp->out_width;
     area_resample_kernel<<<ew_grid(opix * ch.nb * g.n_classes), 256, 0, st>>>(
@@ -540,6 +563,7 @@ extern "C" int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* sr
   taps3x3(&d);
   d.scale = scale; d.shift = shift; d.relu = relu; d.out = out; d.pooled = pooled; d.block_n = block_n;
   HaloLaunch L;
-  GSD_TRY(build_halo_launch(d, sms, base_off_mode, &L));
+  (void)base_off_mode;
+  GSD_TRY(build_halo_launch(d, sms, &L));
   return run_halo_launch(L, static_cast<cudaStream_t>(stream));
 }

@@ -286,3 +286,20 @@ def test_conv3x3_halo_kernel(cin, cin1, cout, h, w, b, pool):
     if pool:
         want = F.max_pool2d(out.permute(0, 3, 1, 2).float().cpu(), 2)
         assert torch.equal(r[1].permute(0, 3, 1, 2).float().cpu(), want)
+
+
+def test_first_layer_halo_kernel():
+    """inc.double_conv.0 through the SW32 / 16-channel variant of the halo kernel."""
+    from gelslim_depth_b200.engine import conv3x3_halo_op
+    g = torch.Generator().manual_seed(11)
+    for cin, h, w in ((3, 21, 37), (6, 40, 53), (6, 16, 8)):
+        x = bf16r(torch.rand(2, cin, h, w, generator=g))
+        wt = bf16r(torch.randn(64, cin, 3, 3, generator=g) * 0.3)
+        sc, sh = 0.5 + torch.rand(64, generator=g), 0.3 * torch.randn(64, generator=g)
+        ref = torch.relu(F.conv2d(x, wt, padding=1) * sc[None, :, None, None] + sh[None, :, None, None])
+        x16 = torch.zeros(2, h, w, 16)
+        x16[..., :cin] = nhwc(x)
+        d = dev()
+        out = conv3x3_halo_op(x16.to(torch.bfloat16).to(d), pack_w3(wt, 16).to(d), sc.to(d), sh.to(d), relu=True)
+        torch.cuda.synchronize()
+        check_close(out.permute(0, 3, 1, 2), ref, f"first layer (halo) cin={cin}")
