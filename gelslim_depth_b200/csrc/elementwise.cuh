@@ -60,6 +60,30 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_b
   }
 }
 
+// fp32 parity mode: same arithmetic, NHWC fp32 with exactly C channels.
+__global__ void __launch_bounds__(256) prologue_f32_kernel(const PreParams p, float* __restrict__ out) {
+  const long total = (long)p.B * p.H * p.W * p.C;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % p.C);
+    const int x = (int)((idx / p.C) % p.W);
+    const int y = (int)((idx / ((long)p.C * p.W)) % p.H);
+    const int b = (int)(idx / ((long)p.C * p.W * p.H));
+    const int ys = (int)(((long)y * p.Hr) / p.H), ye = (int)((((long)y + 1) * p.Hr + p.H - 1) / p.H);
+    const int xs = (int)(((long)x * p.Wr) / p.W), xe = (int)((((long)x + 1) * p.Wr + p.W - 1) / p.W);
+    const float* px = p.x + ((long)b * p.C + c) * p.Hr * p.Wr;
+    const float* pb = p.base ? p.base + ((long)(p.base_batch == 1 ? 0 : b) * p.C + c) * p.Hr * p.Wr : nullptr;
+    float acc = 0.f;
+    for (int yy = ys; yy < ye; ++yy)
+      for (int xx = xs; xx < xe; ++xx) {
+        float t = __ldg(px + (long)yy * p.Wr + xx);
+        if (p.use_diff) t = (t - __ldg(pb + (long)yy * p.Wr + xx) + 255.0f) * 0.5f;
+        acc += t;
+      }
+    const int cc = c < 8 ? c : 7;
+    out[idx] = p.in_scale[cc] * (acc / (float)((ye - ys) * (xe - xs))) + p.in_shift[cc];
+  }
+}
+
 // OutConv 1x1 + bias (unet.py:54) + denormalize_depth_image (normalization_utils.py:129):
 // (B,H,W,64) bf16 NHWC -> (B,ncls,H,W) fp32 NCHW.  One thread per pixel: 128 contiguous bytes in,
 // ncls coalesced floats out.

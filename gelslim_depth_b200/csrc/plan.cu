@@ -2,6 +2,7 @@
 #include <vector>
 
 #include "../../include/gsd_b200.h"
+#include "conv_fp32.cuh"
 #include "conv_host.h"
 #include "elementwise.cuh"
 #include "host_util.h"
@@ -22,9 +23,17 @@ struct AnyLaunch {      // one GEMM launch of the network: tap-streaming kernel 
   double flops = 0;
 };
 
+struct F32Step {        // fp32 parity mode: one conv GEMM or one 2x2 max-pool
+  int pool = 0;
+  F32Conv c;
+  const float* pin = nullptr; float* pout = nullptr; int B = 0, H = 0, W = 0, C = 0;
+  double flops = 0;
+};
+
 struct ChunkLaunches {
   int b0 = 0, nb = 0;
   std::vector<AnyLaunch> convs;
+  std::vector<F32Step> f32;
 };
 
 }  // namespace
@@ -77,7 +86,7 @@ extern "C" int gsd_device_count(void) {
 
 extern "C" int gsd_plan_create(gsd_plan** out, const gsd_geometry* g, int device) {
   GSD_CHECK(out && g, "gsd_plan_create: null argument");
-  GSD_CHECK(g->dtype == GSD_DTYPE_BF16, "gsd_plan_create: dtype %d not implemented (bf16 only in this build)", g->dtype);
+  GSD_CHECK(g->dtype == GSD_DTYPE_BF16 || g->dtype == GSD_DTYPE_FP32, "gsd_plan_create: unknown dtype %d", g->dtype);
   GSD_CHECK(g->mode == GSD_MODE_INFER, "gsd_plan_create: mode %d not implemented (inference only in this build)", g->mode);
   GSD_CHECK(g->batch >= 1 && g->height >= 1 && g->width >= 1, "gsd_plan_create: bad shape");
   GSD_CHECK(g->in_channels >= 1 && g->in_channels <= 8, "gsd_plan_create: in_channels %d not in 1..8", g->in_channels);
@@ -115,10 +124,14 @@ extern "C" int gsd_plan_create(gsd_plan** out, const gsd_geometry* g, int device
   }
   // ---- packed arena
   size_t cur = 0;
+  const bool f32 = g->dtype == GSD_DTYPE_FP32;
+  const size_t es = f32 ? 4 : 2;                 // activation / weight element size
+  const int in_cpad = f32 ? g->in_channels : 16; // first-layer input channels as stored
   auto add_conv = [&](std::vector<ConvW>& v, int cin, int cin_pad, int cout, int taps, int ngroups) {
     ConvW c;
+    if (f32) cin_pad = cin;
     c.cin = cin; c.cin_pad = cin_pad; c.cout = cout; c.taps = taps;
-    c.w_off = bump(&cur, (size_t)ngroups * cout * taps * cin_pad * 2);
+    c.w_off = bump(&cur, (size_t)ngroups * cout * taps * cin_pad * es);
     c.scale_off = bump(&cur, (size_t)ngroups * cout * 4);
     c.shift_off = bump(&cur, (size_t)ngroups * cout * 4);
     v.push_back(c);
@@ -141,19 +154,19 @@ extern "C" int gsd_plan_create(gsd_plan** out, const gsd_geometry* g, int device
   // ---- workspace
   cur = 0;
   const size_t B = g->batch;
-  p->in16_off = bump(&cur, B * g->height * g->width * 16 * 2);
+  p->in16_off = bump(&cur, B * g->height * g->width * in_cpad * es);
   for (int l = 0; l <= p->depth; ++l) {
     const size_t px = B * p->Hs[l] * p->Ws[l];
-    p->a_off.push_back(bump(&cur, px * g->dims[l] * 2));
-    p->s_off.push_back(bump(&cur, px * g->dims[l] * 2));
-    if (l < p->depth) p->p_off.push_back(bump(&cur, B * p->Hs[l + 1] * p->Ws[l + 1] * g->dims[l] * 2));
+    p->a_off.push_back(bump(&cur, px * g->dims[l] * es));
+    p->s_off.push_back(bump(&cur, px * g->dims[l] * es));
+    if (l < p->depth) p->p_off.push_back(bump(&cur, B * p->Hs[l + 1] * p->Ws[l + 1] * g->dims[l] * es));
   }
   for (int i = 0; i < p->depth; ++i) {
     const int l = p->depth - 1 - i;
-    p->u_off.push_back(bump(&cur, B * (2 * p->Hs[l + 1]) * (2 * p->Ws[l + 1]) * g->dims[l] * 2));
+    p->u_off.push_back(bump(&cur, B * (2 * p->Hs[l + 1]) * (2 * p->Ws[l + 1]) * g->dims[l] * es));
     const size_t px = B * p->Hs[l] * p->Ws[l];
-    p->da_off.push_back(bump(&cur, px * g->dims[l] * 2));
-    p->db_off.push_back(bump(&cur, px * g->dims[l] * 2));
+    p->da_off.push_back(bump(&cur, px * g->dims[l] * es));
+    p->db_off.push_back(bump(&cur, px * g->dims[l] * es));
   }
   p->head_tmp_off = bump(&cur, B * g->n_classes * g->height * g->width * 4);
   p->ws_bytes = align_up(cur, 1024);
@@ -204,8 +217,11 @@ extern "C" int gsd_pack_weights(gsd_plan* p, const void* const* params, const vo
     const float* mean = F(bn[bi++]);
     const float* var = F(bn[bi++]);
     const long total = (long)c.cout * c.taps * c.cin_pad;
-    pack_conv_weight_kernel<<<ew_grid(total), 256, 0, st>>>(w, c.cout, c.cin, c.taps, c.cin_pad,
-                                                             reinterpret_cast<__nv_bfloat16*>(base + c.w_off));
+    if (p->g.dtype == GSD_DTYPE_FP32)
+      pack_conv_weight_f32_kernel<<<ew_grid(total), 256, 0, st>>>(w, c.cout, c.cin, c.taps, reinterpret_cast<float*>(base + c.w_off));
+    else
+      pack_conv_weight_kernel<<<ew_grid(total), 256, 0, st>>>(w, c.cout, c.cin, c.taps, c.cin_pad,
+                                                               reinterpret_cast<__nv_bfloat16*>(base + c.w_off));
     fold_bn_kernel<<<(c.cout + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, c.cout, 1e-5f,
                                                          reinterpret_cast<float*>(base + c.scale_off),
                                                          reinterpret_cast<float*>(base + c.shift_off));
@@ -217,8 +233,11 @@ extern "C" int gsd_pack_weights(gsd_plan* p, const void* const* params, const vo
     const ConvW& u = p->upT[i];
     const float* w = F(params[pi++]);
     const float* b = F(params[pi++]);
-    pack_convt_weight_kernel<<<ew_grid(4L * u.cout * u.cin), 256, 0, st>>>(w, u.cin, u.cout,
-                                                                           reinterpret_cast<__nv_bfloat16*>(base + u.w_off));
+    if (p->g.dtype == GSD_DTYPE_FP32)
+      pack_convt_weight_f32_kernel<<<ew_grid(4L * u.cout * u.cin), 256, 0, st>>>(w, u.cin, u.cout, reinterpret_cast<float*>(base + u.w_off));
+    else
+      pack_convt_weight_kernel<<<ew_grid(4L * u.cout * u.cin), 256, 0, st>>>(w, u.cin, u.cout,
+                                                                             reinterpret_cast<__nv_bfloat16*>(base + u.w_off));
     convt_bias_kernel<<<(4 * u.cout + 127) / 128, 128, 0, st>>>(b, u.cout, reinterpret_cast<float*>(base + u.scale_off),
                                                                 reinterpret_cast<float*>(base + u.shift_off));
     GSD_CUDA(cudaGetLastError());
@@ -251,14 +270,34 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
     ChunkLaunches ch;
     ch.b0 = b0;
     ch.nb = (b0 + p->chunk <= g.batch) ? p->chunk : g.batch - b0;
-    auto act = [&](size_t off, int l_h, int l_w, int c) {   // address of frame b0 inside a (B,h,w,c) bf16 tensor
-      return static_cast<void*>(W + off + (size_t)b0 * l_h * l_w * c * 2);
+    const size_t es = g.dtype == GSD_DTYPE_FP32 ? 4 : 2;
+    auto act = [&](size_t off, int l_h, int l_w, int c) {   // address of frame b0 inside a (B,h,w,c) tensor
+      return static_cast<void*>(W + off + (size_t)b0 * l_h * l_w * c * es);
     };
     auto use_halo = [&](const ConvDesc& d) {
       // halo-resident kernel wherever its fixed 16x8 tiling wastes < 25 % of the MMA rows
       return !getenv("GSD_NO_HALO") && halo_supported(d) && halo_tile_efficiency(d.H, d.W) >= 0.75;
     };
     auto add = [&](ConvDesc& d) -> int {
+      if (g.dtype == GSD_DTYPE_FP32) {
+        F32Step s;
+        F32Conv& c = s.c;
+        c.src0 = static_cast<const float*>(d.src0); c.C0 = d.C0;
+        c.src1 = static_cast<const float*>(d.src1); c.C1 = d.C1; c.H1 = d.H1; c.W1 = d.W1; c.off_y = d.off_y; c.off_x = d.off_x;
+        c.w = static_cast<const float*>(d.w); c.scale = d.scale; c.shift = d.shift;
+        c.out = static_cast<float*>(d.out);
+        c.B = d.B; c.H = d.H; c.W = d.W; c.Cout = d.Cout; c.groups = d.groups; c.ntaps = d.ntaps; c.relu = d.relu;
+        for (int t = 0; t < d.ntaps; ++t) { c.dy[t] = d.dy[t]; c.dx[t] = d.dx[t]; }
+        s.flops = 2.0 * d.B * d.H * d.W * (double)d.groups * d.Cout * d.ntaps * (d.C0 + d.C1);
+        p->conv_flops += s.flops;
+        ch.f32.push_back(s);
+        if (d.pooled) {
+          F32Step q;
+          q.pool = 1; q.pin = c.out; q.pout = static_cast<float*>(d.pooled); q.B = d.B; q.H = d.H; q.W = d.W; q.C = d.Cout;
+          ch.f32.push_back(q);
+        }
+        return 0;
+      }
       AnyLaunch A;
       if (use_halo(d)) {
         A.halo = 1;
@@ -278,7 +317,7 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       ConvDesc d0;
       taps3x3(&d0);
       d0.B = ch.nb; d0.H = h; d0.W = w;
-      if (l == 0) { d0.src0 = act(p->in16_off, h, w, 16); d0.C0 = 16; }
+      if (l == 0) { d0.C0 = g.dtype == GSD_DTYPE_FP32 ? g.in_channels : 16; d0.src0 = act(p->in16_off, h, w, d0.C0); }
       else { d0.src0 = act(p->p_off[l - 1], h, w, g.dims[l - 1]); d0.C0 = g.dims[l - 1]; }
       const ConvW& c0 = p->enc[2 * l];
       d0.w = P + c0.w_off; d0.scale = fptr(c0.scale_off); d0.shift = fptr(c0.shift_off);
@@ -329,7 +368,7 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       d1.w = P + c1.w_off; d1.scale = fptr(c1.scale_off); d1.shift = fptr(c1.shift_off);
       d1.Cout = g.dims[l]; d1.relu = 1;
       d1.out = act(p->db_off[i], h, w, g.dims[l]);
-      if (i == p->depth - 1 && use_halo(d1) && g.dims[0] == 64 && !getenv("GSD_NO_HEAD_FUSION")) {
+      if (i == p->depth - 1 && g.dtype == GSD_DTYPE_BF16 && use_halo(d1) && g.dims[0] == 64 && !getenv("GSD_NO_HEAD_FUSION")) {
         // OutConv + bias + denormalize_depth_image ride in this conv's epilogue; its bf16 output is never written
         d1.head_w = fptr(p->head_w_off); d1.head_b = fptr(p->head_b_off); d1.head_ncls = g.n_classes;
         d1.head_y = reinterpret_cast<float*>(W + p->head_tmp_off);   // patched per call in run_chunk
@@ -383,14 +422,46 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const
   pre.use_diff = pp->use_diff;
   pre.B = ch.nb; pre.C = g.in_channels; pre.Hr = pp->raw_height; pre.Wr = pp->raw_width; pre.H = g.height; pre.W = g.width;
   for (int c = 0; c < 8; ++c) { pre.in_scale[c] = pp->in_scale[c]; pre.in_shift[c] = pp->in_shift[c]; }
-  __nv_bfloat16* in16 = reinterpret_cast<__nv_bfloat16*>(W + p->in16_off + (size_t)ch.b0 * g.height * g.width * 16 * 2);
-  prologue_kernel<<<ew_grid((long)ch.nb * g.height * g.width), 256, 0, st>>>(pre, in16);
-  GSD_CUDA(cudaGetLastError());
-  GSD_TRY(mark());
   const long npix = (long)g.height * g.width;
   const bool resample = pp->out_height != g.height || pp->out_width != g.width;
   float* head_out = resample ? reinterpret_cast<float*>(W + p->head_tmp_off) + (size_t)ch.b0 * g.n_classes * npix
                              : y + (size_t)ch.b0 * g.n_classes * npix;
+  if (g.dtype == GSD_DTYPE_FP32) {
+    // ---------------- fp32 parity mode (FFMA kernels, conv_fp32.cuh)
+    float* in0 = reinterpret_cast<float*>(W + p->in16_off) + (size_t)ch.b0 * npix * g.in_channels;
+    prologue_f32_kernel<<<ew_grid((long)ch.nb * npix * g.in_channels), 256, 0, st>>>(pre, in0);
+    GSD_CUDA(cudaGetLastError());
+    GSD_TRY(mark());
+    for (const F32Step& s : ch.f32) {
+      if (s.pool) {
+        maxpool_f32_kernel<<<ew_grid((long)s.B * (s.H / 2) * (s.W / 2) * s.C), 256, 0, st>>>(s.pin, s.B, s.H, s.W, s.C, s.pout);
+      } else {
+        const long M = (long)s.c.B * s.c.H * s.c.W;
+        dim3 grid((unsigned)((M + 63) / 64), (unsigned)((s.c.groups * s.c.Cout + 63) / 64));
+        conv_f32_kernel<<<grid, 256, 0, st>>>(s.c);
+        GSD_CUDA(cudaGetLastError());
+        GSD_TRY(mark());
+      }
+    }
+    const float* last = reinterpret_cast<const float*>(W + p->db_off[p->depth - 1]) + (size_t)ch.b0 * npix * g.dims[0];
+    head_f32_kernel<<<ew_grid(npix * ch.nb * g.n_classes), 256, 0, st>>>(last, g.dims[0], reinterpret_cast<const float*>(P + p->head_w_off),
+                                                                        reinterpret_cast<const float*>(P + p->head_b_off), g.n_classes,
+                                                                        pp->out_scale, pp->out_shift, npix, ch.nb, head_out);
+    GSD_CUDA(cudaGetLastError());
+    if (resample) {
+      const long opix = (long)pp->out_height * pp->out_width;
+      area_resample_kernel<<<ew_grid(opix * ch.nb * g.n_classes), 256, 0, st>>>(
+          head_out, ch.nb * g.n_classes, g.height, g.width, pp->out_height, pp->out_width,
+          y + (size_t)ch.b0 * g.n_classes * opix);
+      GSD_CUDA(cudaGetLastError());
+    }
+    GSD_TRY(mark());
+    return 0;
+  }
+  __nv_bfloat16* in16 = reinterpret_cast<__nv_bfloat16*>(W + p->in16_off + (size_t)ch.b0 * g.height * g.width * 16 * 2);
+  prologue_kernel<<<ew_grid((long)ch.nb * g.height * g.width), 256, 0, st>>>(pre, in16);
+  GSD_CUDA(cudaGetLastError());
+  GSD_TRY(mark());
   for (const AnyLaunch& L : ch.convs) {
     if (L.halo && L.hl.p.head_w) {
       HaloLaunch t = L.hl;
@@ -527,7 +598,8 @@ extern "C" int gsd_forward_profiled(gsd_plan* p, const float* x, const float* ba
   GSD_CUDA(cudaSetDevice(p->device));
   GSD_TRY(bind(p, workspace, packed));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int per_chunk = (int)p->chunks[0].convs.size() + 2;
+  const int nconv = p->g.dtype == GSD_DTYPE_FP32 ? 2 * (p->depth + 1) + 3 * p->depth : (int)p->chunks[0].convs.size();
+  const int per_chunk = nconv + 2;
   GSD_CHECK(capacity >= per_chunk, "gsd_forward_profiled: capacity %d < %d", capacity, per_chunk);
   for (int i = 0; i < per_chunk; ++i) { ms_host[i] = 0.f; flops_host[i] = 0.0; }
   for (const ChunkLaunches& ch : p->chunks) {
@@ -538,7 +610,7 @@ extern "C" int gsd_forward_profiled(gsd_plan* p, const float* x, const float* ba
       float ms = 0.f;
       GSD_CUDA(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
       ms_host[i] += ms;
-      if (i >= 1 && i - 1 < (int)ch.convs.size()) flops_host[i] += ch.convs[i - 1].flops;
+      if (p->g.dtype == GSD_DTYPE_BF16 && i >= 1 && i - 1 < (int)ch.convs.size()) flops_host[i] += ch.convs[i - 1].flops;
     }
     for (auto e : evs) cudaEventDestroy(e);
   }

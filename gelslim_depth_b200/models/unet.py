@@ -67,8 +67,20 @@ class UNet(nn.Module):
         self.outc.conv = nn.Conv2d(dims[0], n_classes, kernel_size=1)
 
         self._plans = PlanCache(capacity=4)
-        self._packed = None          # torch.uint8 arena of bf16 GEMM operands + folded BN
+        self._packed = None          # torch.uint8 arena of GEMM operands + folded BN
         self._packed_key = None
+        self.precision = "bf16"      # "bf16": tcgen05 tensor-core path; "fp32": FFMA parity path (set_precision)
+
+    def set_precision(self, precision: str) -> "UNet":
+        """'bf16' (default): bf16 operands / fp32 accumulation on tcgen05 tensor cores.
+        'fp32': CUDA-core fp32 parity mode (max-abs depth error <= 1e-3 mm vs the fp32 reference)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision != self.precision:
+            self.precision = precision
+            self._plans.clear()
+            self._packed, self._packed_key = None, None
+        return self
 
     # ------------------------------------------------------------------ validation
     @staticmethod
@@ -105,7 +117,7 @@ class UNet(nn.Module):
     def packed_weights(self, plan: Plan) -> torch.Tensor:
         """bf16 K-major GEMM operands + folded eval-mode BatchNorm; re-packed whenever any parameter or
         running statistic changed (optimizer.step, ema.average_parameters(), load_state_dict, .to())."""
-        key = self._weights_key()
+        key = self._weights_key() + (self.precision,)
         if self._packed is None or self._packed_key != key or self._packed.device != plan.device \
                 or self._packed.numel() != plan.packed_bytes:
             if self._packed is None or self._packed.device != plan.device or self._packed.numel() != plan.packed_bytes:
@@ -115,9 +127,10 @@ class UNet(nn.Module):
         return self._packed
 
     def plan_for(self, batch: int, height: int, width: int, device: torch.device) -> Plan:
-        key = (batch, height, width, device)
+        key = (batch, height, width, device, self.precision)
+        dtype = _lib.DTYPE_FP32 if self.precision == "fp32" else _lib.DTYPE_BF16
         return self._plans.get(key, lambda: Plan(batch, self.n_channels, height, width, self.n_classes,
-                                                 self.layer_dimensions, device))
+                                                 self.layer_dimensions, device, dtype=dtype))
 
     def _apply(self, fn, *a, **k):          # .to()/.cuda()/.float(): drop device-specific caches
         self._plans.clear()
