@@ -37,6 +37,7 @@ struct HaloParams {
   const float* head_w;   // [ncls][64] or null
   const float* head_b;   // [ncls]
   float* head_y;         // (B, ncls, H, W) fp32 NCHW
+  float* stats;          // global [2][Cout] (sum, sum of squares of the raw conv output) or null -- train-mode BatchNorm
   float head_scale, head_shift;
   int head_ncls;
   int cb0, cb1;          // channel blocks (BKB/2 channels each) of source 0 / 1
@@ -86,7 +87,9 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
   const uint32_t s_epi = s_aux + 2 * p.Cout * 4 + (4 * 64 + 4) * 4 + 16;   // per-warp 2 KB epilogue transpose patches
   const uint32_t s_hx = s_epi + NEPI * kEpiStageBytesPerWarp;         // head partial-sum exchange [4 quadrants][32][4]
   float* g_hx = reinterpret_cast<float*>(smem_gen + (s_hx - smem_base));
-  const uint32_t s_bar = s_hx + 4 * 32 * 4 * 4;
+  const uint32_t s_st = s_hx + 4 * 32 * 4 * 4;                             // per-CTA partial batch statistics [2][Cout]
+  float* g_stats = reinterpret_cast<float*>(smem_gen + (s_st - smem_base));
+  const uint32_t s_bar = s_st + 2 * p.Cout * 4;
   const uint32_t bar_fullA = s_bar;                    // [na]
   const uint32_t bar_emptyA = bar_fullA + 8 * na;      // [na]
   const uint32_t bar_fullB = bar_emptyA + 8 * na;      // [nb] (or [1] = resident weights landed)
@@ -114,6 +117,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
   for (int i = threadIdx.x; i < p.Cout; i += kHaloThreads) {
     g_scale[i] = __ldg(p.scale + i);
     g_shift[i] = __ldg(p.shift + i);
+    g_stats[i] = 0.f;
+    g_stats[p.Cout + i] = 0.f;
   }
   if (p.head_w) {
     for (int i = threadIdx.x; i < p.head_ncls * 64; i += kHaloThreads) g_head[i] = __ldg(p.head_w + i);
@@ -257,6 +262,10 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
         EpiPixel px;
         const bool valid = (y < p.H) && (x < p.W);
         px.store_out = p.out != nullptr;
+        px.valid = valid;
+        px.s_stats = p.stats ? g_stats : nullptr;
+        px.stats_ch0 = nt * BN;
+        px.stats_stride = p.Cout;
         px.pvalid = ((y >> 1) < Hp) && ((x >> 1) < Wp);
         px.hx = hx; px.hy = hy; px.ypart = 8;
         px.prow = p.pooled ? p.pooled + (((size_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout + nt * BN + (hx ? 16 : 0) + (hy ? 8 : 0)
@@ -305,6 +314,9 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += kHaloThreads) atomicAdd(p.stats + i, g_stats[i]);
+  }
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 

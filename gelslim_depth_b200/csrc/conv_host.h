@@ -26,6 +26,7 @@ struct ConvDesc {
   // fused OutConv 1x1 + bias + depth de-normalisation (halo kernel only, Cout == 64)
   const float* head_w = nullptr; const float* head_b = nullptr; float* head_y = nullptr;
   float head_scale = 1.f, head_shift = 0.f; int head_ncls = 0;
+  float* stats = nullptr;      // [2][groups*Cout] fp32, accumulated (caller zeroes): sum / sum of squares of the raw output
 };
 
 struct ConvLaunch {
@@ -123,6 +124,7 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
   p.out = static_cast<__nv_bfloat16*>(d.out);
   p.pooled = static_cast<__nv_bfloat16*>(d.pooled);
   p.H = d.H; p.W = d.W; p.groups = d.groups; p.ntot = ntot;
+  p.stats = d.stats;
   GSD_CHECK(ntot <= 2048, "conv: more than 2048 output channels per launch are not supported");
   const long total = (long)m_tiles * p.n_tiles;
   L->grid = (int)(total < num_sms ? total : num_sms);
@@ -200,6 +202,7 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   p.pooled = static_cast<__nv_bfloat16*>(d.pooled);
   p.head_w = d.head_w; p.head_b = d.head_b; p.head_y = d.head_y;
   p.head_scale = d.head_scale; p.head_shift = d.head_shift; p.head_ncls = d.head_ncls;
+  p.stats = d.stats;
   GSD_CHECK(!d.head_w || (d.Cout == 64 && d.head_ncls >= 1 && d.head_ncls <= 4 && d.head_y && d.head_b),
             "halo conv: fused 1x1 head needs Cout == 64 and 1..4 classes");
   GSD_CHECK(d.out || d.head_w, "halo conv: no output requested");
@@ -212,7 +215,7 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   else if (d.Cout == 64) { bn = 64; mt = 2; wres = 0; }
   else { bn = 128; mt = 2; wres = 0; }
   GSD_CHECK(bkb == 128 || wres, "halo conv: first-layer path needs resident weights");
-  const int aux = 2 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
+  const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
   const int b_bytes = bn * bkb;
   if (wres) {
     p.nb = 0;
@@ -272,6 +275,71 @@ inline int run_halo_launch(const HaloLaunch& L, cudaStream_t st) {
   if (L.bn == 64 && L.mt == 2 && !L.wres) return launch_halo_cfg<64, 2, false, 128, 8>(L, st);
   if (L.bn == 128 && L.mt == 2 && !L.wres) return launch_halo_cfg<128, 2, false, 128, 8>(L, st);
   return fail(-1, "halo conv: no kernel for bn=%d mt=%d wres=%d nepi=%d", L.bn, L.mt, L.wres, L.nepi);
+}
+
+}  // namespace gsd
+
+// ------------------------------------------------------------------------------------------------
+// wgrad kernel (wgrad_tc.cuh) host side
+#include "wgrad_tc.cuh"
+
+namespace gsd {
+
+struct WgradLaunch {
+  WgradParams p;
+  int grid = 0, smem = 0;
+  double flops = 0;
+};
+
+inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, int H1, int W1, int off_y, int off_x,
+                              const void* dz, int Cout, int B, int H, int W, float* dw, int num_sms, WgradLaunch* L) {
+  memset(L, 0, sizeof *L);
+  GSD_CHECK(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0 && C0 > 0, "wgrad: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)",
+            C0, C1, Cout);
+  GSD_CHECK(Cout == 64 || Cout % 128 == 0, "wgrad: Cout must be 64 or a multiple of 128");
+  WgradParams& p = L->p;
+  p.cb0 = C0 / 64; p.cb1 = C1 / 64;
+  p.off_x = off_x; p.off_y = off_y;
+  p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16; p.batch = B;
+  p.Cout = Cout; p.co_blocks = (Cout + 127) / 128;
+  p.dw = dw;
+  p.stages = 4;
+  const int blocks = p.co_blocks * (p.cb0 + p.cb1) * 2;
+  const long m_tiles = (long)p.tiles_x * p.tiles_y * B;
+  int split = blocks >= num_sms ? 1 : (num_sms + blocks / 2) / blocks;
+  if (split > m_tiles) split = (int)m_tiles;
+  if (split < 1) split = 1;
+  p.split = split;
+  L->grid = blocks * split;
+  L->smem = p.stages * kWgStageBytes + 1024 + 512;
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    uint32_t box[4] = {64, 8, 16, 1};
+    GSD_TRY(encode_bf16_map(&p.tm_dz, const_cast<void*>(dz), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
+  }
+  auto src_map = [&](CUtensorMap* m, const void* base, int C, int h, int w) -> int {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
+    uint32_t box[4] = {64, 10, 18, 1};
+    return encode_bf16_map(m, const_cast<void*>(base), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false);
+  };
+  GSD_TRY(src_map(&p.tm_x0, x0, C0, H, W));
+  if (C1) GSD_TRY(src_map(&p.tm_x1, x1, C1, H1, W1));
+  else p.tm_x1 = p.tm_x0;
+  L->flops = 2.0 * B * H * W * (double)Cout * 9 * (C0 + C1);
+  return 0;
+}
+
+inline int run_wgrad_launch(const WgradLaunch& L, cudaStream_t st) {
+  static int attr = 0;
+  if (attr < L.smem) {
+    GSD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
+    attr = L.smem;
+  }
+  wgrad_tc_kernel<<<L.grid, kWgThreads, L.smem, st>>>(L.p);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace gsd

@@ -36,6 +36,7 @@ struct ConvParams {
   __nv_bfloat16* out;     // (B, H, W, Cout), or (B, 2H, 2W, Cout) for the transposed-conv scatter (groups == 4)
   __nv_bfloat16* pooled;  // (B, H/2, W/2, Cout) or null
   int H, W, groups, ntot;
+  float* stats;           // global [2][ntot] batch statistics of the raw conv output, or null
   const float* scale;     // [Ntot]
   const float* shift;     // [Ntot]
   int kb0, kb1;           // channel blocks per tap of source 0 / 1
@@ -57,7 +58,7 @@ struct ConvCfg {
   static constexpr int B_BYTES = BN * BKB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int MAX_NTOT = 2048;                    // scale/shift of the whole layer live in smem
-  static constexpr int AUX_BYTES = 2 * MAX_NTOT * 4 + kEpiWarps * kEpiStageBytesPerWarp + 256;   // scale/shift + epilogue patches + barriers
+  static constexpr int AUX_BYTES = 4 * MAX_NTOT * 4 + kEpiWarps * kEpiStageBytesPerWarp + 256;   // scale/shift/stats + patches + barriers
   static constexpr int BUDGET = 227 * 1024 - 1024;         // minus manual 1024-byte alignment slack
   static constexpr int STAGES_RAW = (BUDGET - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   const uint32_t s_aux = s_stage + STAGES * Cfg::STAGE_BYTES;
   float* g_scale = reinterpret_cast<float*>(smem_gen + (s_aux - smem_base));
   float* g_shift = g_scale + Cfg::MAX_NTOT;
-  const uint32_t s_epi = s_aux + 2 * Cfg::MAX_NTOT * 4;
+  float* g_stats = g_shift + Cfg::MAX_NTOT;                 // [2][ntot]
+  const uint32_t s_epi = s_aux + 4 * Cfg::MAX_NTOT * 4;
   const uint32_t s_bar = s_epi + kEpiWarps * kEpiStageBytesPerWarp;
   // barrier slots (8 bytes each): full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
   const uint32_t bar_full = s_bar;
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   for (int i = threadIdx.x; i < p.ntot; i += kConvThreads) {
     g_scale[i] = __ldg(p.scale + i);
     g_shift[i] = __ldg(p.shift + i);
+    g_stats[i] = 0.f;
+    g_stats[p.ntot + i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -220,6 +224,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       const int n0 = nt * BN;
       EpiPixel px;
       px.store_out = true;
+      px.valid = (y < p.H) && (x < p.W);
+      px.s_stats = p.stats ? g_stats : nullptr;
+      px.stats_ch0 = n0;
+      px.stats_stride = p.ntot;
       px.pvalid = ((y >> 1) < Hp) && ((x >> 1) < Wp);
       px.hx = hx; px.hy = hy; px.ypart = p.tw;
       // pixel index (in units of one output pixel record) of the 4 rows this lane stores after the transpose
@@ -258,6 +266,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    for (int i = threadIdx.x; i < 2 * p.ntot; i += kConvThreads) atomicAdd(p.stats + i, g_stats[i]);
+  }
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 

@@ -22,6 +22,10 @@ constexpr int kEpiStageBytesPerWarp = 32 * 64;   // 32 pixels x 32 channels bf16
 struct EpiPixel {
   __nv_bfloat16* prow;    // &pooled[window][channel base + this lane's 8-channel piece] or null
   __nv_bfloat16* rp[4];   // &out[pixel of warp row 8*i + lane/4][tile channel base] (null: outside the image)
+  float* s_stats;         // smem [2][stats_stride] per-CTA partial (sum, sum of squares) of the RAW accumulator, or null
+  int stats_ch0;          // absolute channel of accumulator column 0 of this tile
+  int stats_stride;       //   (train-mode BatchNorm batch statistics, unet.py:12 in .train()); indexed by absolute channel
+  bool valid;             // this lane's pixel lies inside the image (only such pixels enter the statistics)
   bool store_out;         // warp-uniform: the bf16 activation is written
   bool pvalid;            // pooling window inside the pooled image
   bool hx, hy;            // which half this lane keeps in the x / y pooling exchange
@@ -38,6 +42,36 @@ __device__ __forceinline__ void epilogue_32cols(uint32_t t_row, int c0, const fl
   uint32_t v[32];
   tmem_ld32(t_row + c0, v);
   tmem_ld_wait();
+  if (px.s_stats) {
+    // Batch statistics over the 32 pixels of this warp for 32 channels: butterfly transpose-reduce -- at every
+    // step a lane keeps half of its channels and adds the partner's copy of them, so 31 shuffles (not 160) leave
+    // lane l with the warp total of channel bitrev-free index `l` of this unit.
+    float s1[32], s2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float a = px.valid ? __uint_as_float(v[i]) : 0.f;
+      s1[i] = a;
+      s2[i] = a * a;
+    }
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+      const int n = 16 >> step;                 // channels kept after this step
+      const int mask = 16 >> step;              // partner lane
+      const bool upper = (lane & mask) != 0;    // upper lanes keep the upper half of the channel range
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        const float send1 = upper ? s1[i] : s1[i + n];
+        const float send2 = upper ? s2[i] : s2[i + n];
+        const float keep1 = upper ? s1[i + n] : s1[i];
+        const float keep2 = upper ? s2[i + n] : s2[i];
+        s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, mask);
+        s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
+      }
+    }
+    // after the 5 steps lane l holds channel index l (bit k of l selected the upper half at step with mask 16>>k')
+    atomicAdd(px.s_stats + px.stats_ch0 + c0 + lane, s1[0]);
+    atomicAdd(px.s_stats + px.stats_stride + px.stats_ch0 + c0 + lane, s2[0]);
+  }
   // per-channel constants are warp-uniform smem reads: fetch them as 128-bit broadcasts (one smem wavefront per
   // 4 channels) -- the smem data pipe is shared with the tensor core's operand reads and is the scarce resource.
   float f[32];

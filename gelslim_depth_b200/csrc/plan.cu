@@ -639,3 +639,18 @@ extern "C" int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* sr
   GSD_TRY(build_halo_launch(d, sms, &L));
   return run_halo_launch(L, static_cast<cudaStream_t>(stream));
 }
+
+// dW[co][tap][ci] += sum_pixels dZ[.,co] * X[.+tap, ci]  (conv3x3 / pad 1 weight gradient; fp32, accumulated --
+// the caller zeroes dw).  X may be the virtual concat of two NHWC sources like in gsd_op_conv_bf16.
+extern "C" int gsd_op_wgrad3x3_bf16(const void* x0, int C0, const void* x1, int C1, int H1, int W1, int off_y, int off_x,
+                                    const void* dz, int Cout, int B, int H, int W, float* dw, int device, void* stream) {
+  GSD_CHECK(x0 && dz && dw, "gsd_op_wgrad3x3_bf16: null argument");
+  GSD_CUDA(cudaSetDevice(device));
+  int sms = 0, major = 0;
+  GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  GSD_CHECK(major == 10, "gsd_op_wgrad3x3_bf16: device %d is not sm_100 (no fallback)", device);
+  WgradLaunch L;
+  GSD_TRY(build_wgrad_launch(x0, C0, x1 ? x1 : nullptr, x1 ? C1 : 0, H1, W1, off_y, off_x, dz, Cout, B, H, W, dw, sms, &L));
+  return run_wgrad_launch(L, static_cast<cudaStream_t>(stream));
+}

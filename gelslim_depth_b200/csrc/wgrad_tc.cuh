@@ -1,0 +1,160 @@
+// Weight gradient of a 3x3 convolution as a tcgen05 GEMM whose K dimension is the PIXELS:
+//
+//   dW[co][tap][ci] = sum_{b,y,x} dZ[b,y,x,co] * X[b, y+dy, x+dx, ci]
+//
+// Both operands are NHWC, i.e. channel-contiguous = "MN-major" for this GEMM (M = co, N = ci, K = pixel), which
+// tcgen05 reads directly (instruction-descriptor a_major = b_major = 1): no transposition pass.
+//   A = dZ tile  : one TMA box (64 co, 8, 16) per 64-channel block = 128 pixels x 128 B, pixels are the K rows
+//   B = X halo   : the same (16+2)x(8+2) halo box the forward kernel uses; the tap shift is again only a shifted
+//                  descriptor start ((2k+dy)*10+dx rows) with the 8-pixel K atoms 1280 bytes apart
+// One UMMA (K = 16) covers two image rows of the 16x8 tile; 8 UMMAs per tap per tile.  A CTA owns one
+// (128 co) x (64 ci) x (group of taps) block of dW, keeps it in TMEM (taps x 64 fp32 columns) while it streams
+// its share of the pixel tiles (split-K across CTAs), and adds it to the fp32 gradient with red.global at the end.
+// Cout == 64: the second half of the 128-row A operand re-reads the first (its accumulator rows are ignored).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gsd_ptx.cuh"
+
+namespace gsd {
+
+constexpr int kWgThreads = 192;            // TMA warp, MMA warp, 4 drain warps
+constexpr int kWgDzBytes = 128 * 128;      // one 64-channel dZ box
+constexpr int kWgHaloBox = 180 * 128;
+constexpr int kWgHaloBuf = 23 * 1024;
+constexpr int kWgStageBytes = 2 * kWgDzBytes + kWgHaloBuf;   // 55 KB
+
+struct WgradParams {
+  CUtensorMap tm_dz;     // (Cout, W, H, B) bf16, box (64, 8, 16, 1)
+  CUtensorMap tm_x0;     // (C0, W, H, B) bf16, box (64, 10, 18, 1)
+  CUtensorMap tm_x1;     // second source of the virtual concat
+  float* dw;             // [Cout][9][C0+C1] fp32, accumulated
+  int cb0, cb1;          // 64-channel blocks of the two X sources
+  int off_x, off_y;
+  int tiles_x, tiles_y, batch;
+  int Cout;
+  int co_blocks;         // ceil(Cout / 128)
+  int split;             // CTAs sharing one dW block (split-K over pixel tiles)
+  int stages;
+};
+
+// MN-major, 128B-swizzled operand descriptor: LBO = distance between 64-element MN blocks, SBO = distance between
+// 8-row K atoms (both >> 4); version 1, SWIZZLE_128B.
+__device__ __forceinline__ uint32_t mn_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t mn_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = p.stages;
+  const uint32_t s_stage = smem_base;
+  const uint32_t s_bar = s_stage + stages * kWgStageBytes;
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * stages, bar_done = bar_empty + 8 * stages;
+  const uint32_t s_tmem_slot = bar_done + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_dz);
+    tma_prefetch_desc(&p.tm_x0);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(s_tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // block decode: blockIdx.x = ((co_blk * cbt + ci_blk) * 2 + tap_group) * split + s
+  const int cbt = p.cb0 + p.cb1;
+  int bid = blockIdx.x;
+  const int s = bid % p.split; bid /= p.split;
+  const int tg = bid & 1; bid >>= 1;
+  const int ci_blk = bid % cbt;
+  const int co_blk = bid / cbt;
+  const int tap0 = tg ? 5 : 0, ntap = tg ? 4 : 5;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
+  const bool half_m = (p.Cout - co_blk * 128) < 128;      // only 64 real co rows
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int t = s; t < m_tiles; t += p.split) {
+        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+        mbar_wait(bar_empty + 8 * st, ph ^ 1);
+        const uint32_t sa = s_stage + st * kWgStageBytes, fb = bar_full + 8 * st;
+        mbar_arrive_expect_tx(fb, (half_m ? 1 : 2) * kWgDzBytes + kWgHaloBox);
+        tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * 8, ty * 16, b);
+        if (!half_m) tma_load_4d(sa + kWgDzBytes, &p.tm_dz, fb, co_blk * 128 + 64, tx * 8, ty * 16, b);
+        if (ci_blk < p.cb0)
+          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x0, fb, ci_blk * 64, tx * 8 - 1, ty * 16 - 1, b);
+        else
+          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x1, fb, (ci_blk - p.cb0) * 64, tx * 8 - 1 - p.off_x, ty * 16 - 1 - p.off_y, b);
+        if (++st == stages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // instruction descriptor: fp32 accum, bf16 A/B, A and B MN-major (bits 15, 16), N = 64, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    int st = 0; uint32_t ph = 0;
+    bool first = true;
+    for (int t = s; t < m_tiles; t += p.split) {
+      mbar_wait(bar_full + 8 * st, ph);
+      tc_fence_after();
+      const uint32_t sa = s_stage + st * kWgStageBytes;
+      const uint32_t a_lbo = half_m ? 0u : (uint32_t)kWgDzBytes;
+      if (elect_one()) {
+        for (int tp = 0; tp < ntap; ++tp) {
+          const int tap = tap0 + tp, dy = tap / 3, dx = tap % 3;
+          const uint32_t d_tmem = tmem_base + tp * 64;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t a_lo = mn_desc_lo(sa + k * 2048, a_lbo);
+            const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy) * 10 + dx) * 128, 0);
+            umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, mn_desc_hi(1280), idesc, (first && k == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(bar_empty + 8 * st);
+      }
+      __syncwarp();
+      first = false;
+      if (++st == stages) { st = 0; ph ^= 1; }
+    }
+    if (elect_one()) umma_commit(bar_done);
+    __syncwarp();
+  } else {
+    // drain: TMEM -> red.global.add.f32 into dW[co][tap][ci]
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // co within the block
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int co = co_blk * 128 + row;
+    const int ctot = cbt * 64;
+    const bool live = (s < m_tiles) && co < p.Cout && !(half_m && row >= 64);
+    for (int tp = 0; tp < ntap; ++tp) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + tp * 64 + c0 + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (live) {
+          float* dst = p.dw + ((size_t)co * 9 + tap0 + tp) * ctot + ci_blk * 64 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace gsd

@@ -163,3 +163,17 @@ def conv3x3_halo_op(src0, w, scale, shift, relu=True, src1=None, off=(0, 0), poo
                                        _ptr(scale), _ptr(shift), int(relu), _ptr(out), _ptr(pooled), block_n,
                                        base_off_mode, dev.index or 0, _stream(dev)), "gsd_op_conv3x3_halo_bf16")
     return (out, pooled) if pool else out
+
+
+def wgrad3x3_op(x0, dz, x1=None, off=(0, 0)):
+    """conv3x3 weight gradient (gsd_op_wgrad3x3_bf16): NHWC bf16 x / dz -> fp32 [Cout][9][C0+C1]."""
+    B, H, W, C0 = x0.shape
+    cout = dz.shape[-1]
+    dev = x0.device
+    C1 = H1 = W1 = 0
+    if x1 is not None:
+        _, H1, W1, C1 = x1.shape
+    dw = torch.zeros(cout, 9, C0 + C1, dtype=torch.float32, device=dev)
+    check(lib.gsd_op_wgrad3x3_bf16(_ptr(x0), C0, _ptr(x1), C1, H1, W1, off[0], off[1], _ptr(dz), cout, B, H, W, _ptr(dw),
+                                   dev.index or 0, _stream(dev)), "gsd_op_wgrad3x3_bf16")
+    return dw

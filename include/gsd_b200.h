@@ -145,6 +145,12 @@ int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* src1, int C1,
                              const float* shift, int relu, void* out, void* pooled, int block_n,
                              int base_off_mode, int device, void* stream);
 
+/* conv3x3 / pad 1 weight gradient (autograd of unet.py:11,14 -- train_unet.py:374) as a tcgen05 GEMM over pixels:
+ *   dw[co][tap][ci] += sum_{b,y,x} dz[b,y,x,co] * x[b,y+dy,x+dx,ci]      (fp32, accumulated; caller zeroes dw)
+ * x0/x1: NHWC bf16 sources of the (virtual) concat, dz: NHWC bf16 gradient of the conv output. */
+int gsd_op_wgrad3x3_bf16(const void* x0, int C0, const void* x1, int C1, int H1, int W1, int off_y, int off_x,
+                         const void* dz, int Cout, int B, int H, int W, float* dw, int device, void* stream);
+
 /* Stand-alone processing helper: fp32 NCHW -> fp32 NCHW,
  *   out[:, c] = scale8[min(c,7)] * area_resample(use_diff ? (x - base + 255)/2 : x) + shift8[min(c,7)]
  * Replaces (when called outside the fused forward): get_difference_image (image_utils.py:6-10),

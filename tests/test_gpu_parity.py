@@ -336,3 +336,26 @@ def test_fp32_parity_mode_within_1e3_mm(golden_full):
     ref = oracle.predict_depth_from_RGB(fingers, lambda t: oracle.unet_forward(sd, t), (64, 85), cfg)
     got = predict_depth_from_RGB(fingers.to(dev()), net, (64, 85), cfg).cpu()
     assert float((got - ref).abs().max()) <= 1e-3, float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize("cin,cin1,cout,h,w,b", [(64, 0, 64, 19, 23, 2), (64, 0, 128, 16, 8, 1), (128, 0, 256, 21, 27, 2),
+                                                 (64, 64, 64, 20, 26, 2), (256, 0, 128, 10, 13, 3)])
+def test_wgrad3x3_tcgen05(cin, cin1, cout, h, w, b):
+    """conv weight gradient = GEMM over pixels with MN-major operands (csrc/wgrad_tc.cuh) vs autograd."""
+    from gelslim_depth_b200.engine import wgrad3x3_op
+    g = torch.Generator().manual_seed(cin + cout + h)
+    ct = cin + cin1
+    x = bf16r(torch.randn(b, ct, h, w, generator=g))
+    dz = bf16r(torch.randn(b, cout, h, w, generator=g))
+    wt = torch.zeros(cout, ct, 3, 3, requires_grad=True)
+    F.conv2d(x, wt, padding=1).backward(dz)
+    ref = wt.grad.reshape(cout, ct, 9).permute(0, 2, 1)        # [co][tap][ci]
+    d = dev()
+    xs = nhwc(x).to(torch.bfloat16).to(d)
+    s0 = xs[..., :cin].contiguous()
+    s1 = xs[..., cin:].contiguous() if cin1 else None
+    got = wgrad3x3_op(s0, nhwc(dz).to(torch.bfloat16).to(d), x1=s1).cpu()
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) < 2e-3 * scale + 1e-3, (float((got - ref).abs().max()), scale)
+    assert rel_l2(got, ref) < 1e-3
