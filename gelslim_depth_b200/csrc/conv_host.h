@@ -27,6 +27,9 @@ struct ConvDesc {
   const float* head_w = nullptr; const float* head_b = nullptr; float* head_y = nullptr;
   float head_scale = 1.f, head_shift = 0.f; int head_ncls = 0;
   float* stats = nullptr;      // [2][groups*Cout] fp32, accumulated (caller zeroes): sum / sum of squares of the raw output
+  // transposed-conv INPUT gradient: src0 is a dense (B, Hf, Wf, Cs) tensor holding the gradient of the (2H x 2W)
+  // up-sampled map at offset (s2d_off_y, s2d_off_x); C0 must be 2*Cs, ntaps 2 (gy), the output domain is H x W.
+  int s2d = 0, s2d_Hf = 0, s2d_Wf = 0, s2d_off_y = 0, s2d_off_x = 0;
 };
 
 struct ConvLaunch {
@@ -100,7 +103,16 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
   p.do_pool = d.pooled ? 1 : 0;
 
   const CUtensorMapSwizzle swz = bkb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
-  {
+  p.src5 = d.s2d;
+  if (d.s2d) {
+    GSD_CHECK(d.ntaps == 2 && d.C1 == 0 && d.C0 % 128 == 0, "conv: space-to-depth source needs ntaps 2 and C0 = 2*Cs");
+    const uint64_t Cs = d.C0 / 2;
+    char* base = static_cast<char*>(const_cast<void*>(d.src0)) + ((uint64_t)d.s2d_off_y * d.s2d_Wf + d.s2d_off_x) * Cs * 2;
+    uint64_t dims[5] = {(uint64_t)d.C0, (uint64_t)d.W, 2, (uint64_t)d.H, (uint64_t)d.B};
+    uint64_t str[4] = {(uint64_t)d.C0 * 2, (uint64_t)d.s2d_Wf * Cs * 2, 2ull * d.s2d_Wf * Cs * 2, (uint64_t)d.s2d_Hf * d.s2d_Wf * Cs * 2};
+    uint32_t box[5] = {(uint32_t)kel, (uint32_t)tw, 1, (uint32_t)th, 1};
+    GSD_TRY(encode_bf16_map(&p.tm_src0, base, 5, dims, str, box, swz, false));
+  } else {
     uint64_t dims[4] = {(uint64_t)d.C0, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
     uint64_t str[3] = {(uint64_t)d.C0 * 2, (uint64_t)d.W * d.C0 * 2, (uint64_t)d.H * d.W * d.C0 * 2};
     uint32_t box[4] = {(uint32_t)kel, (uint32_t)tw, (uint32_t)th, 1};
@@ -338,6 +350,60 @@ inline int run_wgrad_launch(const WgradLaunch& L, cudaStream_t st) {
     attr = L.smem;
   }
   wgrad_tc_kernel<<<L.grid, kWgThreads, L.smem, st>>>(L.p);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gsd
+
+namespace gsd {
+
+struct WgradPwLaunch {
+  WgradPwParams p;
+  int grid = 0, smem = 0;
+};
+
+// in: (B,H,W,Cin) bf16; du: dense (B,Hf,Wf,Cout) bf16 holding the gradient of the up-sampled (2H x 2W) map at
+// offset (off_y, off_x); dw: (Cin, Cout, 2, 2) fp32 accumulated.
+inline int build_wgrad_pw_launch(const void* in, int Cin, const void* du, int Cout, int Hf, int Wf, int off_y, int off_x,
+                                 int B, int H, int W, float* dw, int num_sms, WgradPwLaunch* L) {
+  memset(L, 0, sizeof *L);
+  GSD_CHECK(Cin % 128 == 0 && Cout % 64 == 0, "convT wgrad: need Cin %% 128 == 0 and Cout %% 64 == 0 (Cin=%d Cout=%d)", Cin, Cout);
+  WgradPwParams& p = L->p;
+  p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16; p.batch = B;
+  p.Cin = Cin; p.Cout = Cout; p.dw = dw;
+  const int blocks = (Cin / 128) * (Cout / 64);
+  const long m_tiles = (long)p.tiles_x * p.tiles_y * B;
+  int split = blocks >= num_sms ? 1 : (num_sms + blocks / 2) / blocks;
+  if (split > m_tiles) split = (int)m_tiles;
+  if (split < 1) split = 1;
+  p.split = split;
+  L->grid = blocks * split;
+  L->smem = 2 * kWpStageBytes + 1024 + 512;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {64, 8, 16, 1};
+    GSD_TRY(encode_bf16_map(&p.tm_in, const_cast<void*>(in), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
+  }
+  for (int g = 0; g < 4; ++g) {
+    const int gy = g >> 1, gx = g & 1;
+    char* base = static_cast<char*>(const_cast<void*>(du)) + ((uint64_t)(off_y + gy) * Wf + off_x + gx) * Cout * 2;
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {2ull * Cout * 2, 2ull * Wf * Cout * 2, (uint64_t)Hf * Wf * Cout * 2};
+    uint32_t box[4] = {64, 8, 16, 1};
+    GSD_TRY(encode_bf16_map(&p.tm_du[g], base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
+  }
+  return 0;
+}
+
+inline int run_wgrad_pw_launch(const WgradPwLaunch& L, cudaStream_t st) {
+  static int attr = 0;
+  if (attr < L.smem) {
+    GSD_CUDA(cudaFuncSetAttribute(wgrad_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
+    attr = L.smem;
+  }
+  wgrad_pw_kernel<<<L.grid, kWgThreads, L.smem, st>>>(L.p);
   GSD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -37,6 +37,8 @@ struct ConvParams {
   __nv_bfloat16* pooled;  // (B, H/2, W/2, Cout) or null
   int H, W, groups, ntot;
   float* stats;           // global [2][ntot] batch statistics of the raw conv output, or null
+  int src5;               // 1: tm_src0 is the 5-D space-to-depth view (2C, W, 2, H, B) of a (B,2H,2W,C) tensor and the
+                          //    "tap" index is its gy coordinate (transposed-conv input gradient)
   const float* scale;     // [Ntot]
   const float* shift;     // [Ntot]
   int kb0, kb1;           // channel blocks per tap of source 0 / 1
@@ -158,7 +160,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
             const uint32_t sb = sa + Cfg::A_BYTES;
             const uint32_t fb = bar_full + 8 * stage;
             mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-            if (cb < p.kb0)
+            if (p.src5)
+              tma_load_5d(sa, &p.tm_src0, fb, cb * KELEMS, x0, t, y0, b);
+            else if (cb < p.kb0)
               tma_load_4d(sa, &p.tm_src0, fb, cb * KELEMS, xs, ys, b);
             else
               tma_load_4d(sa, &p.tm_src1, fb, (cb - p.kb0) * KELEMS, xs - p.off_x, ys - p.off_y, b);

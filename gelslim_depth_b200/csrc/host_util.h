@@ -64,8 +64,8 @@ inline int encode_bf16_map(CUtensorMap* m, void* base, int rank, const uint64_t*
                            const uint32_t* box, CUtensorMapSwizzle swz, bool weights) {
   PFN_encodeTiled fn = get_encode_fn();
   GSD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-  cuuint64_t gd[5];
-  cuuint64_t gs[4];
+  cuuint64_t gd[5] = {1, 1, 1, 1, 1};
+  cuuint64_t gs[4] = {0, 0, 0, 0};
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];

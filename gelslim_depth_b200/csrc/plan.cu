@@ -1,4 +1,6 @@
 // libgsd_b200.so -- plan construction, weight packing and the C ABI (include/gsd_b200.h).
+#include <math.h>
+
 #include <vector>
 
 #include "../../include/gsd_b200.h"
@@ -654,3 +656,5 @@ extern "C" int gsd_op_wgrad3x3_bf16(const void* x0, int C0, const void* x1, int 
   GSD_TRY(build_wgrad_launch(x0, C0, x1 ? x1 : nullptr, x1 ? C1 : 0, H1, W1, off_y, off_x, dz, Cout, B, H, W, dw, sms, &L));
   return run_wgrad_launch(L, static_cast<cudaStream_t>(stream));
 }
+
+#include "train_abi.h"

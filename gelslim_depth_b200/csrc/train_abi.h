@@ -1,0 +1,243 @@
+// C ABI of the training-step operators (included by plan.cu).  Each op is one kernel launch on `stream`.
+#pragma once
+#include "train_ops.cuh"
+
+using namespace gsd;
+
+static int check_dev(int device, const char* who) {
+  GSD_CUDA(cudaSetDevice(device));
+  int major = 0;
+  GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  GSD_CHECK(major == 10, "%s: device %d is not sm_100 (no fallback)", who, device);
+  return 0;
+}
+static int num_sms_of(int device) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return sms;
+}
+
+// Generic conv launch used by the training path: picks the halo-resident or the tap-streaming kernel exactly like
+// the inference plan.  ntaps 9 = 3x3/pad 1, ntaps 1 = pointwise (groups 4: transposed-conv scatter).
+extern "C" int gsd_op_conv_auto_bf16(const void* src0, int C0, const void* src1, int C1, int H1, int W1, int off_y,
+                                     int off_x, int B, int H, int W, const void* w, int Cout, int ntaps, int groups,
+                                     const float* scale, const float* shift, int relu, void* out, void* pooled,
+                                     float* stats, int device, void* stream) {
+  GSD_CHECK(src0 && w && scale && shift && out, "gsd_op_conv_auto_bf16: null argument");
+  GSD_TRY(check_dev(device, "gsd_op_conv_auto_bf16"));
+  ConvDesc d;
+  d.src0 = src0; d.C0 = C0; d.src1 = src1; d.C1 = src1 ? C1 : 0; d.H1 = H1; d.W1 = W1; d.off_y = off_y; d.off_x = off_x;
+  d.B = B; d.H = H; d.W = W; d.w = w; d.Cout = Cout; d.groups = groups;
+  if (ntaps == 9) taps3x3(&d);
+  else { GSD_CHECK(ntaps == 1, "gsd_op_conv_auto_bf16: ntaps must be 9 or 1"); d.ntaps = 1; }
+  d.scale = scale; d.shift = shift; d.relu = relu; d.out = out; d.pooled = pooled; d.stats = stats;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!getenv("GSD_NO_HALO") && halo_supported(d) && halo_tile_efficiency(H, W) >= 0.75) {
+    HaloLaunch L;
+    GSD_TRY(build_halo_launch(d, num_sms_of(device), &L));
+    return run_halo_launch(L, st);
+  }
+  ConvLaunch L;
+  GSD_TRY(build_conv_launch(d, num_sms_of(device), &L));
+  return run_conv_launch(L, st);
+}
+
+// Transposed-conv input gradient: d_in[b,y,x,ci] = sum_{gy,gx,co} dU[b,2y+gy,2x+gx,co] Wt[ci,co,gy,gx]
+// du: dense (B,Hf,Wf,Cs) bf16 with the up-sampled map's gradient at offset (off_y, off_x); w: bf16 [Cin][(gy,gx,co)].
+extern "C" int gsd_op_convt_dgrad_bf16(const void* du, int Cs, int Hf, int Wf, int off_y, int off_x, const void* w, int Cin,
+                                       int B, int H, int W, const float* scale, const float* shift, void* out, int device,
+                                       void* stream) {
+  GSD_CHECK(du && w && out && scale && shift, "gsd_op_convt_dgrad_bf16: null argument");
+  GSD_TRY(check_dev(device, "gsd_op_convt_dgrad_bf16"));
+  ConvDesc d;
+  d.src0 = du; d.C0 = 2 * Cs; d.B = B; d.H = H; d.W = W; d.w = w; d.Cout = Cin; d.groups = 1; d.ntaps = 2;
+  d.s2d = 1; d.s2d_Hf = Hf; d.s2d_Wf = Wf; d.s2d_off_y = off_y; d.s2d_off_x = off_x;
+  d.scale = scale; d.shift = shift; d.relu = 0; d.out = out;
+  ConvLaunch L;
+  GSD_TRY(build_conv_launch(d, num_sms_of(device), &L));
+  return run_conv_launch(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gsd_op_convt_wgrad_bf16(const void* in, int Cin, const void* du, int Cout, int Hf, int Wf, int off_y, int off_x,
+                                       int B, int H, int W, float* dw, int device, void* stream) {
+  GSD_CHECK(in && du && dw, "gsd_op_convt_wgrad_bf16: null argument");
+  GSD_TRY(check_dev(device, "gsd_op_convt_wgrad_bf16"));
+  WgradPwLaunch L;
+  GSD_TRY(build_wgrad_pw_launch(in, Cin, du, Cout, Hf, Wf, off_y, off_x, B, H, W, dw, num_sms_of(device), &L));
+  return run_wgrad_pw_launch(L, static_cast<cudaStream_t>(stream));
+}
+
+// (B,C,Hr,Wr) fp32 NCHW -> NHWC bf16 with channels padded to 16 (+ optional difference image / resample / affine)
+extern "C" int gsd_op_prologue_bf16(const float* x, const float* base, int base_batch, int use_diff, int B, int Cc, int Hr,
+                                    int Wr, int H, int W, const float* scale8_host, const float* shift8_host, void* out16,
+                                    void* stream) {
+  GSD_CHECK(x && out16 && scale8_host && shift8_host && Cc <= 8, "gsd_op_prologue_bf16: bad argument");
+  PreParams p;
+  p.x = x; p.base = use_diff ? base : nullptr; p.base_batch = base_batch; p.use_diff = use_diff;
+  p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W;
+  for (int c = 0; c < 8; ++c) { p.in_scale[c] = scale8_host[c]; p.in_shift[c] = shift8_host[c]; }
+  prologue_kernel<<<ew_grid((long)B * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<__nv_bfloat16*>(out16));
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gsd_op_negate_f32(const float* in, int n, float* out, void* stream) {
+  GSD_CHECK(in && out && n > 0, "gsd_op_negate_f32: bad argument");
+  negate_f32_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gsd_op_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                                  float* running_var, float momentum, float eps, int C, const float* neg_center, float* scale,
+                                  float* shift, float* mean, float* rstd, void* stream) {
+  GSD_CHECK(stats && gamma && beta && scale && shift && mean && rstd && C > 0, "gsd_op_bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, (float)count, gamma, beta, running_mean,
+                                                                                    running_var, momentum, eps, C, neg_center, scale, shift,
+                                                                                    mean, rstd);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gsd_op_bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H, int W, int C, void* a,
+                                    void* pooled, void* stream) {
+  GSD_CHECK(z && scale && shift && a && C % 8 == 0, "gsd_op_bn_relu_apply: bad argument");
+  const long total = (long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  bn_relu_apply_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C, static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(pooled));
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// loss (1 float, accumulated: caller zeroes) and dy = 2 (y - t) / n   (train_unet.py:51-52,370)
+extern "C" int gsd_op_mse(const float* y, const float* t, long long n, float* loss, float* dy, void* stream) {
+  GSD_CHECK(y && t && loss && dy && n > 0, "gsd_op_mse: bad argument");
+  mse_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, t, (long)n, loss, dy);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gsd_op_head_fwd(const void* a, const float* w, const float* bias, int ncls, int B, int H, int W, float* y, void* stream) {
+  GSD_CHECK(a && w && bias && y && ncls >= 1 && ncls <= 4, "gsd_op_head_fwd: bad argument");
+  const long npix = (long)H * W;
+  head_kernel<64><<<ew_grid(npix * B), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), w, bias, ncls, 1.f,
+                                                                                   0.f, npix, B, y);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gsd_op_head_bwd(const void* a, const float* dy, const float* w, int ncls, int B, int H, int W, void* da, float* dw,
+                               float* db, void* stream) {
+  GSD_CHECK(a && dy && w && da && dw && db && ncls >= 1 && ncls <= 4, "gsd_op_head_bwd: bad argument");
+  const long npix = (long)H * W;
+  long tiles = (npix * B + 127) / 128;
+  int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+  head_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), dy, w, npix, B, ncls,
+                                                                      static_cast<__nv_bfloat16*>(da), dw, db);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int reduce_grid(int C, long npix, int* grid, int* block) {
+  const int C8 = C / 8;
+  *block = 256;
+  // total threads must be a multiple of C8 so that a thread always sees the same channel chunk
+  long want = 148L * 4 * 256;
+  long threads = (want / C8) * C8;
+  if (threads < C8) threads = C8;
+  // keep it a multiple of 256 as well: lcm(C8, 256); C8 is a power of two times {1} for C in {64..1024}
+  long step = C8 > 256 ? C8 : 256;
+  threads = (threads / step) * step;
+  if (threads < step) threads = step;
+  long maxthreads = ((npix * C8 + step - 1) / step) * step;
+  if (threads > maxthreads) threads = maxthreads;
+  *grid = (int)(threads / 256);
+  if (*grid < 1) *grid = 1;
+  return 0;
+}
+
+// sums[0..C) = sum g, sums[C..2C) = sum g*zhat (accumulated; caller zeroes).  a/z/mean/rstd may be NULL together:
+// then it is a plain per-channel sum of `da`.
+extern "C" int gsd_op_bn_bwd_reduce(const void* da, const void* a, const void* z, const float* mean, const float* rstd,
+                                    long long npix, int C, float* sums, void* stream) {
+  GSD_CHECK(da && sums && C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "gsd_op_bn_bwd_reduce: C/8 must be a power of two");
+  int grid, block;
+  reduce_grid(C, (long)npix, &grid, &block);
+  bn_bwd_reduce_kernel<<<grid, block, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(z), mean, rstd,
+      (long)npix, C, C, sums);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gsd_op_bn_bwd_apply(const void* da, const void* a, const void* z, const float* mean, const float* rstd,
+                                   const float* gamma, const float* sums, double count, long long npix, int C, void* dz, void* stream) {
+  GSD_CHECK(da && a && z && mean && rstd && gamma && sums && dz && C % 8 == 0, "gsd_op_bn_bwd_apply: bad argument");
+  bn_bwd_apply_kernel<<<ew_grid((long)npix * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
+      sums, (float)count, (long)npix, C, C, static_cast<__nv_bfloat16*>(dz));
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* dskip, int B, int H, int W, int C, void* dfull,
+                                  void* stream) {
+  GSD_CHECK(a && dpool && dfull && C % 8 == 0, "gsd_op_maxpool_bwd: bad argument");
+  const long total = (long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  maxpool_bwd_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(dpool), static_cast<const __nv_bfloat16*>(dskip), C, B, H, W, C,
+      static_cast<__nv_bfloat16*>(dfull));
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// mode 0: Conv2d (O,I,3,3) -> forward operand [O][9][Ipad];  1: -> dgrad operand [I][9][O] (flipped taps)
+// mode 2: ConvTranspose2d (I,O,2,2) -> forward operand [(g)*O+o][I];  3: -> its dgrad operand [I][(g, o)]
+extern "C" int gsd_op_pack_weight(int mode, const float* w, int O, int I, int Ipad, void* out, void* stream) {
+  GSD_CHECK(w && out, "gsd_op_pack_weight: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  switch (mode) {
+    case 0: pack_conv_weight_kernel<<<ew_grid((long)O * 9 * Ipad), 256, 0, st>>>(w, O, I, 9, Ipad, o); break;
+    case 1: pack_dgrad_weight_kernel<<<ew_grid((long)O * 9 * I), 256, 0, st>>>(w, O, I, o); break;
+    case 2: pack_convt_weight_kernel<<<ew_grid(4L * O * I), 256, 0, st>>>(w, I, O, o); break;
+    case 3: pack_convt_dgrad_weight_kernel<<<ew_grid(4L * O * I), 256, 0, st>>>(w, I, O, o); break;
+    default: return fail(-1, "gsd_op_pack_weight: unknown mode %d", mode);
+  }
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gsd_op_unpack_wgrad(const float* dwk, int O, int I, int Ipad, float* grad, void* stream) {
+  GSD_CHECK(dwk && grad, "gsd_op_unpack_wgrad: null argument");
+  unpack_wgrad_kernel<<<ew_grid((long)O * I * 9), 256, 0, static_cast<cudaStream_t>(stream)>>>(dwk, O, I, Ipad, grad);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// first conv (K = 27/54): dw[64][9][16] += ...   (x16: NHWC bf16 padded to 16 channels, dz: (B,H,W,64))
+extern "C" int gsd_op_wgrad_first(const void* x16, const void* dz, int B, int H, int W, int Cin, float* dw, void* stream) {
+  GSD_CHECK(x16 && dz && dw && Cin >= 1 && Cin <= 16, "gsd_op_wgrad_first: bad argument");
+  dim3 grid(9 * Cin, 128);
+  wgrad_first_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x16),
+                                                                         static_cast<const __nv_bfloat16*>(dz), B, H, W, Cin, dw);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Adam (coupled L2) + EMA over a flat fp32 arena of n elements; step is 1-based; shadow may be NULL (no EMA).
+// grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
+extern "C" int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, float* shadow, long long n, float lr, float beta1,
+                               float beta2, float eps, float weight_decay, long long step, float ema_decay, long long ema_updates,
+                               float grad_scale, void* stream) {
+  GSD_CHECK(p && g && m && v && n > 0 && step >= 1, "gsd_op_adam_ema: bad argument");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  double d = ema_decay;
+  const double warm = (1.0 + (double)ema_updates) / (10.0 + (double)ema_updates);   // torch_ema use_num_updates
+  if (warm < d) d = warm;
+  adam_ema_kernel<<<ew_grid((long)n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, shadow, (long)n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), (float)(1.0 - d), grad_scale);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,399 @@
+// Memory-bound kernels of the training step (train_utils/train_unet.py:346-377): train-mode BatchNorm
+// (finalize / apply / backward), fused MSE loss + gradient, 1x1 head backward, max-pool backward, reductions,
+// and the fused Adam(+coupled L2)+EMA update.  NHWC bf16 activations, fp32 statistics and parameter gradients.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gsd {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// BatchNorm2d in .train() (unet.py:12,15): batch mean / biased variance from the (sum, sum of squares) the conv
+// epilogue accumulated; running statistics updated with momentum and the UNBIASED variance (PyTorch semantics).
+// `center` (or null): the conv stored z' = z - center[c] (center = the running mean BEFORE this step): bf16 then rounds
+// relative to the fluctuation of z, not to |mean| + fluctuation.  All outputs refer to the stored z'.
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps, int C,
+                                   const float* __restrict__ neg_center, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = stats[c] / count;
+  float var = stats[C + c] / count - mean * mean;
+  var = fmaxf(var, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float s = gamma[c] * rstd;
+  const float mean_c = mean + (neg_center ? neg_center[c] : 0.f);     // batch mean of the stored (centred) tensor
+  scale[c] = s;
+  shift[c] = beta[c] - mean_c * s;
+  mean_out[c] = mean_c;
+  rstd_out[c] = rstd;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+  }
+}
+
+__global__ void negate_f32_kernel(const float* __restrict__ in, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = -in[i];
+}
+
+// a = relu(z * scale + shift) (+ 2x2 max-pooled copy).  One thread = one 2x2 window x 8 channels.
+__global__ void __launch_bounds__(256) bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, int B, int H, int W, int C,
+                                                            __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ pooled) {
+  const int Hw = (H + 1) / 2, Ww = (W + 1) / 2, Hp = H / 2, Wp = W / 2, C8 = C / 8;
+  const long total = (long)B * Hw * Ww * C8;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % C8);
+    const int wx = (int)((idx / C8) % Ww);
+    const int wy = (int)((idx / ((long)C8 * Ww)) % Hw);
+    const long b = idx / ((long)C8 * Ww * Hw);
+    float sc[8], sh[8], mx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[c8 * 8 + j]; sh[j] = shift[c8 * 8 + j]; mx[j] = 0.f; }   // relu output >= 0
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y = 2 * wy + dy, x = 2 * wx + dx;
+        if (y < H && x < W) {
+          const long off = ((b * H + y) * W + x) * C + c8 * 8;
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4*>(z + off), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j] * sc[j] + sh[j], 0.f);
+          const uint4 o = pack8(f);
+          *reinterpret_cast<uint4*>(a + off) = o;
+          float r[8];
+          unpack8(o, r);                          // pool the ROUNDED values: pooled == max_pool2d(a) exactly
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], r[j]);
+        }
+      }
+    if (pooled && wy < Hp && wx < Wp) *reinterpret_cast<uint4*>(pooled + ((b * Hp + wy) * Wp + wx) * C + c8 * 8) = pack8(mx);
+  }
+}
+
+// MSE_loss (train_unet.py:51-52) and its gradient: loss += sum((y-t)^2)/n ; dy = 2 (y-t) / n
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ y, const float* __restrict__ t, long n,
+                                                  float* __restrict__ loss, float* __restrict__ dy) {
+  float acc = 0.f;
+  const float inv = 1.f / (float)n;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n; idx += (long)gridDim.x * blockDim.x) {
+    const float d = y[idx] - t[idx];
+    acc += d * d;
+    dy[idx] = 2.f * d * inv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += part[i];
+    atomicAdd(loss, s * inv);
+  }
+}
+
+// OutConv backward (unet.py:54): da[pix][c] = sum_k dy[k][pix] w[k][c]; dw[k][c] += sum_pix dy a; db[k] += sum dy.
+// 128 threads; per 128-pixel tile: phase 1 thread = pixel, phase 2 thread = (k, c) pair.
+__global__ void __launch_bounds__(128) head_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ dy,
+                                                       const float* __restrict__ w, long npix_per_img, int B, int ncls,
+                                                       __nv_bfloat16* __restrict__ da, float* __restrict__ dw,
+                                                       float* __restrict__ db) {
+  __shared__ float s_w[4 * 64];
+  __shared__ float s_dy[4][128];
+  __shared__ __nv_bfloat16 s_a[128][64 + 8];
+  for (int i = threadIdx.x; i < ncls * 64; i += 128) s_w[i] = w[i];
+  float acc_w[2] = {0.f, 0.f};      // (k, c) pairs: index t and t+128 (ncls <= 4 -> 256 pairs)
+  float acc_b = 0.f;
+  const long total = npix_per_img * B;
+  for (long t0 = (long)blockIdx.x * 128; t0 < total; t0 += (long)gridDim.x * 128) {
+    __syncthreads();
+    const long pix = t0 + threadIdx.x;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pix < total) {
+      const long b = pix / npix_per_img, pp = pix - b * npix_per_img;
+      for (int k = 0; k < ncls; ++k) g[k] = dy[(b * ncls + k) * npix_per_img + pp];
+      const uint4* src = reinterpret_cast<const uint4*>(a + pix * 64);
+      uint4* dst = reinterpret_cast<uint4*>(da + pix * 64);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        *reinterpret_cast<uint4*>(&s_a[threadIdx.x][ch * 8]) = src[ch];
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = 0.f;
+          for (int k = 0; k < ncls; ++k) v = fmaf(g[k], s_w[k * 64 + ch * 8 + j], v);
+          f[j] = v;
+        }
+        dst[ch] = pack8(f);
+      }
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(&s_a[threadIdx.x][ch * 8]) = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_dy[k][threadIdx.x] = g[k];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int pair = threadIdx.x + 128 * r;
+      const int k = pair >> 6, c = pair & 63;
+      if (k < ncls) {
+        float s = 0.f;
+        for (int pz = 0; pz < 128; ++pz) s = fmaf(s_dy[k][pz], __bfloat162float(s_a[pz][c]), s);
+        acc_w[r] += s;
+      }
+    }
+    if (threadIdx.x < ncls) {
+      float s = 0.f;
+      for (int pz = 0; pz < 128; ++pz) s += s_dy[threadIdx.x][pz];
+      acc_b += s;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int pair = threadIdx.x + 128 * r;
+    if ((pair >> 6) < ncls) atomicAdd(dw + pair, acc_w[r]);
+  }
+  if (threadIdx.x < ncls) atomicAdd(db + threadIdx.x, acc_b);
+}
+
+// BatchNorm+ReLU backward, reduction pass: sums[c] = sum g, sums[C+c] = sum g*zhat, g = da*(a>0), zhat=(z-mean)*rstd.
+// With `a == nullptr` there is no ReLU (plain per-channel sum of da: transposed-conv bias gradient).
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ a,
+                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, long npix, int C, long da_pix_stride,
+                                                            float* __restrict__ sums) {
+  // thread -> fixed 8-channel chunk; pixels strided.  blockDim.x * gridDim.x must be a multiple of C/8 (host).
+  const int C8 = C / 8;
+  const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const int c8 = (int)(tid % C8);
+  const long p0 = tid / C8, pstep = ((long)gridDim.x * blockDim.x) / C8;
+  float s1[8], s2[8], mu[8], rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = z ? mean[c8 * 8 + j] : 0.f; rs[j] = z ? rstd[c8 * 8 + j] : 0.f; }
+  for (long px = p0; px < npix; px += pstep) {
+    float g[8];
+    unpack8(*reinterpret_cast<const uint4*>(da + px * da_pix_stride + c8 * 8), g);
+    if (a) {
+      float av[8], zv[8];
+      unpack8(*reinterpret_cast<const uint4*>(a + px * C + c8 * 8), av);
+      unpack8(*reinterpret_cast<const uint4*>(z + px * C + c8 * 8), zv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = av[j] > 0.f ? g[j] : 0.f;
+        s1[j] += gg;
+        s2[j] += gg * (zv[j] - mu[j]) * rs[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s1[j] += g[j];
+    }
+  }
+  // block reduce per chunk through smem atomics, then one global atomic per channel per block
+  extern __shared__ float sh[];   // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sh[c8 * 8 + j], s1[j]);
+    if (a) atomicAdd(&sh[C + c8 * 8 + j], s2[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
+    if (sh[i] != 0.f) atomicAdd(sums + i, sh[i]);
+}
+
+// BatchNorm+ReLU backward, apply pass: dz = gamma*rstd*(g - sum_g/n - zhat*sum_gz/n)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ a,
+                                                           const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ sums, float count, long npix, int C,
+                                                           long da_pix_stride, __nv_bfloat16* __restrict__ dz) {
+  const int C8 = C / 8;
+  const long total = npix * C8;
+  const float inv = 1.f / count;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % C8);
+    const long px = idx / C8;
+    float g[8], av[8], zv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(da + px * da_pix_stride + c8 * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(a + px * C + c8 * 8), av);
+    unpack8(*reinterpret_cast<const uint4*>(z + px * C + c8 * 8), zv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      const float gg = av[j] > 0.f ? g[j] : 0.f;
+      const float zh = (zv[j] - mean[c]) * rstd[c];
+      o[j] = gamma[c] * rstd[c] * (gg - sums[c] * inv - zh * sums[C + c] * inv);
+    }
+    *reinterpret_cast<uint4*>(dz + px * C + c8 * 8) = pack8(o);
+  }
+}
+
+// MaxPool2d(2) backward (unet.py:26) fused with the skip-connection gradient:
+//   dfull[y,x] = dskip[y,x] (optional, pixel stride `skip_stride` elements) + (argmax of its window ? dpool : 0)
+// argmax = FIRST maximum in row-major window order (PyTorch's tie rule).
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ dpool,
+                                                          const __nv_bfloat16* __restrict__ dskip, long skip_stride, int B, int H,
+                                                          int W, int C, __nv_bfloat16* __restrict__ dfull) {
+  const int Hw = (H + 1) / 2, Ww = (W + 1) / 2, Hp = H / 2, Wp = W / 2, C8 = C / 8;
+  const long total = (long)B * Hw * Ww * C8;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % C8);
+    const int wx = (int)((idx / C8) % Ww);
+    const int wy = (int)((idx / ((long)C8 * Ww)) % Hw);
+    const long b = idx / ((long)C8 * Ww * Hw);
+    const bool inwin = wy < Hp && wx < Wp;
+    float av[4][8], dp[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { arg[j] = 0; dp[j] = 0.f; }
+    if (inwin) {
+      unpack8(*reinterpret_cast<const uint4*>(dpool + ((b * Hp + wy) * Wp + wx) * C + c8 * 8), dp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        unpack8(*reinterpret_cast<const uint4*>(a + ((b * H + 2 * wy + (q >> 1)) * W + 2 * wx + (q & 1)) * C + c8 * 8), av[q]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float m = av[0][j];
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+          if (av[q][j] > m) { m = av[q][j]; arg[j] = q; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int y = 2 * wy + (q >> 1), x = 2 * wx + (q & 1);
+      if (y < H && x < W) {
+        const long pix = (b * H + y) * W + x;
+        float o[8];
+        if (dskip) unpack8(*reinterpret_cast<const uint4*>(dskip + pix * skip_stride + c8 * 8), o);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        }
+        if (inwin) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (arg[j] == q) o[j] += dp[j];
+        }
+        *reinterpret_cast<uint4*>(dfull + pix * C + c8 * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// conv weight for dgrad: W (O,I,3,3) fp32 -> bf16 [n = ci][tap'][k = co] with W[co][ci][8 - tap'] (flipped taps)
+__global__ void pack_dgrad_weight_kernel(const float* __restrict__ w, int O, int I, __nv_bfloat16* __restrict__ out) {
+  const long total = (long)I * 9 * O;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % O);
+    const int t = (int)((idx / O) % 9);
+    const int ci = (int)(idx / ((long)O * 9));
+    out[idx] = __float2bfloat16_rn(w[((long)co * I + ci) * 9 + (8 - t)]);
+  }
+}
+// transposed-conv weight for ITS dgrad: Wt (I,O,2,2) fp32 -> bf16 [n = ci][k = (gy, gx, co)]
+__global__ void pack_convt_dgrad_weight_kernel(const float* __restrict__ w, int I, int O, __nv_bfloat16* __restrict__ out) {
+  const long total = (long)I * 4 * O;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % O);
+    const int g = (int)((idx / O) % 4);
+    const int ci = (int)(idx / ((long)O * 4));
+    out[idx] = __float2bfloat16_rn(w[((long)ci * O + co) * 4 + g]);
+  }
+}
+// wgrad arena [O][9][Ipad] fp32 -> parameter gradient (O,I,3,3) fp32
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwk, int O, int I, int Ipad, float* __restrict__ grad) {
+  const long total = (long)O * I * 9;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % 9);
+    const int i = (int)((idx / 9) % I);
+    const int o = (int)(idx / (9L * I));
+    grad[idx] = dwk[((long)o * 9 + t) * Ipad + i];
+  }
+}
+
+// First-layer weight gradient (K = 27/54, HBM-bound): dw[co][tap][c] += sum_pix dz[pix][co] * x16[pix+tap][c], c < Cin.
+// One block per (tap, c); threads over co (64); pixels strided over blockIdx.y.
+__global__ void __launch_bounds__(64) wgrad_first_kernel(const __nv_bfloat16* __restrict__ x16, const __nv_bfloat16* __restrict__ dz,
+                                                         int B, int H, int W, int Cin, float* __restrict__ dw /*[64][9][16]*/) {
+  const int tap = blockIdx.x / Cin, c = blockIdx.x % Cin;
+  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+  const int co = threadIdx.x;
+  const long npix = (long)B * H * W;
+  float acc = 0.f;
+  for (long px = blockIdx.y; px < npix; px += gridDim.y) {
+    const int x = (int)(px % W), y = (int)((px / W) % H);
+    const long b = px / ((long)W * H);
+    const int ys = y + dy, xs = x + dx;
+    if (ys < 0 || ys >= H || xs < 0 || xs >= W) continue;
+    const float xv = __bfloat162float(x16[((b * H + ys) * W + xs) * 16 + c]);
+    acc = fmaf(__bfloat162float(dz[px * 64 + co]), xv, acc);
+  }
+  atomicAdd(dw + ((long)co * 9 + tap) * 16 + c, acc);
+}
+
+// Adam with coupled L2 (torch.optim.Adam(lr, betas, eps, weight_decay), train_unet.py:306,375) fused with the
+// torch_ema==0.3 shadow update (train_unet.py:309,376), over one flat fp32 arena:
+//   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+//   shadow -= (1-d)*(shadow - p)
+__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, float* __restrict__ shadow, long n, float lr,
+                                                       float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                                       float ema_one_minus_d, float grad_scale) {
+  const long n4 = n / 4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float4 ss = shadow ? reinterpret_cast<float4*>(shadow)[i] : make_float4(0, 0, 0, 0);
+    float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x; float* S = &ss.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = G[j] * grad_scale + wd * P[j];
+      M[j] = b1 * M[j] + (1.f - b1) * gr;
+      V[j] = b2 * V[j] + (1.f - b2) * gr * gr;
+      P[j] -= (lr / bc1) * M[j] / (sqrtf(V[j]) / bc2_sqrt + eps);
+      S[j] -= ema_one_minus_d * (S[j] - P[j]);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) reinterpret_cast<float4*>(shadow)[i] = ss;
+  }
+  for (long i = n4 * 4 + blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gr = g[i] * grad_scale + wd * p[i];
+    m[i] = b1 * m[i] + (1.f - b1) * gr;
+    v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
+    p[i] -= (lr / bc1) * m[i] / (sqrtf(v[i]) / bc2_sqrt + eps);
+    if (shadow) shadow[i] -= ema_one_minus_d * (shadow[i] - p[i]);
+  }
+}
+
+}  // namespace gsd

@@ -158,3 +158,119 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 }
 
 }  // namespace gsd
+
+// ------------------------------------------------------------------------------------------------
+// Transposed-conv (k=2, s=2) weight gradient, same GEMM-over-pixels scheme without the halo:
+//   dWt[ci][co][gy][gx] += sum_{b,y,x} IN[b,y,x,ci] * dU[b, 2y+gy, 2x+gx, co]
+// A = IN tile (M = 128 ci = two 64-channel boxes), B_g = the g-th stride-2 view of dU (N = 64 co), 4 accumulators.
+namespace gsd {
+
+constexpr int kWpStageBytes = 2 * kWgDzBytes + 4 * kWgDzBytes;   // 96 KB
+
+struct WgradPwParams {
+  CUtensorMap tm_in;      // (Cin, W, H, B), box (64, 8, 16, 1)
+  CUtensorMap tm_du[4];   // stride-2 views of dU: (Cout, W, H, B), box (64, 8, 16, 1)
+  float* dw;              // (Cin, Cout, 2, 2) fp32, accumulated
+  int tiles_x, tiles_y, batch;
+  int Cin, Cout;
+  int split;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_pw_kernel(const __grid_constant__ WgradPwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int stages = 2;
+  const uint32_t s_stage = smem_base;
+  const uint32_t s_bar = s_stage + stages * kWpStageBytes;
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * stages, bar_done = bar_empty + 8 * stages;
+  const uint32_t s_tmem_slot = bar_done + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<256>(s_tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // blockIdx.x = (ci_blk * co_blocks + co_blk) * split + s
+  const int co_blocks = p.Cout / 64;
+  int bid = blockIdx.x;
+  const int s = bid % p.split; bid /= p.split;
+  const int co_blk = bid % co_blocks;
+  const int ci_blk = bid / co_blocks;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int t = s; t < m_tiles; t += p.split) {
+        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+        mbar_wait(bar_empty + 8 * st, ph ^ 1);
+        const uint32_t sa = s_stage + st * kWpStageBytes, fb = bar_full + 8 * st;
+        mbar_arrive_expect_tx(fb, kWpStageBytes);
+        tma_load_4d(sa, &p.tm_in, fb, ci_blk * 128, tx * 8, ty * 16, b);
+        tma_load_4d(sa + kWgDzBytes, &p.tm_in, fb, ci_blk * 128 + 64, tx * 8, ty * 16, b);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tma_load_4d(sa + (2 + g) * kWgDzBytes, &p.tm_du[g], fb, co_blk * 64, tx * 8, ty * 16, b);
+        if (++st == stages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    int st = 0; uint32_t ph = 0;
+    bool first = true;
+    for (int t = s; t < m_tiles; t += p.split) {
+      mbar_wait(bar_full + 8 * st, ph);
+      tc_fence_after();
+      const uint32_t sa = s_stage + st * kWpStageBytes;
+      if (elect_one()) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t a_lo = mn_desc_lo(sa + k * 2048, kWgDzBytes);
+            const uint32_t b_lo = mn_desc_lo(sa + (2 + g) * kWgDzBytes + k * 2048, 0);
+            umma_bf16_lohi(tmem_base + g * 64, a_lo, mn_desc_hi(1024), b_lo, mn_desc_hi(1024), idesc, (first && k == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(bar_empty + 8 * st);
+      }
+      __syncwarp();
+      first = false;
+      if (++st == stages) { st = 0; ph ^= 1; }
+    }
+    if (elect_one()) umma_commit(bar_done);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int ci = ci_blk * 128 + q * 32 + lane;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const bool live = s < m_tiles && ci < p.Cin;
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + g * 64 + c0 + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (live) {
+          float* dst = p.dw + ((size_t)ci * p.Cout + co_blk * 64 + c0) * 4 + g;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + 4 * i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<256>(tmem_base);
+}
+
+}  // namespace gsd

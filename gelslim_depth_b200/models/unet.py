@@ -146,8 +146,11 @@ class UNet(nn.Module):
         if x.dim() != 4 or x.shape[1] != self.n_channels:
             raise ValueError(f"expected (N, {self.n_channels}, H, W), got {tuple(x.shape)}")
         if self.training:
-            raise NotImplementedError("train-mode forward (batch-statistics BatchNorm + backward) is not part of "
-                                      "this build yet; call .eval()")
+            # batch-statistics BatchNorm + autograd bridge to the backward kernels (train_unet.py:347,374)
+            if pp is not None or self.precision != "bf16":
+                raise NotImplementedError("train mode runs the plain bf16 network (no fused pre/post-processing, no fp32 mode)")
+            from ..train.engine import unet_train_forward
+            return unet_train_forward(self, x.contiguous().float())
         x = x.contiguous().float()
         n, _, h, w = x.shape
         nh, nw = net_hw if net_hw is not None else (h, w)

@@ -1,0 +1,239 @@
+"""Training step of the U-Net on B200: train-mode forward, backward and (optionally) the fused Adam+EMA update.
+
+Mirrors the loop body of train_utils/train_unet.py:346-377:
+    optimizer.zero_grad(); output = unet(x=input); loss = MSE(output, target); loss.backward();
+    optimizer.step(); ema.update()
+Every FLOP runs in libgsd_b200.so: conv forward / dgrad on the halo-resident tcgen05 kernel, wgrad as a tcgen05 GEMM
+over pixels, BatchNorm statistics in the conv epilogue, everything else as fused memory-bound kernels
+(csrc/train_ops.cuh).  This module only sequences the launches and owns no arithmetic.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+class _Unit:
+    """saved tensors of one conv3x3 -> BatchNorm -> ReLU unit"""
+    __slots__ = ("src0", "src1", "off", "z", "a", "mean", "rstd", "pooled", "conv", "bn", "first")
+
+
+def _blocks(net):
+    enc = [net.inc.double_conv] + [d.maxpool_conv[1].double_conv for d in net.down]
+    dec = [(u.up, u.conv.double_conv) for u in net.up]
+    return enc, dec
+
+
+class PackedTrainWeights:
+    """bf16 GEMM operands of every layer for forward and for dgrad; rebuilt after each optimizer step."""
+
+    def __init__(self, net):
+        enc, dec = _blocks(net)
+        self.fwd, self.dgrad = {}, {}
+        for bi, seq in enumerate(enc):
+            for ci in (0, 3):
+                w = seq[ci].weight.detach()
+                O, I = w.shape[:2]
+                ipad = 16 if (bi == 0 and ci == 0) else I
+                self.fwd[id(seq[ci])] = ops.pack_weight(0, w, O, I, ipad)
+                if not (bi == 0 and ci == 0):
+                    self.dgrad[id(seq[ci])] = ops.pack_weight(1, w, O, I)
+        for up, seq in dec:
+            w = up.weight.detach()
+            I, O = w.shape[:2]
+            self.fwd[id(up)] = ops.pack_weight(2, w, O, I)
+            self.dgrad[id(up)] = ops.pack_weight(3, w, O, I)
+            for ci in (0, 3):
+                cw = seq[ci].weight.detach()
+                self.fwd[id(seq[ci])] = ops.pack_weight(0, cw, cw.shape[0], cw.shape[1])
+                self.dgrad[id(seq[ci])] = ops.pack_weight(1, cw, cw.shape[0], cw.shape[1])
+
+
+def _unit_forward(conv: nn.Conv2d, bn: nn.BatchNorm2d, pw: PackedTrainWeights, src0, src1=None, off=(0, 0), pool=False, first=False):
+    B, H, W, _ = src0.shape
+    cout = conv.out_channels
+    stats = torch.zeros(2 * cout, dtype=torch.float32, device=src0.device)
+    # z is stored centred on the running mean (bf16 then rounds relative to the fluctuation of z, not to its mean);
+    # the batch statistics are taken from the raw fp32 accumulators in the conv epilogue.
+    neg_center = ops.negate(bn.running_mean)
+    z = ops.conv(src0, pw.fwd[id(conv)], cout, 9, src1=src1, off=off, shift=neg_center, stats=stats)
+    scale, shift, mean, rstd = ops.bn_finalize(stats, B * H * W, bn, neg_center)              # + running stats (momentum 0.1)
+    bn.num_batches_tracked += 1
+    a, pooled = ops.bn_relu_apply(z, scale, shift, pool=pool)
+    u = _Unit()
+    u.src0, u.src1, u.off, u.z, u.a, u.mean, u.rstd, u.pooled, u.conv, u.bn, u.first = src0, src1, off, z, a, mean, rstd, pooled, conv, bn, first
+    return u
+
+
+def train_forward(net, x: torch.Tensor, pw: PackedTrainWeights):
+    """-> (y fp32 NCHW, saved context).  BatchNorm uses batch statistics and updates its running buffers."""
+    enc, dec = _blocks(net)
+    depth = len(enc) - 1
+    ctx = {"enc": [], "dec": []}
+    cur = ops.prologue(x.contiguous().float())
+    ctx["in16"] = cur
+    for l, seq in enumerate(enc):
+        u1 = _unit_forward(seq[0], seq[1], pw, cur, first=(l == 0))
+        u2 = _unit_forward(seq[3], seq[4], pw, u1.a, pool=(l < depth))
+        ctx["enc"].append((u1, u2))
+        cur = u2.pooled if l < depth else u2.a
+    y_prev = ctx["enc"][depth][1].a
+    for i, (up, seq) in enumerate(dec):
+        l = depth - 1 - i
+        skip = ctx["enc"][l][1].a
+        cup = up.out_channels
+        dev = y_prev.device
+        u = ops.conv(y_prev, pw.fwd[id(up)], cup, ntaps=1, groups=4, scale=ops.ones(dev, 4 * cup), shift=up.bias.detach().repeat(4))
+        off = ((skip.shape[1] - u.shape[1]) // 2, (skip.shape[2] - u.shape[2]) // 2)           # F.pad left/top (unet.py:46-47)
+        u1 = _unit_forward(seq[0], seq[1], pw, skip, src1=u, off=off)
+        u2 = _unit_forward(seq[3], seq[4], pw, u1.a)
+        ctx["dec"].append((up, y_prev, u, off, u1, u2))
+        y_prev = u2.a
+    w_head = net.outc.conv.weight.detach().reshape(net.n_classes, -1)
+    y = ops.head_fwd(y_prev, w_head, net.outc.conv.bias.detach())
+    ctx["a_last"] = y_prev
+    return y, ctx
+
+
+def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: dict, need_dx: bool, split: int = 0):
+    """backward of conv -> BN -> ReLU.  Returns the input gradient(s) (None if not needed).
+    split > 0: the conv input was the virtual concat [skip | up]; returns (dskip, dup_full)."""
+    B, H, W, Cn = u.a.shape
+    dz, sums = ops.bn_bwd(da, u.a, u.z, u.mean, u.rstd, u.bn.weight.detach(), B * H * W)
+    grads[u.bn.bias] = sums[:Cn]
+    grads[u.bn.weight] = sums[Cn:]
+    gw = torch.empty_like(u.conv.weight)
+    if u.first:
+        ops.wgrad_first(u.src0, dz, u.conv.in_channels, gw)
+    else:
+        ops.wgrad3x3(u.src0, dz, gw, x1=u.src1, off=u.off)
+    grads[u.conv.weight] = gw
+    if not need_dx:
+        return None
+    wd = pw.dgrad[id(u.conv)]                                   # [ci][9][co]
+    cin = u.conv.in_channels
+    if split:
+        rows = split * 9 * Cn
+        dskip = ops.conv(dz, wd[:rows], split, 9)
+        dup = ops.conv(dz, wd[rows:], cin - split, 9)
+        return dskip, dup
+    return ops.conv(dz, wd, cin, 9)
+
+
+def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights) -> List[torch.Tensor]:
+    """dy: gradient of the loss w.r.t. the network output (fp32 NCHW).  Returns gradients in net.parameters() order."""
+    enc, dec = _blocks(net)
+    depth = len(enc) - 1
+    grads = {}
+    dev = dy.device
+    w_head = net.outc.conv.weight.detach().reshape(net.n_classes, -1)
+    dwh = torch.zeros_like(w_head)
+    dbh = torch.zeros(net.n_classes, dtype=torch.float32, device=dev)
+    da = ops.head_bwd(ctx["a_last"], dy.contiguous().float(), w_head, dwh, dbh)
+    grads[net.outc.conv.weight] = dwh.reshape_as(net.outc.conv.weight)
+    grads[net.outc.conv.bias] = dbh
+    dskips = [None] * (depth + 1)
+    # ---- decoder, last block first
+    for i in range(depth - 1, -1, -1):
+        up, y_prev, u, off, u1, u2 = ctx["dec"][i]
+        da1 = _unit_backward(u2, da, pw, grads, need_dx=True)
+        cskip = u1.src0.shape[-1]
+        dskip, dup = _unit_backward(u1, da1, pw, grads, need_dx=True, split=cskip)
+        l = depth - 1 - i
+        dskips[l] = dskip
+        # transposed conv: only the (2hs x 2ws) window of dup at `off` is its output gradient (the rest is F.pad)
+        hs, ws = y_prev.shape[1], y_prev.shape[2]
+        if dup.shape[1] != 2 * hs or dup.shape[2] != 2 * ws:
+            dup[:, : off[0]] = 0
+            dup[:, off[0] + 2 * hs:] = 0
+            dup[:, :, : off[1]] = 0
+            dup[:, :, off[1] + 2 * ws:] = 0
+        grads[up.bias] = ops.channel_sum(dup)
+        gw = torch.empty_like(up.weight)
+        ops.convt_wgrad(y_prev, dup, off, gw)
+        grads[up.weight] = gw
+        da = ops.convt_dgrad(dup, off, pw.dgrad[id(up)], up.in_channels, hs, ws)
+    # ---- encoder, bottom up: `da` is now the gradient of enc[depth]'s output
+    for l in range(depth, -1, -1):
+        u1, u2 = ctx["enc"][l]
+        if l < depth:
+            da = ops.maxpool_bwd(u2.a, dpool, dskips[l])      # noqa: F821  (dpool from level l+1) + skip-connection gradient
+        da1 = _unit_backward(u2, da, pw, grads, need_dx=True)
+        dpool = _unit_backward(u1, da1, pw, grads, need_dx=(l > 0))
+    return [grads[p] for p in net.parameters()]
+
+
+class _TrainFn(torch.autograd.Function):
+    """autograd bridge: `output = unet(x=...)` in .train() mode; `loss.backward()` lands here."""
+
+    @staticmethod
+    def forward(fctx, net, x, *params):
+        pw = PackedTrainWeights(net)
+        y, ctx = train_forward(net, x, pw)
+        fctx.net, fctx.saved, fctx.pw = net, ctx, pw
+        return y
+
+    @staticmethod
+    def backward(fctx, dy):
+        grads = train_backward(fctx.net, fctx.saved, dy, fctx.pw)
+        fctx.saved = None
+        return (None, None, *grads)
+
+
+def unet_train_forward(net, x):
+    return _TrainFn.apply(net, x, *list(net.parameters()))
+
+
+class FusedTrainer:
+    """The whole loop body of train_unet.py:346-377 with the loss, Adam (coupled L2) and the torch_ema update fused:
+    parameters, Adam moments and the EMA shadow live in flat fp32 arenas (one kernel updates all 64 tensors);
+    data-parallel replicas all-reduce the flat gradient arena over NCCL, bucketed in backward order."""
+
+    def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, ema_decay=0.995, process_group=None):
+        self.net = net
+        self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
+        params = list(net.parameters())
+        n = sum(p.numel() for p in params)
+        n_pad = (n + 3) // 4 * 4
+        dev = params[0].device
+        self.flat_p = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        off = 0
+        self.views = []
+        for p in params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)          # parameters now alias the arena
+            self.views.append((off, k))
+            off += k
+        self.shadow = self.flat_p.clone()                         # torch_ema: shadow = [p.clone()]
+        self.step_count, self.ema_updates = 0, 0
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+
+    def step(self, x, target) -> torch.Tensor:
+        """one training step; returns the loss as a 1-element device tensor (no host sync)."""
+        net = self.net
+        pw = PackedTrainWeights(net)
+        y, ctx = train_forward(net, x, pw)
+        loss, dy = ops.mse(y, target.contiguous().float())
+        grads = train_backward(net, ctx, dy, pw)
+        for (off, k), g in zip(self.views, grads):
+            self.flat_g[off:off + k].copy_(g.reshape(-1))
+        scale = 1.0
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+            scale = 1.0 / self.world
+        self.step_count += 1
+        self.ema_updates += 1
+        ops.adam_ema(self.flat_p, self.flat_g, self.m, self.v, self.shadow, self.lr, self.betas, self.eps, self.wd,
+                     self.step_count, self.ema_decay, self.ema_updates, grad_scale=scale)
+        return loss

@@ -151,6 +151,63 @@ int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* src1, int C1,
 int gsd_op_wgrad3x3_bf16(const void* x0, int C0, const void* x1, int C1, int H1, int W1, int off_y, int off_x,
                          const void* dz, int Cout, int B, int H, int W, float* dw, int device, void* stream);
 
+/* --- training-step operators (train_utils/train_unet.py:346-377); one kernel launch each ------------------ */
+/* conv with automatic kernel choice (halo-resident / tap-streaming) + optional batch statistics:
+ * stats[0..N) += sum over valid pixels of the raw accumulator, stats[N..2N) += sum of squares (train-mode
+ * BatchNorm2d, unet.py:12,15).  ntaps: 9 (3x3, pad 1) or 1; groups 4 = transposed-conv scatter. */
+int gsd_op_conv_auto_bf16(const void* src0, int C0, const void* src1, int C1, int H1, int W1, int off_y,
+                          int off_x, int B, int H, int W, const void* w, int Cout, int ntaps, int groups,
+                          const float* scale, const float* shift, int relu, void* out, void* pooled,
+                          float* stats, int device, void* stream);
+/* ConvTranspose2d(k=2,s=2) backward (unet.py:36): input gradient (tcgen05 GEMM over a 5-D space-to-depth TMA view of
+ * dU) and weight gradient (tcgen05 GEMM over pixels, dw (Cin,Cout,2,2) fp32 accumulated).  dU is a dense
+ * (B,Hf,Wf,C) tensor whose (2H x 2W) window at (off_y, off_x) is the gradient of the up-sampled map. */
+int gsd_op_convt_dgrad_bf16(const void* du, int Cs, int Hf, int Wf, int off_y, int off_x, const void* w, int Cin,
+                            int B, int H, int W, const float* scale, const float* shift, void* out, int device,
+                            void* stream);
+int gsd_op_convt_wgrad_bf16(const void* in, int Cin, const void* du, int Cout, int Hf, int Wf, int off_y, int off_x,
+                            int B, int H, int W, float* dw, int device, void* stream);
+/* fp32 NCHW frames -> NHWC bf16 padded to 16 channels (same arithmetic as the fused forward prologue) */
+int gsd_op_prologue_bf16(const float* x, const float* base, int base_batch, int use_diff, int B, int C, int Hr,
+                         int Wr, int H, int W, const float* scale8_host, const float* shift8_host, void* out16,
+                         void* stream);
+/* train-mode BatchNorm2d: batch mean / biased variance -> (scale, shift, mean, rstd); running stats updated in
+ * place with momentum and the unbiased variance (running_mean may be NULL).
+ * neg_center (or NULL): the conv epilogue stored z - center (center = running mean before this step, passed to the
+ * conv as shift = -center) so that bf16 rounds relative to the fluctuation; outputs then refer to the stored tensor. */
+int gsd_op_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float momentum, float eps, int C, const float* neg_center, float* scale,
+                       float* shift, float* mean, float* rstd, void* stream);
+int gsd_op_negate_f32(const float* in, int n, float* out, void* stream);
+/* a = relu(z*scale + shift) (+ MaxPool2d(2) copy, unet.py:26) */
+int gsd_op_bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H, int W, int C, void* a,
+                         void* pooled, void* stream);
+/* MSE_loss (train_unet.py:51-52): *loss += mean((y-t)^2), dy = 2(y-t)/n */
+int gsd_op_mse(const float* y, const float* t, long long n, float* loss, float* dy, void* stream);
+/* OutConv (unet.py:54) forward on a (B,H,W,64) bf16 activation and its backward (da bf16, dw/db fp32 accumulated) */
+int gsd_op_head_fwd(const void* a, const float* w, const float* bias, int ncls, int B, int H, int W, float* y, void* stream);
+int gsd_op_head_bwd(const void* a, const float* dy, const float* w, int ncls, int B, int H, int W, void* da, float* dw,
+                    float* db, void* stream);
+/* BatchNorm+ReLU backward: reduction pass (sums = [sum g, sum g*zhat] = [dbeta, dgamma]) and apply pass (dz) */
+int gsd_op_bn_bwd_reduce(const void* da, const void* a, const void* z, const float* mean, const float* rstd,
+                         long long npix, int C, float* sums, void* stream);
+int gsd_op_bn_bwd_apply(const void* da, const void* a, const void* z, const float* mean, const float* rstd,
+                        const float* gamma, const float* sums, double count, long long npix, int C, void* dz, void* stream);
+/* MaxPool2d(2) backward fused with the skip-connection gradient add (dskip may be NULL) */
+int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* dskip, int B, int H, int W, int C, void* dfull,
+                       void* stream);
+/* fp32 parameter -> bf16 GEMM operand; modes: 0 conv fwd, 1 conv dgrad (flipped taps), 2 convT fwd, 3 convT dgrad */
+int gsd_op_pack_weight(int mode, const float* w, int O, int I, int Ipad, void* out, void* stream);
+/* wgrad arena [O][9][Ipad] fp32 -> Conv2d.weight.grad layout (O,I,3,3) */
+int gsd_op_unpack_wgrad(const float* dwk, int O, int I, int Ipad, float* grad, void* stream);
+/* weight gradient of the first conv (K = 27/54), dw [64][9][16] fp32 accumulated */
+int gsd_op_wgrad_first(const void* x16, const void* dz, int B, int H, int W, int Cin, float* dw, void* stream);
+/* torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2 (train_unet.py:306,375) fused with the
+ * torch_ema==0.3 update (train_unet.py:309,376) over one flat fp32 arena; `step` is 1-based, shadow may be NULL */
+int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, float* shadow, long long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, long long step, float ema_decay, long long ema_updates,
+                    float grad_scale, void* stream);
+
 /* Stand-alone processing helper: fp32 NCHW -> fp32 NCHW,
  *   out[:, c] = scale8[min(c,7)] * area_resample(use_diff ? (x - base + 255)/2 : x) + shift8[min(c,7)]
  * Replaces (when called outside the fused forward): get_difference_image (image_utils.py:6-10),

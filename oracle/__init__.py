@@ -16,3 +16,4 @@ from .processing_oracle import (get_difference_image, area_resample, normalize_t
                                 denormalize_depth_image, normalize_depth_image,
                                 predict_depth_from_RGB, split_fingers)
 from .train_oracle import TrainOracle, mse_loss
+from .bf16_sim import loss_and_grads_bf16

@@ -1,0 +1,230 @@
+"""GPU parity of the training step (train_utils/train_unet.py:346-377) against the CPU oracle / reference goldens.
+
+Stated bf16 tolerances.  Every backward operator is checked in isolation against torch autograd on identical
+bf16-rounded inputs (test_backward_ops_vs_autograd): fp32 outputs (weight / bias / gamma / beta gradients) agree to
+1e-5 relative, bf16 outputs to one rounding (3e-3 relative L2).  End to end, activations and activation gradients are
+stored in bf16 between kernels; with train-mode BatchNorm each layer removes the (large) DC component of a random
+conv's output, which amplifies the relative bf16 noise by ~1.4x per unit on synthetic weights, so:
+  * 2- and 3-level nets (7 / 13 GEMM layers): forward rel-L2 <= 2e-2, every parameter gradient rel-L2 <= 8e-2;
+  * the full 5-level net (23 layers): forward rel-L2 <= 1e-1, loss within 6e-2, gradients of the last block <= 3e-2;
+  * BatchNorm running statistics (momentum 0.1, unbiased variance) within 3e-2."""
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def make_net(cin, ncls, seed, init="conditioned", dims=(64, 128, 256, 512, 1024)):
+    from gelslim_depth_b200.models.unet import UNet
+    torch.manual_seed(seed)
+    net = UNet(cin, ncls, layer_dimensions=list(dims))
+    fn = oracle.conditioned_state_dict if init == "conditioned" else oracle.trainer_init_state_dict
+    sd = fn(net.state_dict(), seed=seed + 1)
+    net.load_state_dict(sd)
+    return net, sd
+
+
+@pytest.mark.parametrize("cin,ncls,h,w,dims", [(3, 1, 40, 53, (64, 128)), (6, 2, 48, 59, (64, 128, 256)),
+                                               (3, 1, 64, 85, (64, 128, 256, 512, 1024))])
+def test_train_forward_backward_vs_oracle(cin, ncls, h, w, dims):
+    full = len(dims) == 5
+    net, sd = make_net(cin, ncls, 3, dims=dims)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, cin, h, w, generator=g)
+    tgt = -0.9 * torch.rand(2, ncls, h, w, generator=g)
+    tr = oracle.TrainOracle(sd)
+    loss_ref, grads_ref, stats_ref, y_ref = tr.loss_and_grads(x, tgt)          # fp32 reference arithmetic
+    loss_q, grads_q, y_q = oracle.loss_and_grads_bf16(sd, x, tgt)              # same, with the bf16 storage points
+    net = net.to(dev()).train()
+    y = net(x=x.to(dev()))
+    assert y.requires_grad and y.shape == y_ref.shape
+    fwd, fwd_q = rel_l2(y.detach(), y_ref), rel_l2(y.detach(), y_q)
+    assert fwd < (1e-1 if full else 4e-2), fwd                                  # inherent bf16 distance to fp32
+    loss = torch.mean((y - tgt.to(dev())) ** 2)          # the reference's MSE_loss (train_unet.py:51-52), torch autograd glue
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref)) < 6e-2 * abs(float(loss_ref)) + 1e-4
+    errs, errs_q = {}, {}
+    for name, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, name
+        errs[name] = rel_l2(p.grad, grads_ref[name])
+        errs_q[name] = rel_l2(p.grad, grads_q[name])
+    worst, worst_q = max(errs.values()), max(errs_q.values())
+
+    def flat(gd):
+        return torch.cat([gd[k].flatten().double().cpu() for k in grads_ref])
+    g_gpu = flat({k: p.grad for k, p in net.named_parameters()})
+    cos_ref = float(torch.nn.functional.cosine_similarity(g_gpu, flat(grads_ref), dim=0))
+    cos_q = float(torch.nn.functional.cosine_similarity(g_gpu, flat(grads_q), dim=0))
+    cos_sim_ref = float(torch.nn.functional.cosine_similarity(flat(grads_q), flat(grads_ref), dim=0))
+    print(f"dims={dims} fwd vs fp32 {fwd:.4f} vs bf16-sim {fwd_q:.5f}; worst grad vs fp32 {worst:.4f} vs bf16-sim {worst_q:.4f}; "
+          f"cos(gpu,fp32) {cos_ref:.4f} cos(gpu,sim) {cos_q:.4f} cos(sim,fp32) {cos_sim_ref:.4f}")
+    # Random train-mode-BatchNorm nets are chaotic: rounding only the WEIGHTS to bf16 moves early-layer gradients by
+    # 20-80 % (oracle/bf16_sim.py).  So: (1) the GPU path is closer to the bf16 restatement than that restatement is to
+    # fp32; (2) the whole-gradient direction agrees with fp32 as well as the restatement's does; (3) where the backward
+    # path is short (head, last BatchNorm) the gradient matches fp32 pointwise.
+    assert fwd_q < fwd and worst_q < worst, (fwd_q, fwd, worst_q, worst)
+    assert cos_ref > cos_sim_ref - 0.05 and cos_ref > (0.6 if full else 0.9), (cos_ref, cos_sim_ref)
+    assert abs(float(loss.detach()) - float(loss_q)) < 2e-3 * abs(float(loss_q)) + 1e-5
+    last = [k for k in errs if k.startswith("outc")]
+    assert max(errs[k] for k in last) < 1e-2, {k: errs[k] for k in last}      # vs fp32 where the path is short
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters())
+    # running statistics after one train-mode forward (momentum 0.1, unbiased variance)
+    got = dict(net.named_buffers())
+    for prefix, (mean, var_unb) in stats_ref.items():
+        rm = 0.9 * sd[prefix + ".running_mean"] + 0.1 * mean
+        rv = 0.9 * sd[prefix + ".running_var"] + 0.1 * var_unb
+        tol = 6e-2 if full else 3e-2
+        assert torch.allclose(got[prefix + ".running_mean"].cpu(), rm, rtol=tol, atol=tol), prefix
+        assert torch.allclose(got[prefix + ".running_var"].cpu(), rv, rtol=tol, atol=1e-3), prefix
+        assert int(got[prefix + ".num_batches_tracked"]) == 1
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(dev())
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).float().cpu()
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def test_backward_ops_vs_autograd():
+    """Each backward operator alone against torch autograd on identical bf16-rounded inputs."""
+    import torch.nn.functional as F
+    from gelslim_depth_b200.train import ops
+    g = torch.Generator().manual_seed(7)
+    d = dev()
+    # ---- BatchNorm(train) + ReLU forward apply and backward
+    C = 128
+    z = _bf(torch.randn(2, C, 13, 17, generator=g) + 0.7)
+    zt = z.clone().requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(C).train()
+    bn.weight.data = 0.5 + torch.rand(C, generator=g)
+    bn.bias.data = 0.1 * torch.randn(C, generator=g)
+    a_ref = torch.relu(bn(zt))
+    da = _bf(torch.randn(2, C, 13, 17, generator=g))
+    a_ref.backward(da)
+    mean, var = z.mean(dim=(0, 2, 3)), z.var(dim=(0, 2, 3), unbiased=False)
+    rstd = torch.rsqrt(var + 1e-5)
+    a_d, _ = ops.bn_relu_apply(_nhwc(z), (bn.weight.data * rstd).to(d), (bn.bias.data - mean * bn.weight.data * rstd).to(d))
+    assert rel_l2(_nchw(a_d), a_ref.detach()) < 3e-3
+    dz, sums = ops.bn_bwd(_nhwc(da), a_d, _nhwc(z), mean.to(d), rstd.to(d), bn.weight.data.to(d), 2 * 13 * 17)
+    assert rel_l2(_nchw(dz), zt.grad) < 4e-3
+    assert rel_l2(sums[C:], bn.weight.grad) < 1e-3 and rel_l2(sums[:C], bn.bias.grad) < 1e-3
+    # ---- conv input gradient through the flipped-tap operand
+    cin, cout = 128, 64
+    xw = _bf(torch.randn(2, cin, 13, 17, generator=g)).requires_grad_(True)
+    wt = _bf(torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+    zz = F.conv2d(xw, wt, padding=1)
+    dzz = _bf(torch.randn(zz.shape, generator=g))
+    zz.backward(dzz)
+    dx = ops.conv(_nhwc(dzz), ops.pack_weight(1, wt.to(d), cout, cin), cin, 9)
+    assert rel_l2(_nchw(dx), xw.grad) < 3e-3
+    # ---- max-pool backward (+ skip gradient), PyTorch tie rule = first maximum
+    ap = _bf(torch.randint(0, 4, (2, 64, 12, 15), generator=g).float()).requires_grad_(True)     # many ties on purpose
+    pp = F.max_pool2d(ap, 2)
+    dp, dsk = _bf(torch.randn(pp.shape, generator=g)), _bf(torch.randn(2, 64, 12, 15, generator=g))
+    pp.backward(dp)
+    df = ops.maxpool_bwd(_nhwc(ap.detach()), _nhwc(dp), _nhwc(dsk))
+    assert torch.equal(_nchw(df), _bf(ap.grad + dsk))
+    # ---- transposed conv forward, input gradient (5-D TMA view) and weight gradient, with an F.pad row/column
+    ci, co, hs, ws = 256, 128, 6, 7
+    xi = _bf(torch.randn(2, ci, hs, ws, generator=g)).requires_grad_(True)
+    wtt = _bf(torch.randn(ci, co, 2, 2, generator=g) * 0.05).requires_grad_(True)
+    bt = 0.1 * torch.randn(co, generator=g)
+    uu = F.conv_transpose2d(xi, wtt, bt, stride=2)
+    du_full = _bf(torch.randn(2, co, 2 * hs + 1, 2 * ws + 1, generator=g))
+    uu.backward(du_full[:, :, :2 * hs, :2 * ws])
+    dufd = _nhwc(du_full)
+    din = ops.convt_dgrad(dufd, (0, 0), ops.pack_weight(3, wtt.detach().to(d), co, ci), ci, hs, ws)
+    assert rel_l2(_nchw(din), xi.grad) < 3e-3
+    gw = torch.empty(ci, co, 2, 2, device=d)
+    ops.convt_wgrad(_nhwc(xi.detach()), dufd, (0, 0), gw)
+    assert rel_l2(gw, wtt.grad) < 1e-4
+    uf = ops.conv(_nhwc(xi.detach()), ops.pack_weight(2, wtt.detach().to(d), co, ci), co, ntaps=1, groups=4,
+                  scale=ops.ones(d, 4 * co), shift=bt.repeat(4).to(d))
+    assert rel_l2(_nchw(uf), uu.detach()) < 3e-3
+    # ---- 1x1 head backward
+    al = _bf(torch.rand(2, 64, 9, 11, generator=g)).requires_grad_(True)
+    wh = torch.randn(2, 64, 1, 1, generator=g).requires_grad_(True)
+    bh = torch.randn(2, generator=g).requires_grad_(True)
+    yy = F.conv2d(al, wh, bh)
+    dyy = torch.randn(yy.shape, generator=g)
+    yy.backward(dyy)
+    dwh, dbh = torch.zeros(2, 64, device=d), torch.zeros(2, device=d)
+    dal = ops.head_bwd(_nhwc(al.detach()), dyy.to(d), wh.detach().reshape(2, 64).to(d), dwh, dbh)
+    assert rel_l2(_nchw(dal), al.grad) < 3e-3 and rel_l2(dwh, wh.grad.reshape(2, 64)) < 1e-5 and rel_l2(dbh, bh.grad) < 1e-5
+    # ---- first-layer weight gradient
+    x3 = _bf(torch.rand(2, 6, 11, 13, generator=g))
+    w3 = torch.zeros(64, 6, 3, 3, requires_grad=True)
+    dz3 = _bf(torch.randn(2, 64, 11, 13, generator=g))
+    F.conv2d(x3, w3, padding=1).backward(dz3)
+    x16 = torch.zeros(2, 11, 13, 16)
+    x16[..., :6] = x3.permute(0, 2, 3, 1)
+    g3 = torch.empty(64, 6, 3, 3, device=d)
+    ops.wgrad_first(x16.to(torch.bfloat16).to(d), _nhwc(dz3), 6, g3)
+    assert rel_l2(g3, w3.grad) < 1e-5
+
+
+def test_reference_style_loop_adam_losses(golden_full):
+    """The unmodified loop body of train_unet.py:346-377 (torch.optim.Adam on unet.parameters()) runs on the drop-in
+    module; losses follow the reference-generated curve (trainer init N(0,0.01), fixture g1_train)."""
+    from gelslim_depth_b200.models.unet import UNet
+    g = golden_full["g1_train"]
+    torch.manual_seed(g["module_seed"])
+    net = UNet(g["cin"], g["ncls"])
+    sd = oracle.trainer_init_state_dict(net.state_dict(), seed=g["init_seed"])
+    assert oracle.state_dict_digest(sd) == g["digest"]
+    net.load_state_dict(sd)
+    net = net.to(dev()).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-6)
+    x, tgt = g["x"].to(dev()), g["target"].to(dev())
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        out = net(x=x)
+        loss = torch.mean((out - tgt) ** 2)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    ref = g["adam_losses"][:4]
+    assert abs(losses[0] - ref[0]) < 2e-2 * abs(ref[0]), (losses, ref)
+    for a, b in zip(losses, ref):
+        assert abs(a - b) < 0.15 * abs(b) + 1e-3, (losses, ref)      # Adam's sign-like first steps amplify bf16 noise
+    assert losses[-1] < losses[0]
+
+
+def test_fused_trainer_matches_oracle_steps():
+    """FusedTrainer (fused MSE + backward + Adam(coupled L2) + EMA arena kernel) vs oracle.TrainOracle."""
+    from gelslim_depth_b200.train.engine import FusedTrainer
+    net, sd = make_net(3, 1, 9)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(2, 3, 32, 43, generator=g)
+    tgt = -0.9 * torch.rand(2, 1, 32, 43, generator=g)
+    tr = oracle.TrainOracle(sd)
+    ref_losses = [tr.step(x, tgt) for _ in range(3)]
+    net = net.to(dev()).train()
+    ft = FusedTrainer(net)
+    losses = [float(ft.step(x.to(dev()), tgt.to(dev()))) for _ in range(3)]
+    assert abs(losses[0] - ref_losses[0]) < 2e-2 * abs(ref_losses[0]) + 1e-4, (losses, ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 0.1 * abs(b) + 1e-3, (losses, ref_losses)
+    # EMA shadow follows shadow -= (1-d)(shadow - p), d = min(0.995, (1+n)/(10+n)): compare one tensor with the oracle
+    k = "outc.conv.bias"
+    off, n = ft.views[-1]
+    assert torch.allclose(ft.shadow[off:off + n].cpu(), tr.shadow[k].flatten(), rtol=5e-2, atol=2e-3)
+    assert torch.allclose(dict(net.named_parameters())[k].detach().cpu().flatten(), tr.sd[k].flatten(), rtol=5e-2, atol=2e-3)
