@@ -119,6 +119,51 @@ def cpu_reference_fps(torch, seconds_budget=20.0, max_iters=8, threads=None):
     return 1.0 / med, threads, f"{len(times)} single-frame (1x6x320x427) fp32 forwards of the oracle port, median {med:.3f} s, 1 warm-up"
 
 
+def bench_train(torch, dist, dev, rank, world, batch, steps):
+    """train_unet.py:346-377 loop body on synthetic data: UNet(6,2) @ 6x320x427, bf16, `batch` samples per GPU,
+    trainer init N(0, 0.01), Adam(1e-3, wd 1e-6), EMA 0.995; data-parallel gradient all-reduce over NCCL."""
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.train.engine import FusedTrainer
+    torch.manual_seed(0)
+    net = UNet(CIN, NCLS, layer_dimensions=DIMS)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if "weight" in name:
+                torch.nn.init.normal_(p, mean=0, std=0.01)          # train_unet.py:248-250
+    net = net.to(dev).train()
+    ft = FusedTrainer(net)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.rand(batch, CIN, H, W, generator=g).to(dev)
+    t = (-0.9 * torch.rand(batch, NCLS, H, W, generator=g)).to(dev)
+    stream = torch.cuda.current_stream(dev)
+    losses = []
+    for _ in range(3):
+        losses.append(ft.step(x, t))
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        losses.append(ft.step(x, t))
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt)
+    sps = world * batch * steps / (ms / 1e3)
+    sustained = measured_peaks()[0]
+    return {"metric": "train_samples_per_s_6x320x427", "value": sps, "unit": "samples/s", "ms_per_step": ms / steps,
+            "batch_per_gpu": batch, "steps": steps, "gflop_per_sample": 599.41,
+            "tensor_frac_whole_step": sps / world * 599.41 / 1e3 / sustained,
+            "losses": [float(v) for v in torch.cat(losses).cpu()],
+            "what": "fwd (train-mode BN) + MSE + bwd (dgrad/wgrad on tcgen05) + bucketed NCCL all-reduce + fused Adam/EMA"}
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -167,6 +212,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipelined chunk of the host path (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=4, help="timed training steps (config 4: bf16, batch 32/GPU); 0 = skip")
+    ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--layers", action="store_true", help="print the per-launch table to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -249,10 +296,23 @@ def main():
     e2e = world * B * e2e_steps / (e2e_ms / 1e3)
     plan.set_chunk(B)
 
+    # ---------------- training step (BASELINE configs[3]): fwd + MSE + bwd + bucketed all-reduce + Adam + EMA
+    train = None
+    if args.train_steps > 0:
+        del x_dev, y_dev
+        net._plans.clear()
+        torch.cuda.empty_cache()
+        train = bench_train(torch, dist, dev, rank, world, args.train_batch, args.train_steps)
+        net.eval()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    x_dev = raw.to(dev)
+    y_dev = torch.empty(B, NCLS, H, W, device=dev)
+    plan = net.plan_for(B, H, W, dev)
+    packed = net.packed_weights(plan)
 
     # ---------------- live roofline of the dominant kernel (conv_tc_kernel) + per-launch table
     sustained, burst, hbm, src = measured_peaks()
@@ -294,7 +354,7 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * CIN * H * W * 4,
                     "d2h_bytes_per_step": B * NCLS * H * W * 4, "steps": e2e_steps, "chunk_frames": chunk,
                     "api": "gsd_forward_host (pinned fp32 frames in, fp32 depth maps out, copies inside the timed region)"},
-            "gpu_launches": plan.launches * args.steps, "clocks": clocks, "layers": table}
+            "gpu_launches": plan.launches * args.steps, "clocks": clocks, "train": train, "layers": table}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

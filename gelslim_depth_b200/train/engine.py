@@ -101,19 +101,39 @@ def train_forward(net, x: torch.Tensor, pw: PackedTrainWeights):
     return y, ctx
 
 
-def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: dict, need_dx: bool, split: int = 0):
+class GradSink:
+    """Where parameter gradients land.  Default: fresh tensors (autograd bridge).  FusedTrainer overrides `dest` with
+    views of its flat gradient arena and `done` with the bucketed all-reduce trigger."""
+
+    def __init__(self):
+        self.grads = {}
+
+    def dest(self, p):
+        t = torch.empty_like(p)
+        self.grads[p] = t
+        return t
+
+    def put(self, p, value):
+        self.dest(p).copy_(value.reshape(p.shape))
+        self.done(p)
+
+    def done(self, p):
+        pass
+
+
+def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: "GradSink", need_dx: bool, split: int = 0):
     """backward of conv -> BN -> ReLU.  Returns the input gradient(s) (None if not needed).
     split > 0: the conv input was the virtual concat [skip | up]; returns (dskip, dup_full)."""
     B, H, W, Cn = u.a.shape
     dz, sums = ops.bn_bwd(da, u.a, u.z, u.mean, u.rstd, u.bn.weight.detach(), B * H * W)
-    grads[u.bn.bias] = sums[:Cn]
-    grads[u.bn.weight] = sums[Cn:]
-    gw = torch.empty_like(u.conv.weight)
+    grads.put(u.bn.bias, sums[:Cn])
+    grads.put(u.bn.weight, sums[Cn:])
+    gw = grads.dest(u.conv.weight)
     if u.first:
         ops.wgrad_first(u.src0, dz, u.conv.in_channels, gw)
     else:
         ops.wgrad3x3(u.src0, dz, gw, x1=u.src1, off=u.off)
-    grads[u.conv.weight] = gw
+    grads.done(u.conv.weight)
     if not need_dx:
         return None
     wd = pw.dgrad[id(u.conv)]                                   # [ci][9][co]
@@ -126,18 +146,22 @@ def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: dict, need_dx: b
     return ops.conv(dz, wd, cin, 9)
 
 
-def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights) -> List[torch.Tensor]:
-    """dy: gradient of the loss w.r.t. the network output (fp32 NCHW).  Returns gradients in net.parameters() order."""
+def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "GradSink" = None) -> List[torch.Tensor]:
+    """dy: gradient of the loss w.r.t. the network output (fp32 NCHW).  Gradients go to `grads` (a GradSink) in
+    reverse parameter order; returns them in net.parameters() order when the default sink is used."""
     enc, dec = _blocks(net)
     depth = len(enc) - 1
-    grads = {}
+    own = grads is None
+    grads = GradSink() if own else grads
     dev = dy.device
     w_head = net.outc.conv.weight.detach().reshape(net.n_classes, -1)
-    dwh = torch.zeros_like(w_head)
-    dbh = torch.zeros(net.n_classes, dtype=torch.float32, device=dev)
+    dbh = grads.dest(net.outc.conv.bias)
+    dwh = grads.dest(net.outc.conv.weight)
+    dbh.zero_()
+    dwh.zero_()
     da = ops.head_bwd(ctx["a_last"], dy.contiguous().float(), w_head, dwh, dbh)
-    grads[net.outc.conv.weight] = dwh.reshape_as(net.outc.conv.weight)
-    grads[net.outc.conv.bias] = dbh
+    grads.done(net.outc.conv.bias)
+    grads.done(net.outc.conv.weight)
     dskips = [None] * (depth + 1)
     # ---- decoder, last block first
     for i in range(depth - 1, -1, -1):
@@ -154,10 +178,10 @@ def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights) -> List[t
             dup[:, off[0] + 2 * hs:] = 0
             dup[:, :, : off[1]] = 0
             dup[:, :, off[1] + 2 * ws:] = 0
-        grads[up.bias] = ops.channel_sum(dup)
-        gw = torch.empty_like(up.weight)
+        grads.put(up.bias, ops.channel_sum(dup))
+        gw = grads.dest(up.weight)
         ops.convt_wgrad(y_prev, dup, off, gw)
-        grads[up.weight] = gw
+        grads.done(up.weight)
         da = ops.convt_dgrad(dup, off, pw.dgrad[id(up)], up.in_channels, hs, ws)
     # ---- encoder, bottom up: `da` is now the gradient of enc[depth]'s output
     for l in range(depth, -1, -1):
@@ -166,7 +190,7 @@ def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights) -> List[t
             da = ops.maxpool_bwd(u2.a, dpool, dskips[l])      # noqa: F821  (dpool from level l+1) + skip-connection gradient
         da1 = _unit_backward(u2, da, pw, grads, need_dx=True)
         dpool = _unit_backward(u1, da1, pw, grads, need_dx=(l > 0))
-    return [grads[p] for p in net.parameters()]
+    return [grads.grads[p] for p in net.parameters()] if own else None
 
 
 class _TrainFn(torch.autograd.Function):
@@ -190,12 +214,41 @@ def unet_train_forward(net, x):
     return _TrainFn.apply(net, x, *list(net.parameters()))
 
 
+class _ArenaSink(GradSink):
+    """Gradients are written straight into the flat arena; a bucket (contiguous range, >= bucket_bytes, formed in
+    backward = reverse-parameter order) is all-reduced on a side stream as soon as its last gradient has been launched,
+    so NCCL traffic overlaps the remaining dgrad / wgrad kernels."""
+
+    def __init__(self, trainer):
+        super().__init__()
+        self.t = trainer
+        self.pending = [len(b["params"]) for b in trainer.buckets]
+
+    def dest(self, p):
+        off, k = self.t.index[p]
+        return self.t.flat_g[off:off + k].view(p.shape)
+
+    def done(self, p):
+        t = self.t
+        bi = t.bucket_of[p]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0 and t.world > 1:
+            b = t.buckets[bi]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(t.comm_stream):
+                t.comm_stream.wait_event(ev)
+                torch.distributed.all_reduce(t.flat_g[b["lo"]:b["hi"]], group=t.pg)
+
+
 class FusedTrainer:
     """The whole loop body of train_unet.py:346-377 with the loss, Adam (coupled L2) and the torch_ema update fused:
-    parameters, Adam moments and the EMA shadow live in flat fp32 arenas (one kernel updates all 64 tensors);
-    data-parallel replicas all-reduce the flat gradient arena over NCCL, bucketed in backward order."""
+    parameters, gradients, Adam moments and the EMA shadow live in flat fp32 arenas (one kernel updates all 64 tensors);
+    data-parallel replicas all-reduce the gradient arena over NCCL in buckets overlapped with backward
+    (per-replica BatchNorm statistics, like stock DistributedDataParallel)."""
 
-    def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, ema_decay=0.995, process_group=None):
+    def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, ema_decay=0.995, process_group=None,
+                 bucket_bytes=25 << 20, distributed=None):
         self.net = net
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         params = list(net.parameters())
@@ -207,17 +260,22 @@ class FusedTrainer:
         self.m = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         off = 0
-        self.views = []
+        self.views, self.index = [], {}
         for p in params:
             k = p.numel()
             self.flat_p[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + k].view_as(p)          # parameters now alias the arena
             self.views.append((off, k))
+            self.index[p] = (off, k)
             off += k
         self.shadow = self.flat_p.clone()                         # torch_ema: shadow = [p.clone()]
         self.step_count, self.ema_updates = 0, 0
         self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        if distributed is None:
+            distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.world = torch.distributed.get_world_size(process_group) if distributed else 1
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.buckets, self.bucket_of = plan_buckets([(p, *self.index[p]) for p in params], bucket_bytes)
 
     def step(self, x, target) -> torch.Tensor:
         """one training step; returns the loss as a 1-element device tensor (no host sync)."""
@@ -225,15 +283,34 @@ class FusedTrainer:
         pw = PackedTrainWeights(net)
         y, ctx = train_forward(net, x, pw)
         loss, dy = ops.mse(y, target.contiguous().float())
-        grads = train_backward(net, ctx, dy, pw)
-        for (off, k), g in zip(self.views, grads):
-            self.flat_g[off:off + k].copy_(g.reshape(-1))
+        train_backward(net, ctx, dy, pw, grads=_ArenaSink(self))
         scale = 1.0
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
             scale = 1.0 / self.world
         self.step_count += 1
         self.ema_updates += 1
         ops.adam_ema(self.flat_p, self.flat_g, self.m, self.v, self.shadow, self.lr, self.betas, self.eps, self.wd,
                      self.step_count, self.ema_decay, self.ema_updates, grad_scale=scale)
         return loss
+
+
+def plan_buckets(entries, bucket_bytes):
+    """entries: [(key, offset, numel)] in parameter (= arena) order.  Gradients appear in REVERSE order during backward,
+    so buckets are contiguous arena ranges grown from the end.  -> ([{lo, hi, params}], {key: bucket index})"""
+    buckets, bucket_of = [], {}
+    cur = None
+    for key, off, k in reversed(entries):
+        if cur is None:
+            cur = {"lo": off, "hi": off + k, "params": []}
+        cur["lo"] = off
+        cur["params"].append(key)
+        if (cur["hi"] - cur["lo"]) * 4 >= bucket_bytes:
+            buckets.append(cur)
+            cur = None
+    if cur is not None:
+        buckets.append(cur)
+    for i, b in enumerate(buckets):
+        for key in b["params"]:
+            bucket_of[key] = i
+    return buckets, bucket_of

@@ -228,3 +228,41 @@ def test_fused_trainer_matches_oracle_steps():
     off, n = ft.views[-1]
     assert torch.allclose(ft.shadow[off:off + n].cpu(), tr.shadow[k].flatten(), rtol=5e-2, atol=2e-3)
     assert torch.allclose(dict(net.named_parameters())[k].detach().cpu().flatten(), tr.sd[k].flatten(), rtol=5e-2, atol=2e-3)
+
+
+def test_loss_curve_200_steps_vs_reference():
+    """north star: matching training-loss curves over 200 steps.  Fixture: 200 steps of the unmodified reference
+    (fp32, CPU, torch.optim.Adam lr 1e-3 wd 1e-6, trainer init) on a fixed synthetic problem
+    (tests/golden/make_train_curve.py).  The B200 path (bf16, fused MSE + Adam + EMA) must follow it: same first-step
+    loss, the same decades-long descent (log10 distance of the 10-step-smoothed curves <= 0.5 everywhere, <= 0.25 on
+    average) and a final loss within a factor 3."""
+    import math
+    import os
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.train.engine import FusedTrainer
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "train_curve.pt"), weights_only=False)
+    torch.manual_seed(g["module_seed"])
+    net = UNet(3, 1)
+    sd = oracle.trainer_init_state_dict(net.state_dict(), seed=g["init_seed"])
+    assert oracle.state_dict_digest(sd) == g["digest"]
+    net.load_state_dict(sd)
+    net = net.to(dev()).train()
+    ft = FusedTrainer(net)
+    X, T = g["X"].to(dev()), g["T"].to(dev())
+    losses = []
+    for step in range(g["steps"]):
+        idx = torch.arange(4) + 4 * (step % 4)
+        losses.append(ft.step(X[idx], T[idx]))
+    losses = [float(v) for v in torch.cat(losses).cpu()]
+    ref = g["losses"]
+    assert abs(losses[0] - ref[0]) < 1e-2 * ref[0], (losses[0], ref[0])
+
+    def smooth(v):
+        return [sum(v[max(0, i - 9): i + 1]) / len(v[max(0, i - 9): i + 1]) for i in range(len(v))]
+    a, b = smooth(losses), smooth(ref)
+    dist = [abs(math.log10(x) - math.log10(y)) for x, y in zip(a, b)]
+    print("gpu ", [f"{v:.2e}" for v in losses[::20]], f"{losses[-1]:.2e}")
+    print("ref ", [f"{v:.2e}" for v in ref[::20]], f"{ref[-1]:.2e}")
+    print("max/mean log10 distance of smoothed curves:", max(dist), sum(dist) / len(dist))
+    assert max(dist) <= 0.5 and sum(dist) / len(dist) <= 0.25
+    assert losses[-1] < 3 * ref[-1] + 1e-5 and losses[-1] < 1e-2 * losses[0]
