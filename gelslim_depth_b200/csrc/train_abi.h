@@ -217,9 +217,10 @@ extern "C" int gsd_op_unpack_wgrad(const float* dwk, int O, int I, int Ipad, flo
 
 // first conv (K = 27/54): dw[64][9][16] += ...   (x16: NHWC bf16 padded to 16 channels, dz: (B,H,W,64))
 extern "C" int gsd_op_wgrad_first(const void* x16, const void* dz, int B, int H, int W, int Cin, float* dw, void* stream) {
-  GSD_CHECK(x16 && dz && dw && Cin >= 1 && Cin <= 16, "gsd_op_wgrad_first: bad argument");
-  dim3 grid(9 * Cin, 128);
-  wgrad_first_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x16),
+  GSD_CHECK(x16 && dz && dw && Cin >= 1 && Cin <= 8, "gsd_op_wgrad_first: bad argument");
+  long rows = (long)B * H;
+  int grid = (int)(rows < 148 * 4 ? rows : 148 * 4);
+  wgrad_first_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x16),
                                                                          static_cast<const __nv_bfloat16*>(dz), B, H, W, Cin, dw);
   GSD_CUDA(cudaGetLastError());
   return 0;
