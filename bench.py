@@ -200,10 +200,27 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was diverted to stderr"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # libraries that print to fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -355,7 +372,7 @@ def main():
                     "d2h_bytes_per_step": B * NCLS * H * W * 4, "steps": e2e_steps, "chunk_frames": chunk,
                     "api": "gsd_forward_host (pinned fp32 frames in, fp32 depth maps out, copies inside the timed region)"},
             "gpu_launches": plan.launches * args.steps, "clocks": clocks, "train": train, "layers": table}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -277,8 +277,29 @@ class FusedTrainer:
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.buckets, self.bucket_of = plan_buckets([(p, *self.index[p]) for p in params], bucket_bytes)
 
+    def average_parameters(self):
+        """`with trainer.average_parameters():` == torch_ema's context manager (train_unet.py:389,428,480): the EMA
+        shadow is swapped into the parameters for validation / checkpointing and the live weights are restored on exit
+        (two arena copies; BatchNorm running statistics stay live, exactly like the reference)."""
+        trainer = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                trainer._stash = trainer.flat_p.clone()
+                trainer.flat_p.copy_(trainer.shadow)
+                return trainer
+
+            def __exit__(self_inner, *exc):
+                trainer.flat_p.copy_(trainer._stash)
+                trainer._stash = None
+                return False
+
+        return _Ctx()
+
     def step(self, x, target) -> torch.Tensor:
-        """one training step; returns the loss as a 1-element device tensor (no host sync)."""
+        """one training step; returns the loss as a 1-element device tensor (no host sync).
+        A NaN loss is NOT replaced by a constant (train_unet.py:371-373 does that and would then crash in
+        backward): the step runs and the NaN is visible to the caller."""
         net = self.net
         pw = PackedTrainWeights(net)
         y, ctx = train_forward(net, x, pw)

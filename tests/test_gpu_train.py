@@ -266,3 +266,31 @@ def test_loss_curve_200_steps_vs_reference():
     print("max/mean log10 distance of smoothed curves:", max(dist), sum(dist) / len(dist))
     assert max(dist) <= 0.5 and sum(dist) / len(dist) <= 0.25
     assert losses[-1] < 3 * ref[-1] + 1e-5 and losses[-1] < 1e-2 * losses[0]
+
+
+def test_ema_average_parameters_and_checkpoint_roundtrip(tmp_path):
+    """eval under `ema.average_parameters()` and state_dict save/load (train_unet.py:380-390,476-484)."""
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.train.engine import FusedTrainer
+    net, sd = make_net(3, 1, 5, dims=(64, 128))
+    net = net.to(dev()).train()
+    ft = FusedTrainer(net)
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 3, 32, 43, generator=g).to(dev())
+    t = (-0.9 * torch.rand(2, 1, 32, 43, generator=g)).to(dev())
+    for _ in range(3):
+        ft.step(x, t)
+    live = ft.flat_p.clone()
+    net.eval()
+    y_live = net(x=x)
+    with ft.average_parameters():
+        assert torch.equal(ft.flat_p, ft.shadow)
+        y_ema = net(x=x)                                  # packed-weight cache must notice the in-place swap
+        torch.save(net.state_dict(), tmp_path / "ema.pth")
+    assert torch.equal(ft.flat_p, live)
+    assert not torch.allclose(y_live, y_ema)
+    assert torch.allclose(net(x=x), y_live)
+    net2 = UNet(3, 1, layer_dimensions=[64, 128])
+    net2.load_state_dict(torch.load(tmp_path / "ema.pth", map_location="cpu"))
+    net2 = net2.to(dev()).eval()
+    assert torch.allclose(net2(x=x), y_ema)
