@@ -25,7 +25,8 @@ class Geometry(C.Structure):
 class PrePost(C.Structure):
     _fields_ = [("use_diff", C.c_int32), ("base_batch", C.c_int32), ("raw_height", C.c_int32), ("raw_width", C.c_int32),
                 ("out_height", C.c_int32), ("out_width", C.c_int32), ("in_scale", C.c_float * 8),
-                ("in_shift", C.c_float * 8), ("out_scale", C.c_float), ("out_shift", C.c_float)]
+                ("in_shift", C.c_float * 8), ("out_scale", C.c_float), ("out_shift", C.c_float),
+                ("split_fingers", C.c_int32), ("input_u8", C.c_int32)]
 
 
 # name -> (restype, argtypes): every symbol include/gsd_b200.h declares

@@ -8,13 +8,26 @@
 namespace gsd {
 
 struct PreParams {
-  const float* x;      // (B, C, Hr, Wr) fp32 NCHW raw frames
-  const float* base;   // (Bb, C, Hr, Wr) or null
+  const void* x;       // raw frames, NCHW, fp32 or uint8: (B, C, Hr, Wr), or (B/2, 2C, Hr, Wr) when split_fingers
+  const float* base;   // (Bb, C or 2C, Hr, Wr) fp32 or null
   int base_batch;
   int use_diff;
   int B, C, Hr, Wr, H, W;
+  int split_fingers;   // general_dataset.py:71: network batch b -> finger b / (B/2) (channels [f*C, f*C+C)) of frame b % (B/2)
+  int input_u8;        // frames are uint8 (camera bytes) instead of float 0..255
   float in_scale[8], in_shift[8];
 };
+
+// plane (b, c) of the raw frames / base image for network batch index b, honouring the Left/Right split
+__device__ __forceinline__ long pre_plane(const PreParams& p, int b, int c, int batch_of_tensor) {
+  if (!p.split_fingers) return ((long)(batch_of_tensor == 1 ? 0 : b) * p.C + c);
+  const int frames = p.B >> 1, f = b / frames, n = b - f * frames;
+  return ((long)(batch_of_tensor == 1 ? 0 : n) * 2 * p.C + f * p.C + c);
+}
+__device__ __forceinline__ float pre_load(const PreParams& p, long plane, long off) {
+  const long i = plane * p.Hr * p.Wr + off;
+  return p.input_u8 ? (float)__ldg(static_cast<const unsigned char*>(p.x) + i) : __ldg(static_cast<const float*>(p.x) + i);
+}
 
 // get_difference_image (image_utils.py:6-10) -> area down-sample (image_utils.py:12-15) ->
 // normalize_tactile_image (normalization_utils.py:29-34) -> NHWC bf16 with channels padded to 16
@@ -36,12 +49,12 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_b
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       if (c < p.C) {
-        const float* px = p.x + ((long)b * p.C + c) * p.Hr * p.Wr;
-        const float* pb = p.base ? p.base + ((long)(p.base_batch == 1 ? 0 : b) * p.C + c) * p.Hr * p.Wr : nullptr;
+        const long plx = pre_plane(p, b, c, 0);
+        const float* pb = p.base ? p.base + pre_plane(p, b, c, p.base_batch) * p.Hr * p.Wr : nullptr;
         float acc = 0.f;
         for (int yy = ys; yy < ye; ++yy)
           for (int xx = xs; xx < xe; ++xx) {
-            float t = __ldg(px + (long)yy * p.Wr + xx);
+            float t = pre_load(p, plx, (long)yy * p.Wr + xx);
             if (p.use_diff) t = (t - __ldg(pb + (long)yy * p.Wr + xx) + 255.0f) * 0.5f;
             acc += t;
           }
@@ -70,12 +83,12 @@ __global__ void __launch_bounds__(256) prologue_f32_kernel(const PreParams p, fl
     const int b = (int)(idx / ((long)p.C * p.W * p.H));
     const int ys = (int)(((long)y * p.Hr) / p.H), ye = (int)((((long)y + 1) * p.Hr + p.H - 1) / p.H);
     const int xs = (int)(((long)x * p.Wr) / p.W), xe = (int)((((long)x + 1) * p.Wr + p.W - 1) / p.W);
-    const float* px = p.x + ((long)b * p.C + c) * p.Hr * p.Wr;
-    const float* pb = p.base ? p.base + ((long)(p.base_batch == 1 ? 0 : b) * p.C + c) * p.Hr * p.Wr : nullptr;
+    const long plx = pre_plane(p, b, c, 0);
+    const float* pb = p.base ? p.base + pre_plane(p, b, c, p.base_batch) * p.Hr * p.Wr : nullptr;
     float acc = 0.f;
     for (int yy = ys; yy < ye; ++yy)
       for (int xx = xs; xx < xe; ++xx) {
-        float t = __ldg(px + (long)yy * p.Wr + xx);
+        float t = pre_load(p, plx, (long)yy * p.Wr + xx);
         if (p.use_diff) t = (t - __ldg(pb + (long)yy * p.Wr + xx) + 255.0f) * 0.5f;
         acc += t;
       }
@@ -148,12 +161,12 @@ __global__ void __launch_bounds__(256) image_affine_kernel(const PreParams p, fl
     const int b = (int)(idx / ((long)p.W * p.H * p.C));
     const int ys = (int)(((long)y * p.Hr) / p.H), ye = (int)((((long)y + 1) * p.Hr + p.H - 1) / p.H);
     const int xs = (int)(((long)x * p.Wr) / p.W), xe = (int)((((long)x + 1) * p.Wr + p.W - 1) / p.W);
-    const float* px = p.x + ((long)b * p.C + c) * p.Hr * p.Wr;
-    const float* pb = p.base ? p.base + ((long)(p.base_batch == 1 ? 0 : b) * p.C + c) * p.Hr * p.Wr : nullptr;
+    const long plx = pre_plane(p, b, c, 0);
+    const float* pb = p.base ? p.base + pre_plane(p, b, c, p.base_batch) * p.Hr * p.Wr : nullptr;
     float acc = 0.f;
     for (int yy = ys; yy < ye; ++yy)
       for (int xx = xs; xx < xe; ++xx) {
-        float t = __ldg(px + (long)yy * p.Wr + xx);
+        float t = pre_load(p, plx, (long)yy * p.Wr + xx);
         if (p.use_diff) t = (t - __ldg(pb + (long)yy * p.Wr + xx) + 255.0f) * 0.5f;
         acc += t;
       }

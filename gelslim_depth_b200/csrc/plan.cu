@@ -395,13 +395,15 @@ static int check_prepost(const gsd_plan* p, const gsd_prepost* pp, const float* 
             pp->raw_width, p->g.height, p->g.width);
   GSD_CHECK(pp->out_height >= 1 && pp->out_width >= 1, "gsd_forward: bad output size");
   GSD_CHECK(!pp->use_diff || base != nullptr, "gsd_forward: use_diff set but base is NULL");
-  GSD_CHECK(!pp->use_diff || pp->base_batch == 1 || pp->base_batch == p->g.batch,
-            "gsd_forward: base_batch must be 1 or batch");
+  GSD_CHECK(!pp->split_fingers || (p->g.batch % 2 == 0 && (int)p->chunks.size() <= 1 && p->chunk >= p->g.batch),
+            "gsd_forward: split_fingers needs an even batch processed as one chunk");
+  const int frames = pp->split_fingers ? p->g.batch / 2 : p->g.batch;
+  GSD_CHECK(!pp->use_diff || pp->base_batch == 1 || pp->base_batch == frames, "gsd_forward: base_batch must be 1 or the number of frames");
   return 0;
 }
 
 // one chunk of frames through the whole network on `st`
-static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const float* base, const gsd_prepost* pp,
+static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const float* base, const gsd_prepost* pp,
                      float* y, void* ws, const void* packed, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
   auto mark = [&]() -> int {
     if (evs) {
@@ -418,10 +420,14 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const
   const char* P = static_cast<const char*>(packed);
   PreParams pre;
   const size_t raw_frame = (size_t)g.in_channels * pp->raw_height * pp->raw_width;
-  pre.x = x + (size_t)ch.b0 * raw_frame;
-  pre.base = pp->use_diff ? (pp->base_batch == 1 ? base : base + (size_t)ch.b0 * raw_frame) : nullptr;
+  // frame pointers of this chunk (element size 1 for uint8 frames); the Left/Right split needs the whole batch
+  const size_t esz = pp->input_u8 ? 1 : 4;
+  pre.x = reinterpret_cast<const char*>(x) + (pp->split_fingers ? 0 : (size_t)ch.b0 * raw_frame * esz);
+  pre.base = pp->use_diff ? ((pp->base_batch == 1 || pp->split_fingers) ? base : base + (size_t)ch.b0 * raw_frame) : nullptr;
   pre.base_batch = pp->base_batch;
   pre.use_diff = pp->use_diff;
+  pre.split_fingers = pp->split_fingers;
+  pre.input_u8 = pp->input_u8;
   pre.B = ch.nb; pre.C = g.in_channels; pre.Hr = pp->raw_height; pre.Wr = pp->raw_width; pre.H = g.height; pre.W = g.width;
   for (int c = 0; c < 8; ++c) { pre.in_scale[c] = pp->in_scale[c]; pre.in_shift[c] = pp->in_shift[c]; }
   const long npix = (long)g.height * g.width;
@@ -496,7 +502,7 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const float* x, const
   return 0;
 }
 
-extern "C" int gsd_forward(gsd_plan* p, const float* x, const float* base, const gsd_prepost* pp, float* y,
+extern "C" int gsd_forward(gsd_plan* p, const void* x, const float* base, const gsd_prepost* pp, float* y,
                            void* workspace, const void* packed, void* stream) {
   GSD_CHECK(p && x && y && workspace && packed, "gsd_forward: null argument");
   GSD_TRY(check_prepost(p, pp, base));
@@ -507,8 +513,8 @@ extern "C" int gsd_forward(gsd_plan* p, const float* x, const float* base, const
   return 0;
 }
 
-extern "C" int gsd_forward_host(gsd_plan* p, const float* x_host, const float* base, const gsd_prepost* pp,
-                                float* y_host, float* x_dev, float* y_dev, void* workspace, const void* packed,
+extern "C" int gsd_forward_host(gsd_plan* p, const void* x_host, const float* base, const gsd_prepost* pp,
+                                float* y_host, void* x_dev, float* y_dev, void* workspace, const void* packed,
                                 void* stream) {
   GSD_CHECK(p && x_host && y_host && x_dev && y_dev && workspace && packed, "gsd_forward_host: null argument");
   GSD_TRY(check_prepost(p, pp, base));
@@ -536,7 +542,9 @@ extern "C" int gsd_forward_host(gsd_plan* p, const float* x_host, const float* b
   GSD_CUDA(cudaStreamWaitEvent(p->copy_out, p->ev_start, 0));
   for (size_t c = 0; c < p->chunks.size(); ++c) {
     const ChunkLaunches& ch = p->chunks[c];
-    GSD_CUDA(cudaMemcpyAsync(x_dev + ch.b0 * raw_frame, x_host + ch.b0 * raw_frame, ch.nb * raw_frame * 4,
+    const size_t esz = pp->input_u8 ? 1 : 4;
+    GSD_CUDA(cudaMemcpyAsync(static_cast<char*>(x_dev) + ch.b0 * raw_frame * esz,
+                             static_cast<const char*>(x_host) + ch.b0 * raw_frame * esz, ch.nb * raw_frame * esz,
                              cudaMemcpyHostToDevice, p->copy_in));
     GSD_CUDA(cudaEventRecord(p->ev_in[c], p->copy_in));
     GSD_CUDA(cudaStreamWaitEvent(st, p->ev_in[c], 0));
@@ -582,7 +590,7 @@ extern "C" int gsd_op_image_affine(const float* x, const float* base, int base_b
   GSD_CUDA(cudaSetDevice(device));
   PreParams p;
   p.x = x; p.base = use_diff ? base : nullptr; p.base_batch = base_batch; p.use_diff = use_diff;
-  p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W;
+  p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W; p.split_fingers = 0; p.input_u8 = 0;
   for (int c = 0; c < 8; ++c) { p.in_scale[c] = scale8[c]; p.in_shift[c] = shift8[c]; }
   image_affine_kernel<<<ew_grid((long)B * Cc * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, out);
   GSD_CUDA(cudaGetLastError());
@@ -592,7 +600,7 @@ extern "C" int gsd_op_image_affine(const float* x, const float* base, int base_b
 // Instrumented forward: CUDA events between consecutive launches of chunk 0.. (bench.py's live roofline).
 // ms_host[i] = duration of launch i (prologue, convs in network order, head[+resample]) summed over chunks;
 // flops_host[i] = 2*M*N*K of that launch (0 for the memory-bound ones).  Synchronises the stream.
-extern "C" int gsd_forward_profiled(gsd_plan* p, const float* x, const float* base, const gsd_prepost* pp, float* y,
+extern "C" int gsd_forward_profiled(gsd_plan* p, const void* x, const float* base, const gsd_prepost* pp, float* y,
                                     void* workspace, const void* packed, void* stream, float* ms_host,
                                     double* flops_host, int capacity, int* n_out) {
   GSD_CHECK(p && x && y && workspace && packed && ms_host && flops_host && n_out, "gsd_forward_profiled: null argument");

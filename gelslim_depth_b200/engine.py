@@ -24,7 +24,8 @@ def _stream(device) -> C.c_void_p:
 
 def make_prepost(in_channels: int, raw_hw: Tuple[int, int], out_hw: Tuple[int, int], use_diff: bool = False,
                  base_batch: int = 1, in_scale: Sequence[float] = (1.0,), in_shift: Sequence[float] = (0.0,),
-                 out_scale: float = 1.0, out_shift: float = 0.0) -> _lib.PrePost:
+                 out_scale: float = 1.0, out_shift: float = 0.0, split_fingers: bool = False,
+                 input_u8: bool = False) -> _lib.PrePost:
     pp = _lib.PrePost()
     pp.use_diff = int(use_diff)
     pp.base_batch = int(base_batch)
@@ -34,6 +35,7 @@ def make_prepost(in_channels: int, raw_hw: Tuple[int, int], out_hw: Tuple[int, i
         pp.in_scale[c] = float(in_scale[min(c, len(in_scale) - 1)])
         pp.in_shift[c] = float(in_shift[min(c, len(in_shift) - 1)])
     pp.out_scale, pp.out_shift = float(out_scale), float(out_shift)
+    pp.split_fingers, pp.input_u8 = int(split_fingers), int(input_u8)
     return pp
 
 

@@ -126,6 +126,11 @@ class UNet(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def invalidate_packed_weights(self):
+        """Force a re-pack on the next forward.  Needed by code that updates parameters through raw pointers
+        (FusedTrainer's arena kernel), which torch's version counters cannot see."""
+        self._packed_key = None
+
     def plan_for(self, batch: int, height: int, width: int, device: torch.device) -> Plan:
         key = (batch, height, width, device, self.precision)
         dtype = _lib.DTYPE_FP32 if self.precision == "fp32" else _lib.DTYPE_BF16
@@ -143,16 +148,25 @@ class UNet(nn.Module):
         normalisation and depth de-normalisation are fused around the network."""
         if not x.is_cuda:
             raise RuntimeError("gelslim_depth_b200.UNet runs on a B200 only; got a CPU tensor (no CPU fallback)")
-        if x.dim() != 4 or x.shape[1] != self.n_channels:
-            raise ValueError(f"expected (N, {self.n_channels}, H, W), got {tuple(x.shape)}")
+        split = bool(pp is not None and pp.split_fingers)
+        want_c = self.n_channels * (2 if split else 1)
+        if x.dim() != 4 or x.shape[1] != want_c:
+            raise ValueError(f"expected (N, {want_c}, H, W), got {tuple(x.shape)}")
         if self.training:
             # batch-statistics BatchNorm + autograd bridge to the backward kernels (train_unet.py:347,374)
             if pp is not None or self.precision != "bf16":
                 raise NotImplementedError("train mode runs the plain bf16 network (no fused pre/post-processing, no fp32 mode)")
             from ..train.engine import unet_train_forward
             return unet_train_forward(self, x.contiguous().float())
-        x = x.contiguous().float()
+        if x.dtype == torch.uint8:
+            if pp is None or not pp.input_u8:
+                raise ValueError("uint8 frames need a gsd_prepost with input_u8 set (predict_depth_from_frames does that)")
+            x = x.contiguous()
+        else:
+            x = x.contiguous().float()
         n, _, h, w = x.shape
+        if split:
+            n *= 2                                   # one Left and one Right network sample per frame pair
         nh, nw = net_hw if net_hw is not None else (h, w)
         if pp is None:
             pp = make_prepost(self.n_channels, (h, w), (h, w))

@@ -287,11 +287,13 @@ class FusedTrainer:
             def __enter__(self_inner):
                 trainer._stash = trainer.flat_p.clone()
                 trainer.flat_p.copy_(trainer.shadow)
+                trainer.net.invalidate_packed_weights()
                 return trainer
 
             def __exit__(self_inner, *exc):
                 trainer.flat_p.copy_(trainer._stash)
                 trainer._stash = None
+                trainer.net.invalidate_packed_weights()
                 return False
 
         return _Ctx()
@@ -313,6 +315,7 @@ class FusedTrainer:
         self.ema_updates += 1
         ops.adam_ema(self.flat_p, self.flat_g, self.m, self.v, self.shadow, self.lr, self.betas, self.eps, self.wd,
                      self.step_count, self.ema_decay, self.ema_updates, grad_scale=scale)
+        net.invalidate_packed_weights()          # the arena kernel wrote through raw pointers
         return loss
 
 

@@ -63,6 +63,9 @@ typedef struct gsd_prepost {
   float in_shift[8];            /*                         -scale*bias/denominator              */
   float out_scale;              /* denormalize_depth_image: denominator/scale                   */
   float out_shift;              /*                          bias                                */
+  int32_t split_fingers;        /* 1: x holds batch/2 frame PAIRS with 2*in_channels channels; network sample b is
+                                 *    finger b/(batch/2) of pair b%(batch/2) (general_dataset.py:71: all Left, then all Right) */
+  int32_t input_u8;             /* 1: x is uint8 camera bytes instead of float 0..255 (4x less host->device traffic) */
 } gsd_prepost;
 
 typedef struct gsd_plan gsd_plan;
@@ -102,25 +105,25 @@ int gsd_pack_weights(gsd_plan* p, const void* const* params, const void* const* 
 
 /* Replaces: UNet.forward (unet.py:79-88) and, with a non-trivial gsd_prepost, the whole of
  * predict_depth_from_RGB (complete_prediction.py:4-10).
- * x:    fp32 NCHW (batch, in_channels, raw_height, raw_width)
+ * x:    fp32 (or uint8, see gsd_prepost.input_u8) NCHW (batch, in_channels, raw_height, raw_width)
  * base: fp32 NCHW (base_batch, in_channels, raw_height, raw_width) or NULL
  * y:    fp32 NCHW (batch, n_classes, out_height, out_width) */
-int gsd_forward(gsd_plan* p, const float* x, const float* base, const gsd_prepost* pp, float* y,
+int gsd_forward(gsd_plan* p, const void* x, const float* base, const gsd_prepost* pp, float* y,
                 void* workspace, const void* packed, void* stream);
 
 /* Same computation with HOST buffers (pinned or pageable): copies the frames host->device in
  * `chunk`-frame pieces on a copy stream overlapped with compute, and the depth maps back.
  * `x_dev`/`y_dev` are caller-owned device staging buffers of the full batch size.
  * Blocks until y_host is complete. */
-int gsd_forward_host(gsd_plan* p, const float* x_host, const float* base, const gsd_prepost* pp,
-                     float* y_host, float* x_dev, float* y_dev, void* workspace, const void* packed,
+int gsd_forward_host(gsd_plan* p, const void* x_host, const float* base, const gsd_prepost* pp,
+                     float* y_host, void* x_dev, float* y_dev, void* workspace, const void* packed,
                      void* stream);
 
 /* gsd_forward with CUDA events recorded between consecutive launches (synchronises `stream`):
  * ms_host[i] / flops_host[i] = device time and 2*M*N*K of launch i in network order (index 0 = input
  * prologue, 1..n-2 = conv / transposed-conv GEMMs, n-1 = 1x1 head [+ area resample]).  Measurement aid
  * for bench.py's live roofline; not on the product path. */
-int gsd_forward_profiled(gsd_plan* p, const float* x, const float* base, const gsd_prepost* pp, float* y,
+int gsd_forward_profiled(gsd_plan* p, const void* x, const float* base, const gsd_prepost* pp, float* y,
                          void* workspace, const void* packed, void* stream, float* ms_host,
                          double* flops_host, int capacity, int* n_out);
 

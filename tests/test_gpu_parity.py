@@ -359,3 +359,27 @@ def test_wgrad3x3_tcgen05(cin, cin1, cout, h, w, b):
     scale = float(ref.abs().max())
     assert float((got - ref).abs().max()) < 2e-3 * scale + 1e-3, (float((got - ref).abs().max()), scale)
     assert rel_l2(got, ref) < 1e-3
+
+
+def test_frame_pairs_split_and_uint8_ingest():
+    """Left/Right split (general_dataset.py:71), difference image, area down-sampling, normalisation
+    fused into the first kernel, from float and from uint8 camera frames."""
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.processing_utils.complete_prediction import predict_depth_from_frame_pairs
+    torch.manual_seed(4)
+    net = UNet(3, 1)
+    sd = oracle.conditioned_state_dict(net.state_dict(), seed=8)
+    net.load_state_dict(sd)
+    net = net.to(dev()).eval()
+    g = torch.Generator().manual_seed(12)
+    raw8 = torch.randint(0, 256, (3, 6, 64, 85), generator=g, dtype=torch.uint8)
+    base = torch.randint(0, 256, (1, 6, 64, 85), generator=g).float()
+    cfg = shipped_cfg((32, 43))
+    fingers = oracle.split_fingers(oracle.get_difference_image(raw8.float(), base))           # (6, 3, 64, 85)
+    ref = oracle.predict_depth_from_RGB(fingers, lambda t: oracle.unet_forward(sd, t), (64, 85), cfg)
+    ref = ref.view(2, 3, 64, 85).permute(1, 0, 2, 3)
+    got_f = predict_depth_from_frame_pairs(raw8.float().to(dev()), base.to(dev()), net, (64, 85), cfg)
+    got_u = predict_depth_from_frame_pairs(raw8.to(dev()), base.to(dev()), net, (64, 85), cfg)
+    assert got_f.shape == (3, 2, 64, 85)
+    assert torch.equal(got_f, got_u)                       # uint8 ingest is bit-identical to float frames
+    assert rel_l2(got_f, ref) < 2e-2
