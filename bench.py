@@ -131,7 +131,7 @@ def bench_train(torch, dist, dev, rank, world, batch, steps):
             if "weight" in name:
                 torch.nn.init.normal_(p, mean=0, std=0.01)          # train_unet.py:248-250
     net = net.to(dev).train()
-    ft = FusedTrainer(net)
+    ft = FusedTrainer(net, use_graph=True)
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.rand(batch, CIN, H, W, generator=g).to(dev)
     t = (-0.9 * torch.rand(batch, NCLS, H, W, generator=g)).to(dev)
@@ -161,7 +161,8 @@ def bench_train(torch, dist, dev, rank, world, batch, steps):
             "batch_per_gpu": batch, "steps": steps, "gflop_per_sample": 599.41,
             "tensor_frac_whole_step": sps / world * 599.41 / 1e3 / sustained,
             "losses": [float(v) for v in torch.cat(losses).cpu()],
-            "what": "fwd (train-mode BN) + MSE + bwd (dgrad/wgrad on tcgen05) + bucketed NCCL all-reduce + fused Adam/EMA"}
+            "what": "fwd (train-mode BN) + MSE + bwd (dgrad/wgrad on tcgen05) + bucketed NCCL all-reduce + fused Adam/EMA, "
+                    "whole step replayed as one CUDA graph"}
 
 
 def run_reference(args):

@@ -299,31 +299,33 @@ namespace gsd {
 
 struct WgradLaunch {
   WgradParams p;
-  int grid = 0, smem = 0;
+  int grid = 0, smem = 0, xb = 128;
   double flops = 0;
 };
 
 inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, int H1, int W1, int off_y, int off_x,
                               const void* dz, int Cout, int B, int H, int W, float* dw, int num_sms, WgradLaunch* L) {
   memset(L, 0, sizeof *L);
-  GSD_CHECK(C0 % 64 == 0 && C1 % 64 == 0 && Cout % 64 == 0 && C0 > 0, "wgrad: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)",
-            C0, C1, Cout);
+  const bool first = (C0 == 16 && C1 == 0);          // the 16-channel padded network input: N = 16 per tap, SWIZZLE_32B
+  GSD_CHECK(first || (C0 % 64 == 0 && C1 % 64 == 0 && C0 > 0), "wgrad: input channels must be multiples of 64, or 16 (C0=%d C1=%d)", C0, C1);
   GSD_CHECK(Cout == 64 || Cout % 128 == 0, "wgrad: Cout must be 64 or a multiple of 128");
   WgradParams& p = L->p;
-  p.cb0 = C0 / 64; p.cb1 = C1 / 64;
+  const int xb = first ? 32 : 128, nt = xb / 2;
+  L->xb = xb;
+  p.cb0 = C0 / nt; p.cb1 = C1 / nt;
   p.off_x = off_x; p.off_y = off_y;
   p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16; p.batch = B;
   p.Cout = Cout; p.co_blocks = (Cout + 127) / 128;
   p.dw = dw;
   p.stages = 4;
-  const int blocks = p.co_blocks * (p.cb0 + p.cb1) * 2;
+  const int blocks = p.co_blocks * (p.cb0 + p.cb1) * (first ? 1 : 2);
   const long m_tiles = (long)p.tiles_x * p.tiles_y * B;
   int split = blocks >= num_sms ? 1 : (num_sms + blocks / 2) / blocks;
   if (split > m_tiles) split = (int)m_tiles;
   if (split < 1) split = 1;
   p.split = split;
   L->grid = blocks * split;
-  L->smem = p.stages * kWgStageBytes + 1024 + 512;
+  L->smem = p.stages * (2 * kWgDzBytes + (180 * xb + 1023) / 1024 * 1024) + 1024 + 512;
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
@@ -333,8 +335,9 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   auto src_map = [&](CUtensorMap* m, const void* base, int C, int h, int w) -> int {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
-    uint32_t box[4] = {64, 10, 18, 1};
-    return encode_bf16_map(m, const_cast<void*>(base), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false);
+    uint32_t box[4] = {(uint32_t)nt, 10, 18, 1};
+    return encode_bf16_map(m, const_cast<void*>(base), 4, dims, str, box,
+                           first ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, false);
   };
   GSD_TRY(src_map(&p.tm_x0, x0, C0, H, W));
   if (C1) GSD_TRY(src_map(&p.tm_x1, x1, C1, H1, W1));
@@ -343,15 +346,20 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   return 0;
 }
 
-inline int run_wgrad_launch(const WgradLaunch& L, cudaStream_t st) {
+template <int XB>
+inline int launch_wgrad_cfg(const WgradLaunch& L, cudaStream_t st) {
   static int attr = 0;
   if (attr < L.smem) {
-    GSD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
+    GSD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
     attr = L.smem;
   }
-  wgrad_tc_kernel<<<L.grid, kWgThreads, L.smem, st>>>(L.p);
+  wgrad_tc_kernel<XB><<<L.grid, kWgThreads, L.smem, st>>>(L.p);
   GSD_CUDA(cudaGetLastError());
   return 0;
+}
+
+inline int run_wgrad_launch(const WgradLaunch& L, cudaStream_t st) {
+  return L.xb == 32 ? launch_wgrad_cfg<32>(L, st) : launch_wgrad_cfg<128>(L, st);
 }
 
 }  // namespace gsd

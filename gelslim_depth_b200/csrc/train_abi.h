@@ -158,24 +158,27 @@ static int reduce_grid(int C, long npix, int* grid, int* block) {
 
 // sums[0..C) = sum g, sums[C..2C) = sum g*zhat (accumulated; caller zeroes).  a/z/mean/rstd may be NULL together:
 // then it is a plain per-channel sum of `da`.
-extern "C" int gsd_op_bn_bwd_reduce(const void* da, const void* a, const void* z, const float* mean, const float* rstd,
-                                    long long npix, int C, float* sums, void* stream) {
+extern "C" int gsd_op_bn_bwd_reduce(const void* da, const float* scale, const float* shift, const void* z, const float* mean,
+                                    const float* rstd, long long npix, int C, float* sums, void* stream) {
   GSD_CHECK(da && sums && C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "gsd_op_bn_bwd_reduce: C/8 must be a power of two");
   int grid, block;
   reduce_grid(C, (long)npix, &grid, &block);
   bn_bwd_reduce_kernel<<<grid, block, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(z), mean, rstd,
-      (long)npix, C, C, sums);
+      static_cast<const __nv_bfloat16*>(da), scale, shift, static_cast<const __nv_bfloat16*>(z), mean, rstd, (long)npix, C, C, sums);
   GSD_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int gsd_op_bn_bwd_apply(const void* da, const void* a, const void* z, const float* mean, const float* rstd,
-                                   const float* gamma, const float* sums, double count, long long npix, int C, void* dz, void* stream) {
-  GSD_CHECK(da && a && z && mean && rstd && gamma && sums && dz && C % 8 == 0, "gsd_op_bn_bwd_apply: bad argument");
-  bn_bwd_apply_kernel<<<ew_grid((long)npix * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
-      sums, (float)count, (long)npix, C, C, static_cast<__nv_bfloat16*>(dz));
+extern "C" int gsd_op_bn_bwd_apply(const void* da, const float* scale, const float* shift, const void* z, const float* mean,
+                                   const float* rstd, const float* gamma, const float* sums, double count, long long npix, int C,
+                                   void* dz, void* stream) {
+  GSD_CHECK(da && scale && shift && z && mean && rstd && gamma && sums && dz && C % 8 == 0, "gsd_op_bn_bwd_apply: bad argument");
+  GSD_CHECK(((C / 8) & (C / 8 - 1)) == 0, "gsd_op_bn_bwd_apply: C/8 must be a power of two");
+  int grid, block;
+  reduce_grid(C, (long)npix, &grid, &block);
+  bn_bwd_apply_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(da), scale, shift, static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma, sums, (float)count,
+      (long)npix, C, C, static_cast<__nv_bfloat16*>(dz));
   GSD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -228,6 +231,20 @@ extern "C" int gsd_op_wgrad_first(const void* x16, const void* dz, int B, int H,
 
 // Adam (coupled L2) + EMA over a flat fp32 arena of n elements; step is 1-based; shadow may be NULL (no EMA).
 // grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
+// Graph-replayable variant: `counter` = 2 device int64 (Adam steps and EMA updates done so far); the kernel derives
+// the bias corrections / EMA warm-up from it and a second tiny kernel advances it.
+extern "C" int gsd_op_adam_ema_dev(float* p, const float* g, float* m, float* v, float* shadow, long long n, float lr, float beta1,
+                                   float beta2, float eps, float weight_decay, float ema_decay, long long* counter, float grad_scale,
+                                   void* stream) {
+  GSD_CHECK(p && g && m && v && counter && n > 0, "gsd_op_adam_ema_dev: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_ema_kernel<<<ew_grid((long)n / 4 + 1), 256, 0, st>>>(p, g, m, v, shadow, (long)n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, 0.f,
+                                                            grad_scale, counter, ema_decay);
+  adam_tick_kernel<<<1, 1, 0, st>>>(counter);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, float* shadow, long long n, float lr, float beta1,
                                float beta2, float eps, float weight_decay, long long step, float ema_decay, long long ema_updates,
                                float grad_scale, void* stream) {
@@ -238,7 +255,8 @@ extern "C" int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, flo
   const double warm = (1.0 + (double)ema_updates) / (10.0 + (double)ema_updates);   // torch_ema use_num_updates
   if (warm < d) d = warm;
   adam_ema_kernel<<<ew_grid((long)n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, shadow, (long)n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), (float)(1.0 - d), grad_scale);
+      p, g, m, v, shadow, (long)n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), (float)(1.0 - d), grad_scale, nullptr,
+      ema_decay);
   GSD_CUDA(cudaGetLastError());
   return 0;
 }

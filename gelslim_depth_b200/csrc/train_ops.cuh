@@ -185,28 +185,33 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const __nv_bfloat16* __re
 
 // BatchNorm+ReLU backward, reduction pass: sums[c] = sum g, sums[C+c] = sum g*zhat, g = da*(a>0), zhat=(z-mean)*rstd.
 // With `a == nullptr` there is no ReLU (plain per-channel sum of da: transposed-conv bias gradient).
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ a,
-                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, long npix, int C, long da_pix_stride,
-                                                            float* __restrict__ sums) {
+// The ReLU mask is recomputed from the stored z (z*scale + shift > 0, the very expression bn_relu_apply rounded), so
+// the post-ReLU tensor is not re-read: 2 bytes/element less traffic in each backward pass.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, const __nv_bfloat16* __restrict__ z,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd, long npix,
+                                                            int C, long da_pix_stride, float* __restrict__ sums) {
   // thread -> fixed 8-channel chunk; pixels strided.  blockDim.x * gridDim.x must be a multiple of C/8 (host).
   const int C8 = C / 8;
   const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const int c8 = (int)(tid % C8);
   const long p0 = tid / C8, pstep = ((long)gridDim.x * blockDim.x) / C8;
-  float s1[8], s2[8], mu[8], rs[8];
+  float s1[8], s2[8], mu[8], rs[8], sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = z ? mean[c8 * 8 + j] : 0.f; rs[j] = z ? rstd[c8 * 8 + j] : 0.f; }
+  for (int j = 0; j < 8; ++j) {
+    s1[j] = 0.f; s2[j] = 0.f;
+    mu[j] = z ? mean[c8 * 8 + j] : 0.f; rs[j] = z ? rstd[c8 * 8 + j] : 0.f;
+    sc[j] = z ? scale[c8 * 8 + j] : 0.f; sh[j] = z ? shift[c8 * 8 + j] : 0.f;
+  }
   for (long px = p0; px < npix; px += pstep) {
     float g[8];
     unpack8(*reinterpret_cast<const uint4*>(da + px * da_pix_stride + c8 * 8), g);
-    if (a) {
-      float av[8], zv[8];
-      unpack8(*reinterpret_cast<const uint4*>(a + px * C + c8 * 8), av);
+    if (z) {
+      float zv[8];
       unpack8(*reinterpret_cast<const uint4*>(z + px * C + c8 * 8), zv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float gg = av[j] > 0.f ? g[j] : 0.f;
+        const float gg = (zv[j] * sc[j] + sh[j]) > 0.f ? g[j] : 0.f;
         s1[j] += gg;
         s2[j] += gg * (zv[j] - mu[j]) * rs[j];
       }
@@ -216,41 +221,51 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
     }
   }
   // block reduce per chunk through smem atomics, then one global atomic per channel per block
-  extern __shared__ float sh[];   // [2*C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  extern __shared__ float smem[];   // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) smem[i] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sh[c8 * 8 + j], s1[j]);
-    if (a) atomicAdd(&sh[C + c8 * 8 + j], s2[j]);
+    atomicAdd(&smem[c8 * 8 + j], s1[j]);
+    if (z) atomicAdd(&smem[C + c8 * 8 + j], s2[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
-    if (sh[i] != 0.f) atomicAdd(sums + i, sh[i]);
+    if (smem[i] != 0.f) atomicAdd(sums + i, smem[i]);
 }
 
-// BatchNorm+ReLU backward, apply pass: dz = gamma*rstd*(g - sum_g/n - zhat*sum_gz/n)
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ a,
+// BatchNorm+ReLU backward, apply pass: dz = gamma*rstd*(g - sum_g/n - zhat*sum_gz/n).
+// A thread owns one 8-channel chunk for its whole pixel stride (gridDim*blockDim is a multiple of C/8), so the
+// per-channel constants live in registers and the loop body is 2 loads + 1 store of 16 bytes.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ sums, float count, long npix, int C,
                                                            long da_pix_stride, __nv_bfloat16* __restrict__ dz) {
   const int C8 = C / 8;
-  const long total = npix * C8;
+  const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const int c8 = (int)(tid % C8);
+  const long p0 = tid / C8, pstep = ((long)gridDim.x * blockDim.x) / C8;
   const float inv = 1.f / count;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % C8);
-    const long px = idx / C8;
-    float g[8], av[8], zv[8], o[8];
+  float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    sc[j] = scale[c]; sh[j] = shift[c]; mu[j] = mean[c]; rs[j] = rstd[c];
+    k1[j] = gamma[c] * rstd[c];
+    k2[j] = sums[c] * inv;
+    k3[j] = sums[C + c] * inv;
+  }
+  for (long px = p0; px < npix; px += pstep) {
+    float g[8], zv[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(da + px * da_pix_stride + c8 * 8), g);
-    unpack8(*reinterpret_cast<const uint4*>(a + px * C + c8 * 8), av);
     unpack8(*reinterpret_cast<const uint4*>(z + px * C + c8 * 8), zv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c8 * 8 + j;
-      const float gg = av[j] > 0.f ? g[j] : 0.f;
-      const float zh = (zv[j] - mean[c]) * rstd[c];
-      o[j] = gamma[c] * rstd[c] * (gg - sums[c] * inv - zh * sums[C + c] * inv);
+      const float gg = (zv[j] * sc[j] + sh[j]) > 0.f ? g[j] : 0.f;
+      const float zh = (zv[j] - mu[j]) * rs[j];
+      o[j] = k1[j] * (gg - k2[j] - zh * k3[j]);
     }
     *reinterpret_cast<uint4*>(dz + px * C + c8 * 8) = pack8(o);
   }
@@ -389,10 +404,26 @@ __global__ void __launch_bounds__(256) wgrad_first_kernel(const __nv_bfloat16* _
 // torch_ema==0.3 shadow update (train_unet.py:309,376), over one flat fp32 arena:
 //   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 //   shadow -= (1-d)*(shadow - p)
+// `counter` (device, 2 x int64: Adam step t and EMA update count, BEFORE this step) makes the launch CUDA-graph
+// replayable: bias corrections and the EMA warm-up decay are derived on the device; adam_tick_kernel advances it.
+__global__ void adam_tick_kernel(long long* counter) {
+  counter[0] += 1;
+  counter[1] += 1;
+}
+
 __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ shadow, long n, float lr,
                                                        float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                       float ema_one_minus_d, float grad_scale) {
+                                                       float ema_one_minus_d, float grad_scale, const long long* __restrict__ counter,
+                                                       float ema_decay) {
+  if (counter) {
+    const double t = (double)(counter[0] + 1), nu = (double)(counter[1] + 1);
+    bc1 = (float)(1.0 - pow((double)b1, t));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+    double d = (1.0 + nu) / (10.0 + nu);
+    if (d > (double)ema_decay) d = (double)ema_decay;
+    ema_one_minus_d = (float)(1.0 - d);
+  }
   const long n4 = n / 4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<const float4*>(g)[i];

@@ -22,7 +22,7 @@ constexpr int kWgThreads = 192;            // TMA warp, MMA warp, 4 drain warps
 constexpr int kWgDzBytes = 128 * 128;      // one 64-channel dZ box
 constexpr int kWgHaloBox = 180 * 128;
 constexpr int kWgHaloBuf = 23 * 1024;
-constexpr int kWgStageBytes = 2 * kWgDzBytes + kWgHaloBuf;   // 55 KB
+constexpr int kWgStageBytes = 2 * kWgDzBytes + kWgHaloBuf;   // 55 KB (XB = 128); the XB = 32 variant uses 2*16 KB + 6 KB
 
 struct WgradParams {
   CUtensorMap tm_dz;     // (Cout, W, H, B) bf16, box (64, 8, 16, 1)
@@ -45,13 +45,22 @@ __device__ __forceinline__ uint32_t mn_desc_lo(uint32_t saddr, uint32_t lbo_byte
   return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
 }
 
+// XB = bytes of one halo pixel record of X: 128 (64 channels, N = 64 per tap, taps split into 2 groups across CTAs)
+// or 32 (the 16-channel padded network input of the first conv: N = 16 per tap, all 9 taps in one CTA).
+template <int XB>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int NT = XB / 2;                                   // accumulator columns per tap
+  constexpr int HALO_BOX = 180 * XB;
+  constexpr int HALO_BUF = (HALO_BOX + 1023) / 1024 * 1024;
+  constexpr int STAGE = 2 * kWgDzBytes + HALO_BUF;
+  constexpr uint32_t XLAYOUT = (XB == 128) ? 2u : 6u;           // SWIZZLE_128B / SWIZZLE_32B
+  constexpr int TCOLS = (XB == 128) ? 512 : 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stages = p.stages;
   const uint32_t s_stage = smem_base;
-  const uint32_t s_bar = s_stage + stages * kWgStageBytes;
+  const uint32_t s_bar = s_stage + stages * STAGE;
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * stages, bar_done = bar_empty + 8 * stages;
   const uint32_t s_tmem_slot = bar_done + 8;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_slot - smem_base));
@@ -66,20 +75,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(s_tmem_slot);
+  if (warp == 2) tmem_alloc<TCOLS>(s_tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  // block decode: blockIdx.x = ((co_blk * cbt + ci_blk) * 2 + tap_group) * split + s
+  // block decode: blockIdx.x = ((co_blk * cbt + ci_blk) * tap_groups + tap_group) * split + s
   const int cbt = p.cb0 + p.cb1;
   int bid = blockIdx.x;
   const int s = bid % p.split; bid /= p.split;
-  const int tg = bid & 1; bid >>= 1;
+  int tg = 0;
+  if (XB == 128) { tg = bid & 1; bid >>= 1; }
   const int ci_blk = bid % cbt;
   const int co_blk = bid / cbt;
-  const int tap0 = tg ? 5 : 0, ntap = tg ? 4 : 5;
+  const int tap0 = (XB == 128) ? (tg ? 5 : 0) : 0, ntap = (XB == 128) ? (tg ? 4 : 5) : 9;
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
   const bool half_m = (p.Cout - co_blk * 128) < 128;      // only 64 real co rows
 
@@ -89,36 +99,37 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       for (int t = s; t < m_tiles; t += p.split) {
         const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
         mbar_wait(bar_empty + 8 * st, ph ^ 1);
-        const uint32_t sa = s_stage + st * kWgStageBytes, fb = bar_full + 8 * st;
-        mbar_arrive_expect_tx(fb, (half_m ? 1 : 2) * kWgDzBytes + kWgHaloBox);
+        const uint32_t sa = s_stage + st * STAGE, fb = bar_full + 8 * st;
+        mbar_arrive_expect_tx(fb, (half_m ? 1 : 2) * kWgDzBytes + HALO_BOX);
         tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * 8, ty * 16, b);
         if (!half_m) tma_load_4d(sa + kWgDzBytes, &p.tm_dz, fb, co_blk * 128 + 64, tx * 8, ty * 16, b);
         if (ci_blk < p.cb0)
-          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x0, fb, ci_blk * 64, tx * 8 - 1, ty * 16 - 1, b);
+          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x0, fb, ci_blk * NT, tx * 8 - 1, ty * 16 - 1, b);
         else
-          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x1, fb, (ci_blk - p.cb0) * 64, tx * 8 - 1 - p.off_x, ty * 16 - 1 - p.off_y, b);
+          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x1, fb, (ci_blk - p.cb0) * NT, tx * 8 - 1 - p.off_x, ty * 16 - 1 - p.off_y, b);
         if (++st == stages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // instruction descriptor: fp32 accum, bf16 A/B, A and B MN-major (bits 15, 16), N = 64, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: fp32 accum, bf16 A/B, A and B MN-major (bits 15, 16), N = NT, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (((uint32_t)NT >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t b_hi = ((10u * XB) >> 4) | (1u << 14) | (XLAYOUT << 29);   // K atoms = image rows, 10 halo pixels apart
     int st = 0; uint32_t ph = 0;
     bool first = true;
     for (int t = s; t < m_tiles; t += p.split) {
       mbar_wait(bar_full + 8 * st, ph);
       tc_fence_after();
-      const uint32_t sa = s_stage + st * kWgStageBytes;
+      const uint32_t sa = s_stage + st * STAGE;
       const uint32_t a_lbo = half_m ? 0u : (uint32_t)kWgDzBytes;
       if (elect_one()) {
         for (int tp = 0; tp < ntap; ++tp) {
           const int tap = tap0 + tp, dy = tap / 3, dx = tap % 3;
-          const uint32_t d_tmem = tmem_base + tp * 64;
+          const uint32_t d_tmem = tmem_base + tp * NT;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const uint32_t a_lo = mn_desc_lo(sa + k * 2048, a_lbo);
-            const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy) * 10 + dx) * 128, 0);
-            umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, mn_desc_hi(1280), idesc, (first && k == 0) ? 0u : 1u);
+            const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy) * 10 + dx) * XB, 0);
+            umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, b_hi, idesc, (first && k == 0) ? 0u : 1u);
           }
         }
         umma_commit(bar_empty + 8 * st);
@@ -136,25 +147,42 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     mbar_wait(bar_done, 0);
     tc_fence_after();
     const int co = co_blk * 128 + row;
-    const int ctot = cbt * 64;
+    const int ctot = cbt * NT;
     const bool live = (s < m_tiles) && co < p.Cout && !(half_m && row >= 64);
-    for (int tp = 0; tp < ntap; ++tp) {
+    if (XB == 128) {
+      for (int tp = 0; tp < ntap; ++tp) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + tp * 64 + c0 + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+          if (live) {
+            float* dst = p.dw + ((size_t)co * 9 + tap0 + tp) * ctot + ci_blk * 64 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+          }
+        }
+      }
+    } else {
+      // 9 taps x 16 columns = 144 accumulator columns: 32-column loads cover two taps each (the last one half)
+#pragma unroll 1
+      for (int c0 = 0; c0 < 160; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + tp * 64 + c0 + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld32(tmem_base + c0 + ((uint32_t)(q * 32) << 16), v);
         tmem_ld_wait();
         if (live) {
-          float* dst = p.dw + ((size_t)co * 9 + tap0 + tp) * ctot + ci_blk * 64 + c0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) {
+            const int col = c0 + i;
+            if (col < 144) atomicAdd(p.dw + ((size_t)co * 9 + (col >> 4)) * 16 + (col & 15), __uint_as_float(v[i]));
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (warp == 2) tmem_dealloc<TCOLS>(tmem_base);
 }
 
 }  // namespace gsd

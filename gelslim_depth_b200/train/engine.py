@@ -21,7 +21,7 @@ BF16 = torch.bfloat16
 
 class _Unit:
     """saved tensors of one conv3x3 -> BatchNorm -> ReLU unit"""
-    __slots__ = ("src0", "src1", "off", "z", "a", "mean", "rstd", "pooled", "conv", "bn", "first")
+    __slots__ = ("src0", "src1", "off", "z", "a", "mean", "rstd", "scale", "shift", "pooled", "conv", "bn", "first")
 
 
 def _blocks(net):
@@ -68,6 +68,7 @@ def _unit_forward(conv: nn.Conv2d, bn: nn.BatchNorm2d, pw: PackedTrainWeights, s
     a, pooled = ops.bn_relu_apply(z, scale, shift, pool=pool)
     u = _Unit()
     u.src0, u.src1, u.off, u.z, u.a, u.mean, u.rstd, u.pooled, u.conv, u.bn, u.first = src0, src1, off, z, a, mean, rstd, pooled, conv, bn, first
+    u.scale, u.shift = scale, shift
     return u
 
 
@@ -125,7 +126,7 @@ def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: "GradSink", need
     """backward of conv -> BN -> ReLU.  Returns the input gradient(s) (None if not needed).
     split > 0: the conv input was the virtual concat [skip | up]; returns (dskip, dup_full)."""
     B, H, W, Cn = u.a.shape
-    dz, sums = ops.bn_bwd(da, u.a, u.z, u.mean, u.rstd, u.bn.weight.detach(), B * H * W)
+    dz, sums = ops.bn_bwd(da, u.scale, u.shift, u.z, u.mean, u.rstd, u.bn.weight.detach(), B * H * W)
     grads.put(u.bn.bias, sums[:Cn])
     grads.put(u.bn.weight, sums[Cn:])
     gw = grads.dest(u.conv.weight)
@@ -248,7 +249,7 @@ class FusedTrainer:
     (per-replica BatchNorm statistics, like stock DistributedDataParallel)."""
 
     def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, ema_decay=0.995, process_group=None,
-                 bucket_bytes=25 << 20, distributed=None):
+                 bucket_bytes=25 << 20, distributed=None, use_graph=False):
         self.net = net
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         params = list(net.parameters())
@@ -269,7 +270,8 @@ class FusedTrainer:
             self.index[p] = (off, k)
             off += k
         self.shadow = self.flat_p.clone()                         # torch_ema: shadow = [p.clone()]
-        self.step_count, self.ema_updates = 0, 0
+        self.counter = torch.zeros(2, dtype=torch.int64, device=dev)   # (Adam steps, EMA updates) so far, advanced on device
+        self.use_graph, self._graph, self._warm = use_graph, None, 0
         self.pg = process_group
         if distributed is None:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -301,7 +303,29 @@ class FusedTrainer:
     def step(self, x, target) -> torch.Tensor:
         """one training step; returns the loss as a 1-element device tensor (no host sync).
         A NaN loss is NOT replaced by a constant (train_unet.py:371-373 does that and would then crash in
-        backward): the step runs and the NaN is visible to the caller."""
+        backward): the step runs and the NaN is visible to the caller.
+        use_graph=True: after two eager warm-up steps the whole step (~450 launches incl. the NCCL all-reduces)
+        is captured once into a CUDA graph and replayed; shapes must then stay fixed."""
+        if not self.use_graph:
+            return self._step_impl(x, target)
+        if self._graph is None:
+            if self._warm < 2:
+                self._warm += 1
+                return self._step_impl(x, target)
+            self._x = x.contiguous().float().clone()
+            self._t = target.contiguous().float().clone()
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._loss = self._step_impl(self._x, self._t)
+            # capture records but does not execute: replay once so that this call is a real step too
+        self._x.copy_(x)
+        self._t.copy_(target)
+        self._graph.replay()
+        self.net.invalidate_packed_weights()
+        return self._loss.clone()
+
+    def _step_impl(self, x, target) -> torch.Tensor:
         net = self.net
         pw = PackedTrainWeights(net)
         y, ctx = train_forward(net, x, pw)
@@ -311,10 +335,8 @@ class FusedTrainer:
         if self.world > 1:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
             scale = 1.0 / self.world
-        self.step_count += 1
-        self.ema_updates += 1
-        ops.adam_ema(self.flat_p, self.flat_g, self.m, self.v, self.shadow, self.lr, self.betas, self.eps, self.wd,
-                     self.step_count, self.ema_decay, self.ema_updates, grad_scale=scale)
+        ops.adam_ema_dev(self.flat_p, self.flat_g, self.m, self.v, self.shadow, self.lr, self.betas, self.eps, self.wd,
+                         self.ema_decay, self.counter, grad_scale=scale)
         net.invalidate_packed_weights()          # the arena kernel wrote through raw pointers
         return loss
 

@@ -109,15 +109,16 @@ def head_bwd(a, dy, w, dw, db):
     return da
 
 
-def bn_bwd(da, a, z, mean, rstd, gamma, count):
-    """-> dz (bf16), sums = [dbeta | dgamma] (fp32, 2C)."""
-    Cn = a.shape[-1]
-    npix = a.numel() // Cn
-    sums = torch.zeros(2 * Cn, dtype=torch.float32, device=a.device)
-    check(lib.gsd_op_bn_bwd_reduce(_p(da), _p(a), _p(z), _p(mean), _p(rstd), npix, Cn, _p(sums), _st(a.device)), "gsd_op_bn_bwd_reduce")
-    dz = torch.empty_like(a)
-    check(lib.gsd_op_bn_bwd_apply(_p(da), _p(a), _p(z), _p(mean), _p(rstd), _p(gamma), _p(sums), float(count), npix, Cn, _p(dz),
-                                  _st(a.device)), "gsd_op_bn_bwd_apply")
+def bn_bwd(da, scale, shift, z, mean, rstd, gamma, count):
+    """-> dz (bf16), sums = [dbeta | dgamma] (fp32, 2C).  scale/shift: the forward's BN-apply constants (ReLU mask)."""
+    Cn = z.shape[-1]
+    npix = z.numel() // Cn
+    sums = torch.zeros(2 * Cn, dtype=torch.float32, device=z.device)
+    check(lib.gsd_op_bn_bwd_reduce(_p(da), _p(scale), _p(shift), _p(z), _p(mean), _p(rstd), npix, Cn, _p(sums), _st(z.device)),
+          "gsd_op_bn_bwd_reduce")
+    dz = torch.empty_like(z)
+    check(lib.gsd_op_bn_bwd_apply(_p(da), _p(scale), _p(shift), _p(z), _p(mean), _p(rstd), _p(gamma), _p(sums), float(count), npix, Cn,
+                                  _p(dz), _st(z.device)), "gsd_op_bn_bwd_apply")
     return dz, sums
 
 
@@ -125,7 +126,8 @@ def channel_sum(t):
     """per-channel sum of a dense NHWC bf16 tensor -> fp32 [C]."""
     Cn = t.shape[-1]
     sums = torch.zeros(2 * Cn, dtype=torch.float32, device=t.device)
-    check(lib.gsd_op_bn_bwd_reduce(_p(t), None, None, None, None, t.numel() // Cn, Cn, _p(sums), _st(t.device)), "gsd_op_bn_bwd_reduce")
+    check(lib.gsd_op_bn_bwd_reduce(_p(t), None, None, None, None, None, t.numel() // Cn, Cn, _p(sums), _st(t.device)),
+          "gsd_op_bn_bwd_reduce")
     return sums[:Cn]
 
 
@@ -161,7 +163,9 @@ def wgrad3x3(x0, dz, grad_out, x1=None, off=(0, 0)):
 def wgrad_first(x16, dz, cin, grad_out):
     B, H, W, _ = x16.shape
     dwk = torch.zeros(64, 9, 16, dtype=torch.float32, device=x16.device)
-    check(lib.gsd_op_wgrad_first(_p(x16), _p(dz), B, H, W, cin, _p(dwk), _st(x16.device)), "gsd_op_wgrad_first")
+    # tcgen05 GEMM over pixels with the 16-channel padded input as a 32-byte-row (SWIZZLE_32B, N = 16) operand
+    check(lib.gsd_op_wgrad3x3_bf16(_p(x16), 16, None, 0, 0, 0, 0, 0, _p(dz), 64, B, H, W, _p(dwk), x16.device.index or 0,
+                                   _st(x16.device)), "gsd_op_wgrad3x3_bf16")
     check(lib.gsd_op_unpack_wgrad(_p(dwk), 64, cin, 16, _p(grad_out), _st(x16.device)), "gsd_op_unpack_wgrad")
 
 
@@ -186,3 +190,9 @@ def convt_wgrad(x_in, du_full, off, grad_out):
 def adam_ema(p, g, m, v, shadow, lr, betas, eps, wd, step, ema_decay, ema_updates, grad_scale=1.0):
     check(lib.gsd_op_adam_ema(_p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), lr, betas[0], betas[1], eps, wd, step, ema_decay,
                               ema_updates, grad_scale, _st(p.device)), "gsd_op_adam_ema")
+
+
+def adam_ema_dev(p, g, m, v, shadow, lr, betas, eps, wd, ema_decay, counter, grad_scale=1.0):
+    """CUDA-graph-replayable Adam+EMA: `counter` is a device int64[2] (steps, EMA updates) advanced on the device."""
+    check(lib.gsd_op_adam_ema_dev(_p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), lr, betas[0], betas[1], eps, wd, ema_decay,
+                                  _p(counter), grad_scale, _st(p.device)), "gsd_op_adam_ema_dev")

@@ -192,10 +192,13 @@ int gsd_op_head_fwd(const void* a, const float* w, const float* bias, int ncls, 
 int gsd_op_head_bwd(const void* a, const float* dy, const float* w, int ncls, int B, int H, int W, void* da, float* dw,
                     float* db, void* stream);
 /* BatchNorm+ReLU backward: reduction pass (sums = [sum g, sum g*zhat] = [dbeta, dgamma]) and apply pass (dz) */
-int gsd_op_bn_bwd_reduce(const void* da, const void* a, const void* z, const float* mean, const float* rstd,
-                         long long npix, int C, float* sums, void* stream);
-int gsd_op_bn_bwd_apply(const void* da, const void* a, const void* z, const float* mean, const float* rstd,
-                        const float* gamma, const float* sums, double count, long long npix, int C, void* dz, void* stream);
+/* (the ReLU mask is recomputed as z*scale + shift > 0, so the post-ReLU tensor is not re-read; z == NULL in
+ * gsd_op_bn_bwd_reduce gives a plain per-channel sum of `da`) */
+int gsd_op_bn_bwd_reduce(const void* da, const float* scale, const float* shift, const void* z, const float* mean,
+                         const float* rstd, long long npix, int C, float* sums, void* stream);
+int gsd_op_bn_bwd_apply(const void* da, const float* scale, const float* shift, const void* z, const float* mean,
+                        const float* rstd, const float* gamma, const float* sums, double count, long long npix, int C,
+                        void* dz, void* stream);
 /* MaxPool2d(2) backward fused with the skip-connection gradient add (dskip may be NULL) */
 int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* dskip, int B, int H, int W, int C, void* dfull,
                        void* stream);
@@ -210,6 +213,11 @@ int gsd_op_wgrad_first(const void* x16, const void* dz, int B, int H, int W, int
 int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, float* shadow, long long n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, long long step, float ema_decay, long long ema_updates,
                     float grad_scale, void* stream);
+
+/* CUDA-graph-replayable form: `counter` = 2 device int64 (Adam steps, EMA updates done so far), advanced on device */
+int gsd_op_adam_ema_dev(float* p, const float* g, float* m, float* v, float* shadow, long long n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, float ema_decay, long long* counter, float grad_scale,
+                        void* stream);
 
 /* Stand-alone processing helper: fp32 NCHW -> fp32 NCHW,
  *   out[:, c] = scale8[min(c,7)] * area_resample(use_diff ? (x - base + 255)/2 : x) + shift8[min(c,7)]

@@ -120,9 +120,10 @@ def test_backward_ops_vs_autograd():
     a_ref.backward(da)
     mean, var = z.mean(dim=(0, 2, 3)), z.var(dim=(0, 2, 3), unbiased=False)
     rstd = torch.rsqrt(var + 1e-5)
-    a_d, _ = ops.bn_relu_apply(_nhwc(z), (bn.weight.data * rstd).to(d), (bn.bias.data - mean * bn.weight.data * rstd).to(d))
+    sc_d, sh_d = (bn.weight.data * rstd).to(d), (bn.bias.data - mean * bn.weight.data * rstd).to(d)
+    a_d, _ = ops.bn_relu_apply(_nhwc(z), sc_d, sh_d)
     assert rel_l2(_nchw(a_d), a_ref.detach()) < 3e-3
-    dz, sums = ops.bn_bwd(_nhwc(da), a_d, _nhwc(z), mean.to(d), rstd.to(d), bn.weight.data.to(d), 2 * 13 * 17)
+    dz, sums = ops.bn_bwd(_nhwc(da), sc_d, sh_d, _nhwc(z), mean.to(d), rstd.to(d), bn.weight.data.to(d), 2 * 13 * 17)
     assert rel_l2(_nchw(dz), zt.grad) < 4e-3
     assert rel_l2(sums[C:], bn.weight.grad) < 1e-3 and rel_l2(sums[:C], bn.bias.grad) < 1e-3
     # ---- conv input gradient through the flipped-tap operand
@@ -294,3 +295,21 @@ def test_ema_average_parameters_and_checkpoint_roundtrip(tmp_path):
     net2.load_state_dict(torch.load(tmp_path / "ema.pth", map_location="cpu"))
     net2 = net2.to(dev()).eval()
     assert torch.allclose(net2(x=x), y_ema)
+
+
+def test_fused_trainer_cuda_graph_matches_eager():
+    """use_graph=True replays the captured step; losses must match the eager trainer step for step."""
+    from gelslim_depth_b200.train.engine import FusedTrainer
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(2, 3, 32, 43, generator=g).to(dev())
+    tgt = (-0.9 * torch.rand(2, 1, 32, 43, generator=g)).to(dev())
+    curves = []
+    for use_graph in (False, True):
+        net, _ = make_net(3, 1, 9, dims=(64, 128, 256))
+        net = net.to(dev()).train()
+        ft = FusedTrainer(net, use_graph=use_graph)
+        curves.append([float(ft.step(x, tgt)) for _ in range(6)])
+        assert int(ft.counter[0]) == 6 and int(net.inc.double_conv[1].num_batches_tracked) == 6
+    for a, b in zip(*curves):
+        assert abs(a - b) < 8e-2 * abs(b) + 1e-5, curves       # atomics order differs run to run (chaotic nets); same trajectory
+    assert curves[1][-1] < curves[1][0]
