@@ -295,7 +295,7 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
 
     # ---------------- end to end through the C ABI with HOST buffers (e2e)
-    chunk = args.chunk or max(1, B // 8)
+    chunk = args.chunk or max(1, B // 4)      # 16-frame chunks measured best (profiles/r1_sweep_1gpu.jsonl)
     plan.set_chunk(chunk)
     for _ in range(2):
         plan.forward_host(raw_h, base_dev, pp, y_host, x_dev, y_dev, packed)

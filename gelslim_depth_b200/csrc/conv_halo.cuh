@@ -47,6 +47,7 @@ struct HaloParams {
   int n_tiles;           // Cout / BN
   int relu;
   int na, nb;            // ring depths (A halo buffers, B weight stages)
+  FastDiv fd_ntiles, fd_tx, fd_ty;   // item -> (n tile, m group), m tile -> (tx, ty, b) without integer division
 };
 
 template <int BKB>
@@ -61,7 +62,8 @@ struct HaloGeom {
   static constexpr int ROW16 = BKB / 16;                                  // one halo pixel in descriptor address units
 };
 
-// NEPI = epilogue warps (4: one per TMEM lane quadrant; 8: two per quadrant on alternate 32-column units)
+// NEPI = epilogue warps (4: one per TMEM lane quadrant; 8: two sets of four that drain ALTERNATE work items, i.e.
+// one set per TMEM accumulator buffer -- the per-tile bookkeeping is then paid once per tile, not once per unit)
 template <int BN, int MT, bool WRES, int BKB, int NEPI>
 __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr int kHaloThreads = 64 + 32 * NEPI;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < na; ++i) { mbar_init(bar_fullA + 8 * i, 1); mbar_init(bar_emptyA + 8 * i, 1); }
     for (int i = 0; i < (WRES ? 1 : nb); ++i) { mbar_init(bar_fullB + 8 * i, 1); mbar_init(bar_emptyB + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, NEPI); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(s_tmem_slot);
@@ -143,16 +145,16 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
       int ia = 0, ib = 0;
       uint32_t pa = 0, pb = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int nt = item % p.n_tiles;
-        const int mg = item / p.n_tiles;
+        uint32_t mg, nt;
+        fdivmod((uint32_t)item, p.fd_ntiles, mg, nt);
         for (int cb = 0; cb < cbt; ++cb) {
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
             int mt = mg * MT + j;
             if (mt >= m_tiles) mt = m_tiles - 1;      // dummy duplicate keeps the pipeline protocol uniform
-            const int tx = mt % p.tiles_x;
-            const int ty = (mt / p.tiles_x) % p.tiles_y;
-            const int b = mt / (p.tiles_x * p.tiles_y);
+            uint32_t row, tx, b, ty;
+            fdivmod((uint32_t)mt, p.fd_tx, row, tx);
+            fdivmod(row, p.fd_ty, b, ty);
             const int xs = tx * 8 - 1, ys = ty * 16 - 1;
             mbar_wait(bar_emptyA + 8 * ia, pa ^ 1);
             mbar_arrive_expect_tx(bar_fullA + 8 * ia, G::BOX_BYTES);
@@ -237,9 +239,9 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
       __syncwarp();
     }
   } else {
-    // ===================================================== epilogue (warps 2..9): quadrant q = warp % 4, column half = (warp-2)/4
+    // ===================================================== epilogue (warps 2..): quadrant q = warp % 4, set = (warp-2)/4
     const int q = warp & 3;
-    const int half = (NEPI == 8) ? ((warp - 2) >> 2) : 0;
+    const int eset = (NEPI == 8) ? ((warp - 2) >> 2) : 0;
     const int ew = warp - 2;
     const int ly = 4 * q + (lane >> 3), lx = lane & 7;
     const int Hp = p.H >> 1, Wp = p.W >> 1;
@@ -247,17 +249,18 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int nt = item % p.n_tiles;
-      const int mg = item / p.n_tiles;
+      if (NEPI == 8 && buf != eset) continue;          // the other warp set owns this accumulator buffer
+      uint32_t mg, nt;
+      fdivmod((uint32_t)item, p.fd_ntiles, mg, nt);
       mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < MT; ++j) {
         const int mt = mg * MT + j;
         if (mt >= m_tiles) break;           // warp-uniform
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int b = mt / (p.tiles_x * p.tiles_y);
+        uint32_t trow, tx, b, ty;
+        fdivmod((uint32_t)mt, p.fd_tx, trow, tx);
+        fdivmod(trow, p.fd_ty, b, ty);
         const int y = ty * 16 + ly, x = tx * 8 + lx;
         EpiPixel px;
         const bool valid = (y < p.H) && (x < p.W);
@@ -268,42 +271,27 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
         px.stats_stride = p.Cout;
         px.pvalid = ((y >> 1) < Hp) && ((x >> 1) < Wp);
         px.hx = hx; px.hy = hy; px.ypart = 8;
-        px.prow = p.pooled ? p.pooled + (((size_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout + nt * BN + (hx ? 16 : 0) + (hy ? 8 : 0)
+        const int img_row0 = (int)b * p.H;              // 32-bit pixel arithmetic, one 64-bit multiply per pointer
+        px.prow = p.pooled ? p.pooled + (size_t)(((int)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout + nt * BN + (hx ? 16 : 0) + (hy ? 8 : 0)
                            : nullptr;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = 8 * i + (lane >> 2);
           const int yy = ty * 16 + 4 * q + (r >> 3), xx = tx * 8 + (r & 7);
-          px.rp[i] = (p.out && yy < p.H && xx < p.W) ? p.out + (((size_t)b * p.H + yy) * p.W + xx) * p.Cout + nt * BN : nullptr;
+          px.rp[i] = (p.out && yy < p.H && xx < p.W) ? p.out + (size_t)((img_row0 + yy) * p.W + xx) * p.Cout + nt * BN : nullptr;
         }
         const uint32_t t_row = tmem_base + (buf * MT + j) * BN + ((uint32_t)(q * 32) << 16);
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-        for (int c0 = 32 * half; c0 < BN; c0 += 8 * NEPI)
+        for (int c0 = 0; c0 < BN; c0 += 32)
           epilogue_32cols(t_row, c0, g_scale + nt * BN, g_shift + nt * BN, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc,
                           p.head_w ? g_head : nullptr, p.head_ncls);
-        if (p.head_w) {
-          // the two warps of a quadrant hold the two channel halves of the same 32 pixels: combine through smem
-          float* slot = g_hx + (q * 32 + lane) * 4;
-          if (NEPI == 8) {
-            if (half == 1) {
+        if (p.head_w && valid) {
+          const size_t plane = (size_t)p.H * p.W;
+          float* yo = p.head_y + (size_t)b * p.head_ncls * plane + (size_t)y * p.W + x;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) slot[k] = hacc[k];
-            }
-            named_bar_sync(1 + q, 64);
-            if (half == 0) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) hacc[k] += slot[k];
-            }
-          }
-          if (half == 0 && valid) {
-            const size_t plane = (size_t)p.H * p.W;
-            float* yo = p.head_y + (size_t)b * p.head_ncls * plane + (size_t)y * p.W + x;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < p.head_ncls) yo[k * plane] = (hacc[k] + g_head[256 + k]) * p.head_scale + p.head_shift;
-          }
-          if (NEPI == 8) named_bar_sync(1 + q, 64);
+          for (int k = 0; k < 4; ++k)
+            if (k < p.head_ncls) yo[k * plane] = (hacc[k] + g_head[256 + k]) * p.head_scale + p.head_shift;
         }
       }
       tc_fence_before();

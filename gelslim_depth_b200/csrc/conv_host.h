@@ -136,6 +136,8 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
   p.out = static_cast<__nv_bfloat16*>(d.out);
   p.pooled = static_cast<__nv_bfloat16*>(d.pooled);
   p.H = d.H; p.W = d.W; p.groups = d.groups; p.ntot = ntot;
+  p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
+  GSD_CHECK((long)m_tiles * p.n_tiles < (1L << 24) && p.tiles_x < 4096 && p.tiles_y < 4096 && p.n_tiles < 4096, "conv: too many tiles for the 24-bit tile index");
   p.stats = d.stats;
   GSD_CHECK(ntot <= 2048, "conv: more than 2048 output channels per launch are not supported");
   const long total = (long)m_tiles * p.n_tiles;
@@ -243,6 +245,8 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     L->smem = p.na * buf_bytes + p.nb * b_bytes + aux + 1024;
   }
   p.n_tiles = d.Cout / bn;
+  p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
+  GSD_CHECK((long)p.tiles_x * p.tiles_y * d.B * p.n_tiles < (1L << 24), "halo conv: too many tiles for the 24-bit tile index");
   L->bn = bn; L->mt = mt; L->wres = wres; L->bkb = bkb; L->nepi = nepi;
   const CUtensorMapSwizzle swz = bkb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   auto src_map = [&](CUtensorMap* m, const void* base, int C, int H, int W) -> int {

@@ -37,6 +37,7 @@ struct ConvParams {
   __nv_bfloat16* pooled;  // (B, H/2, W/2, Cout) or null
   int H, W, groups, ntot;
   float* stats;           // global [2][ntot] batch statistics of the raw conv output, or null
+  FastDiv fd_ntiles, fd_tx, fd_ty;
   int src5;               // 1: tm_src0 is the 5-D space-to-depth view (2C, W, 2, H, B) of a (B,2H,2W,C) tensor and the
                           //    "tap" index is its gy coordinate (transposed-conv input gradient)
   const float* scale;     // [Ntot]
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, kEpiWarps);   // one arrive per epilogue warp
+      mbar_init(bar_acc_empty + 8 * i, 4);   // one arrive per epilogue warp of the set that owns the buffer
     }
     fence_barrier_init();
   }
@@ -144,12 +145,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
-        const int tx = mt % p.tiles_x;
-        mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int b = mt / p.tiles_y;
+        uint32_t mt, nt, trow, tx, b, ty;
+        fdivmod((uint32_t)tile, p.fd_ntiles, mt, nt);
+        fdivmod(mt, p.fd_tx, trow, tx);
+        fdivmod(trow, p.fd_ty, b, ty);
         const int x0 = tx * p.tw, y0 = ty * p.th;
         int kidx = 0;
         for (int t = 0; t < p.ntaps; ++t) {
@@ -205,9 +204,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..9): quadrant q = warp % 4, column half = (warp-2)/4
+    // ===================================================== epilogue (warps 2..9): quadrant q = warp % 4, set = (warp-2)/4
+    // (the two sets of four warps drain alternate tiles = one set per TMEM accumulator buffer)
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;
+    const int eset = (warp - 2) >> 2;
     const int ew = warp - 2;
     const int tw_shift = 31 - __clz(p.tw);          // tile width is a power of two
     const int row = q * 32 + lane;        // accumulator row == pixel index inside the tile
@@ -217,13 +217,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
+      if (acc != eset) continue;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int b = mt / p.tiles_y;
+      uint32_t mt, nt, trow, tx, b, ty;
+      fdivmod((uint32_t)tile, p.fd_ntiles, mt, nt);
+      fdivmod(mt, p.fd_tx, trow, tx);
+      fdivmod(trow, p.fd_ty, b, ty);
       const int y = ty * p.th + ly, x = tx * p.tw + lx;
       const int n0 = nt * BN;
       EpiPixel px;
@@ -249,7 +248,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
       float hacc[4];
 #pragma unroll 1
-      for (int c0 = 32 * half; c0 < BN; c0 += 64) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
         // a 32-column unit lies inside ONE (dy,dx) group of the transposed-conv scatter (Cout % 32 == 0)
         const int grp_idx = (n0 + c0) / p.cout_per_group;
         const int ch0 = n0 + c0 - grp_idx * p.cout_per_group;        // channel of column c0 inside its group

@@ -34,14 +34,20 @@ __device__ __forceinline__ float pre_load(const PreParams& p, long plane, long o
 // (the first conv's K-block).  One thread per output pixel; reads are coalesced along x per channel
 // plane, the 32-byte pixel record is written as two 16-byte stores.
 __global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_bfloat16* __restrict__ out) {
-  const long total = (long)p.B * p.H * p.W;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % p.W);
-    const int y = (int)((idx / p.W) % p.H);
-    const int b = (int)(idx / ((long)p.W * p.H));
-    // adaptive-average-pool bin: [floor(i*in/out), ceil((i+1)*in/out))
-    const int ys = (int)(((long)y * p.Hr) / p.H), ye = (int)((((long)y + 1) * p.Hr + p.H - 1) / p.H);
-    const int xs = (int)(((long)x * p.Wr) / p.W), xe = (int)((((long)x + 1) * p.Wr + p.W - 1) / p.W);
+  // one block = 256 consecutive pixels of one image row segment; 32-bit index arithmetic, no per-pixel division
+  const int tiles_per_row = (p.W + 255) / 256;
+  const int rows = p.B * p.H;
+  const bool identity = (p.Hr == p.H) && (p.Wr == p.W);
+  for (int t = blockIdx.x; t < rows * tiles_per_row; t += gridDim.x) {
+    const int r = t / tiles_per_row;                    // block-uniform
+    const int x = (t - r * tiles_per_row) * 256 + threadIdx.x;
+    if (x >= p.W) continue;
+    const int b = r / p.H, y = r - b * p.H;
+    int ys = y, ye = y + 1, xs = x, xe = x + 1;
+    if (!identity) {   // adaptive-average-pool bin: [floor(i*in/out), ceil((i+1)*in/out))
+      ys = (int)(((long)y * p.Hr) / p.H); ye = (int)((((long)y + 1) * p.Hr + p.H - 1) / p.H);
+      xs = (int)(((long)x * p.Wr) / p.W); xe = (int)((((long)x + 1) * p.Wr + p.W - 1) / p.W);
+    }
     const float inv = 1.0f / (float)((ye - ys) * (xe - xs));
     float v[16];
 #pragma unroll
@@ -54,9 +60,9 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_b
         float acc = 0.f;
         for (int yy = ys; yy < ye; ++yy)
           for (int xx = xs; xx < xe; ++xx) {
-            float t = pre_load(p, plx, (long)yy * p.Wr + xx);
-            if (p.use_diff) t = (t - __ldg(pb + (long)yy * p.Wr + xx) + 255.0f) * 0.5f;
-            acc += t;
+            float tv = pre_load(p, plx, (long)yy * p.Wr + xx);
+            if (p.use_diff) tv = (tv - __ldg(pb + (long)yy * p.Wr + xx) + 255.0f) * 0.5f;
+            acc += tv;
           }
         v[c] = p.in_scale[c] * (acc * inv) + p.in_shift[c];
       }
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_b
       __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
       w[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    uint4* o = reinterpret_cast<uint4*>(out + idx * 16);
+    uint4* o = reinterpret_cast<uint4*>(out + ((long)r * p.W + x) * 16);
     o[0] = make_uint4(w[0], w[1], w[2], w[3]);
     o[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }

@@ -21,6 +21,23 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// Division by a launch-invariant divisor as multiply + shift (exact for n < 2^24, d < 2^12: magic = ceil(2^40 / d)).
+struct FastDiv {
+  uint32_t d;
+  uint64_t magic;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d ? d : 1;
+  f.magic = ((1ull << 40) + f.d - 1) / f.d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (uint32_t)(((uint64_t)n * f.magic) >> 40); }
+__device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+  q = fdiv(n, f);
+  r = n - q * f.d;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -467,7 +467,7 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const 
     return 0;
   }
   __nv_bfloat16* in16 = reinterpret_cast<__nv_bfloat16*>(W + p->in16_off + (size_t)ch.b0 * g.height * g.width * 16 * 2);
-  prologue_kernel<<<ew_grid((long)ch.nb * g.height * g.width), 256, 0, st>>>(pre, in16);
+  prologue_kernel<<<ew_grid((long)ch.nb * g.height * ((g.width + 255) / 256) * 256, 256, 148 * 32), 256, 0, st>>>(pre, in16);
   GSD_CUDA(cudaGetLastError());
   GSD_TRY(mark());
   for (const AnyLaunch& L : ch.convs) {
