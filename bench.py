@@ -37,6 +37,17 @@ def measured_peaks():
     return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+def traffic_from_profile():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the 22 conv launches of one batch-64 forward, from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json); bytes per step, like `achieved` is FLOPs per step."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"dram_bytes_per_step": d["traffic_bytes_per_step"], "algorithmic_bytes_per_step": d["algorithmic_activation_bytes_per_step"] + d["weights_bytes"],
+            "source": d["source"]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -351,7 +362,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (22 launches/step: 18 conv3x3 + 4 convT as implicit GEMM)",
                 "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
-                "frac_of_burst": achieved / burst, "traffic": None,
+                "frac_of_burst": achieved / burst, "traffic": traffic_from_profile(),
                 "conv_share_of_step": conv_ms / (conv_ms + other_ms),
                 "flops_per_launch_set": conv_flops, "algorithmic_gflop_per_frame": GFLOP_PER_FRAME}
 
