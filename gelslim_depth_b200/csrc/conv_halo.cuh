@@ -87,9 +87,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
   float* g_shift = g_scale + p.Cout;
   float* g_head = g_shift + p.Cout;                                    // [4][64] + [4]
   const uint32_t s_epi = s_aux + 2 * p.Cout * 4 + (4 * 64 + 4) * 4 + 16;   // per-warp 2 KB epilogue transpose patches
-  const uint32_t s_hx = s_epi + NEPI * kEpiStageBytesPerWarp;         // head partial-sum exchange [4 quadrants][32][4]
-  float* g_hx = reinterpret_cast<float*>(smem_gen + (s_hx - smem_base));
-  const uint32_t s_st = s_hx + 4 * 32 * 4 * 4;                             // per-CTA partial batch statistics [2][Cout]
+  const uint32_t s_st = s_epi + NEPI * kEpiStageBytesPerWarp;              // per-CTA partial batch statistics [2][Cout]
   float* g_stats = reinterpret_cast<float*>(smem_gen + (s_st - smem_base));
   const uint32_t s_bar = s_st + 2 * p.Cout * 4;
   const uint32_t bar_fullA = s_bar;                    // [na]
