@@ -227,7 +227,14 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   // (4 epilogue warps instead of 8 when that leaves too little room for the halo ring)
   if (d.Cout == 64 && 9 * cbt * 64 * bkb <= 150 * 1024) { bn = 64; mt = 1; wres = 1; nepi = (9 * cbt * 64 * bkb > 80 * 1024) ? 4 : 8; }
   else if (d.Cout == 64) { bn = 64; mt = 2; wres = 0; }
-  else { bn = 128; mt = 2; wres = 0; }
+  else {
+    // streamed weights: M = 256 (two tiles share every weight stage) x N = 128 when there is enough work to fill the
+    // SMs; small batches trade weight re-use for parallelism (more, smaller work items)
+    const long mtl = (long)((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
+    bn = 128; mt = 2; wres = 0;
+    if (((mtl + 1) / 2) * (d.Cout / 128) < num_sms) mt = 1;
+    if (mt == 1 && mtl * (d.Cout / 128) < num_sms) bn = 64;
+  }
   GSD_CHECK(bkb == 128 || wres, "halo conv: first-layer path needs resident weights");
   const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
   const int b_bytes = bn * bkb;
@@ -289,6 +296,8 @@ inline int run_halo_launch(const HaloLaunch& L, cudaStream_t st) {
   if (L.bn == 64 && L.mt == 1 && L.wres && L.nepi == 8) return launch_halo_cfg<64, 1, true, 128, 8>(L, st);
   if (L.bn == 64 && L.mt == 1 && L.wres && L.nepi == 4) return launch_halo_cfg<64, 1, true, 128, 4>(L, st);
   if (L.bn == 64 && L.mt == 2 && !L.wres) return launch_halo_cfg<64, 2, false, 128, 8>(L, st);
+  if (L.bn == 64 && L.mt == 1 && !L.wres) return launch_halo_cfg<64, 1, false, 128, 8>(L, st);
+  if (L.bn == 128 && L.mt == 1 && !L.wres) return launch_halo_cfg<128, 1, false, 128, 8>(L, st);
   if (L.bn == 128 && L.mt == 2 && !L.wres) return launch_halo_cfg<128, 2, false, 128, 8>(L, st);
   return fail(-1, "halo conv: no kernel for bn=%d mt=%d wres=%d nepi=%d", L.bn, L.mt, L.wres, L.nepi);
 }
