@@ -333,7 +333,7 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   p.stages = 4;
   const int blocks = p.co_blocks * (p.cb0 + p.cb1) * (first ? 1 : 2);
   const long m_tiles = (long)p.tiles_x * p.tiles_y * B;
-  int split = blocks >= num_sms ? 1 : (num_sms + blocks / 2) / blocks;
+  int split = blocks >= num_sms ? 1 : num_sms / blocks;   // grid <= #SMs: a second, nearly empty wave would double the time
   if (split > m_tiles) split = (int)m_tiles;
   if (split < 1) split = 1;
   p.split = split;
@@ -395,7 +395,7 @@ inline int build_wgrad_pw_launch(const void* in, int Cin, const void* du, int Co
   p.Cin = Cin; p.Cout = Cout; p.dw = dw;
   const int blocks = (Cin / 128) * (Cout / 64);
   const long m_tiles = (long)p.tiles_x * p.tiles_y * B;
-  int split = blocks >= num_sms ? 1 : (num_sms + blocks / 2) / blocks;
+  int split = blocks >= num_sms ? 1 : num_sms / blocks;   // grid <= #SMs: a second, nearly empty wave would double the time
   if (split > m_tiles) split = (int)m_tiles;
   if (split < 1) split = 1;
   p.split = split;

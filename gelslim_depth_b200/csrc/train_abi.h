@@ -131,7 +131,7 @@ extern "C" int gsd_op_head_bwd(const void* a, const float* dy, const float* w, i
   GSD_CHECK(a && dy && w && da && dw && db && ncls >= 1 && ncls <= 4, "gsd_op_head_bwd: bad argument");
   const long npix = (long)H * W;
   long tiles = (npix * B + 127) / 128;
-  int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+  int grid = (int)(tiles < 148 * 4 ? tiles : 148 * 4);
   head_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), dy, w, npix, B, ncls,
                                                                       static_cast<__nv_bfloat16*>(da), dw, db);
   GSD_CUDA(cudaGetLastError());

@@ -119,68 +119,89 @@ __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ y, c
 }
 
 // OutConv backward (unet.py:54): da[pix][c] = sum_k dy[k][pix] w[k][c]; dw[k][c] += sum_pix dy a; db[k] += sum dy.
-// 128 threads; per 128-pixel tile: phase 1 thread = pixel, phase 2 thread = (k, c) pair.
+// One thread = one pixel (its 64 channels = 8 x 16-byte loads).  dW needs sum over pixels of dy[k]*a[c]: a 31-shuffle
+// butterfly transpose-reduce per 32 channels leaves lane l with the warp total of channel l, which it keeps
+// accumulating in registers across the grid-stride loop; one atomic per lane per (k, half) at the very end.
+__device__ __forceinline__ float warp_transpose_reduce32(float (&s)[32], int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int n = 16 >> step, mask = 16 >> step;
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? s[i] : s[i + n];
+      const float keep = upper ? s[i + n] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+  }
+  return s[0];
+}
+
 __global__ void __launch_bounds__(128) head_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ dy,
                                                        const float* __restrict__ w, long npix_per_img, int B, int ncls,
                                                        __nv_bfloat16* __restrict__ da, float* __restrict__ dw,
                                                        float* __restrict__ db) {
   __shared__ float s_w[4 * 64];
-  __shared__ float s_dy[4][128];
-  __shared__ __nv_bfloat16 s_a[128][64 + 8];
   for (int i = threadIdx.x; i < ncls * 64; i += 128) s_w[i] = w[i];
-  float acc_w[2] = {0.f, 0.f};      // (k, c) pairs: index t and t+128 (ncls <= 4 -> 256 pairs)
-  float acc_b = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float acc_w[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // [k][half]: channel lane + 32*half
+  float acc_b[4] = {0.f, 0.f, 0.f, 0.f};
   const long total = npix_per_img * B;
-  for (long t0 = (long)blockIdx.x * 128; t0 < total; t0 += (long)gridDim.x * 128) {
-    __syncthreads();
-    const long pix = t0 + threadIdx.x;
+  const long total_pad = (total + 31) / 32 * 32;          // whole warps iterate together (shuffles)
+  for (long pix = blockIdx.x * 128L + threadIdx.x; pix < total_pad; pix += (long)gridDim.x * 128) {
     float g[4] = {0.f, 0.f, 0.f, 0.f};
-    if (pix < total) {
+    float av[64];
+    const bool live = pix < total;
+    if (live) {
       const long b = pix / npix_per_img, pp = pix - b * npix_per_img;
       for (int k = 0; k < ncls; ++k) g[k] = dy[(b * ncls + k) * npix_per_img + pp];
       const uint4* src = reinterpret_cast<const uint4*>(a + pix * 64);
       uint4* dst = reinterpret_cast<uint4*>(da + pix * 64);
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
-        *reinterpret_cast<uint4*>(&s_a[threadIdx.x][ch * 8]) = src[ch];
-        float f[8];
+        float t[8], f[8];
+        unpack8(src[ch], t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          av[ch * 8 + j] = t[j];
           float v = 0.f;
-          for (int k = 0; k < ncls; ++k) v = fmaf(g[k], s_w[k * 64 + ch * 8 + j], v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < ncls) v = fmaf(g[k], s_w[k * 64 + ch * 8 + j], v);
           f[j] = v;
         }
         dst[ch] = pack8(f);
       }
     } else {
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(&s_a[threadIdx.x][ch * 8]) = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < 64; ++c) av[c] = 0.f;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s_dy[k][threadIdx.x] = g[k];
-    __syncthreads();
+    for (int k = 0; k < 4; ++k) {
+      if (k < ncls) {          // block-uniform
+        acc_b[k] += g[k];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int pair = threadIdx.x + 128 * r;
-      const int k = pair >> 6, c = pair & 63;
-      if (k < ncls) {
-        float s = 0.f;
-        for (int pz = 0; pz < 128; ++pz) s = fmaf(s_dy[k][pz], __bfloat162float(s_a[pz][c]), s);
-        acc_w[r] += s;
+        for (int h = 0; h < 2; ++h) {
+          float s[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = g[k] * av[32 * h + i];
+          acc_w[k][h] += warp_transpose_reduce32(s, lane);
+        }
       }
     }
-    if (threadIdx.x < ncls) {
-      float s = 0.f;
-      for (int pz = 0; pz < 128; ++pz) s += s_dy[threadIdx.x][pz];
-      acc_b += s;
-    }
   }
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int pair = threadIdx.x + 128 * r;
-    if ((pair >> 6) < ncls) atomicAdd(dw + pair, acc_w[r]);
+  for (int k = 0; k < 4; ++k) {
+    if (k < ncls) {
+      atomicAdd(dw + k * 64 + lane, acc_w[k][0]);
+      atomicAdd(dw + k * 64 + 32 + lane, acc_w[k][1]);
+      float sb = acc_b[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+      if (lane == 0) atomicAdd(db + k, sb);
+    }
   }
-  if (threadIdx.x < ncls) atomicAdd(db + threadIdx.x, acc_b);
 }
 
 // BatchNorm+ReLU backward, reduction pass: sums[c] = sum g, sums[C+c] = sum g*zhat, g = da*(a>0), zhat=(z-mean)*rstd.
@@ -203,21 +224,34 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
     mu[j] = z ? mean[c8 * 8 + j] : 0.f; rs[j] = z ? rstd[c8 * 8 + j] : 0.f;
     sc[j] = z ? scale[c8 * 8 + j] : 0.f; sh[j] = z ? shift[c8 * 8 + j] : 0.f;
   }
-  for (long px = p0; px < npix; px += pstep) {
-    float g[8];
-    unpack8(*reinterpret_cast<const uint4*>(da + px * da_pix_stride + c8 * 8), g);
-    if (z) {
-      float zv[8];
-      unpack8(*reinterpret_cast<const uint4*>(z + px * C + c8 * 8), zv);
+  for (long px0 = p0; px0 < npix; px0 += 4 * pstep) {
+    uint4 ug[4], uz[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gg = (zv[j] * sc[j] + sh[j]) > 0.f ? g[j] : 0.f;
-        s1[j] += gg;
-        s2[j] += gg * (zv[j] - mu[j]) * rs[j];
+    for (int u = 0; u < 4; ++u) {            // issue all loads of 4 pixels first (memory-level parallelism)
+      const long px = px0 + u * pstep;
+      if (px < npix) {
+        ug[u] = *reinterpret_cast<const uint4*>(da + px * da_pix_stride + c8 * 8);
+        if (z) uz[u] = *reinterpret_cast<const uint4*>(z + px * C + c8 * 8);
       }
-    } else {
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s1[j] += g[j];
+    for (int u = 0; u < 4; ++u) {
+      if (px0 + u * pstep >= npix) break;
+      float g[8];
+      unpack8(ug[u], g);
+      if (z) {
+        float zv[8];
+        unpack8(uz[u], zv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = (zv[j] * sc[j] + sh[j]) > 0.f ? g[j] : 0.f;
+          s1[j] += gg;
+          s2[j] += gg * (zv[j] - mu[j]) * rs[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] += g[j];
+      }
     }
   }
   // block reduce per chunk through smem atomics, then one global atomic per channel per block
@@ -257,17 +291,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     k2[j] = sums[c] * inv;
     k3[j] = sums[C + c] * inv;
   }
-  for (long px = p0; px < npix; px += pstep) {
-    float g[8], zv[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(da + px * da_pix_stride + c8 * 8), g);
-    unpack8(*reinterpret_cast<const uint4*>(z + px * C + c8 * 8), zv);
+  for (long px0 = p0; px0 < npix; px0 += 4 * pstep) {
+    uint4 ug[4], uz[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gg = (zv[j] * sc[j] + sh[j]) > 0.f ? g[j] : 0.f;
-      const float zh = (zv[j] - mu[j]) * rs[j];
-      o[j] = k1[j] * (gg - k2[j] - zh * k3[j]);
+    for (int u = 0; u < 4; ++u) {
+      const long px = px0 + u * pstep;
+      if (px < npix) {
+        ug[u] = *reinterpret_cast<const uint4*>(da + px * da_pix_stride + c8 * 8);
+        uz[u] = *reinterpret_cast<const uint4*>(z + px * C + c8 * 8);
+      }
     }
-    *reinterpret_cast<uint4*>(dz + px * C + c8 * 8) = pack8(o);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long px = px0 + u * pstep;
+      if (px >= npix) break;
+      float g[8], zv[8], o[8];
+      unpack8(ug[u], g);
+      unpack8(uz[u], zv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = (zv[j] * sc[j] + sh[j]) > 0.f ? g[j] : 0.f;
+        const float zh = (zv[j] - mu[j]) * rs[j];
+        o[j] = k1[j] * (gg - k2[j] - zh * k3[j]);
+      }
+      *reinterpret_cast<uint4*>(dz + px * C + c8 * 8) = pack8(o);
+    }
   }
 }
 
