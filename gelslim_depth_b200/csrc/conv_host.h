@@ -331,13 +331,15 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   p.Cout = Cout; p.co_blocks = (Cout + 127) / 128;
   p.dw = dw;
   p.stages = 4;
-  const int blocks = p.co_blocks * (p.cb0 + p.cb1) * (first ? 1 : 2);
+  // XB = 128: each dW block is served by 3*split CTAs (2*split for filter rows {0,1}, split for row {2})
+  const int blocks = p.co_blocks * (p.cb0 + p.cb1);
+  const int per = first ? 1 : 3;
   const long m_tiles = (long)p.tiles_x * p.tiles_y * B;
-  int split = blocks >= num_sms ? 1 : num_sms / blocks;   // grid <= #SMs: a second, nearly empty wave would double the time
+  int split = blocks * per >= num_sms ? 1 : num_sms / (blocks * per);   // grid <= #SMs: no nearly empty second wave
   if (split > m_tiles) split = (int)m_tiles;
   if (split < 1) split = 1;
   p.split = split;
-  L->grid = blocks * split;
+  L->grid = blocks * per * split;
   L->smem = p.stages * (2 * kWgDzBytes + (180 * xb + 1023) / 1024 * 1024) + 1024 + 512;
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};

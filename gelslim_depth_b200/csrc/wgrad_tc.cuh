@@ -7,9 +7,12 @@
 //   A = dZ tile  : one TMA box (64 co, 8, 16) per 64-channel block = 128 pixels x 128 B, pixels are the K rows
 //   B = X halo   : the same (16+2)x(8+2) halo box the forward kernel uses; the tap shift is again only a shifted
 //                  descriptor start ((2k+dy)*10+dx rows) with the 8-pixel K atoms 1280 bytes apart
-// One UMMA (K = 16) covers two image rows of the 16x8 tile; 8 UMMAs per tap per tile.  A CTA owns one
-// (128 co) x (64 ci) x (group of taps) block of dW, keeps it in TMEM (taps x 64 fp32 columns) while it streams
-// its share of the pixel tiles (split-K across CTAs), and adds it to the fp32 gradient with red.global at the end.
+// One UMMA (K = 16) covers two image rows of the 16x8 tile.  The three dx taps of one filter row are ONE instruction
+// with N = 3 x 64: their B operands are the same halo shifted by one pixel each, i.e. three MN blocks exactly 128 bytes
+// apart (the descriptor's leading-byte-offset).  That makes the instruction tensor-bound (A 32 + B 48 smem wavefronts
+// per 96 tensor cycles) where three N = 64 instructions were smem-bound (3 x 48 per 96).  A CTA owns one
+// (128 co) x (64 ci) x (filter rows {0,1} or {2}) block of dW in TMEM (2 x 192 or 192 fp32 columns) while it streams
+// its share of the pixel tiles (split-K across CTAs; the {0,1} group gets twice as many CTAs), then red.global-adds it.
 // Cout == 64: the second half of the 128-row A operand re-reads the first (its accumulator rows are ignored).
 #pragma once
 #include <cuda_bf16.h>
@@ -34,7 +37,7 @@ struct WgradParams {
   int tiles_x, tiles_y, batch;
   int Cout;
   int co_blocks;         // ceil(Cout / 128)
-  int split;             // CTAs sharing one dW block (split-K over pixel tiles)
+  int split;             // XB = 128: CTAs of tap group {2} per dW block (group {0,1} gets 2*split); XB = 32: CTAs per block
   int stages;
 };
 
@@ -81,22 +84,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  // block decode: blockIdx.x = ((co_blk * cbt + ci_blk) * tap_groups + tap_group) * split + s
+  // block decode.  XB = 128: blockIdx.x = (co_blk * cbt + ci_blk) * 3*split + r, r < 2*split -> filter rows {0,1},
+  // else filter row {2};  XB = 32: blockIdx.x = block * split + s, all 9 taps.
   const int cbt = p.cb0 + p.cb1;
   int bid = blockIdx.x;
-  const int s = bid % p.split; bid /= p.split;
-  int tg = 0;
-  if (XB == 128) { tg = bid & 1; bid >>= 1; }
+  int s, tg = 0, nsplit = p.split;
+  if (XB == 128) {
+    const int r = bid % (3 * p.split);
+    bid /= 3 * p.split;
+    if (r < 2 * p.split) { tg = 0; s = r; nsplit = 2 * p.split; }
+    else { tg = 1; s = r - 2 * p.split; nsplit = p.split; }
+  } else {
+    s = bid % p.split;
+    bid /= p.split;
+  }
   const int ci_blk = bid % cbt;
   const int co_blk = bid / cbt;
-  const int tap0 = (XB == 128) ? (tg ? 5 : 0) : 0, ntap = (XB == 128) ? (tg ? 4 : 5) : 9;
+  const int dy0 = tg ? 2 : 0, ndy = tg ? 1 : 2;                 // XB = 128 only
+  const int tap0 = 0, ntap = 9;                                 // XB = 32 only
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
   const bool half_m = (p.Cout - co_blk * 128) < 128;      // only 64 real co rows
 
   if (warp == 0) {
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
-      for (int t = s; t < m_tiles; t += p.split) {
+      for (int t = s; t < m_tiles; t += nsplit) {
         const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
         mbar_wait(bar_empty + 8 * st, ph ^ 1);
         const uint32_t sa = s_stage + st * STAGE, fb = bar_full + 8 * st;
@@ -114,22 +126,37 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     // instruction descriptor: fp32 accum, bf16 A/B, A and B MN-major (bits 15, 16), N = NT, M = 128
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (((uint32_t)NT >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t b_hi = ((10u * XB) >> 4) | (1u << 14) | (XLAYOUT << 29);   // K atoms = image rows, 10 halo pixels apart
+    // N = 192: the three dx taps of a filter row in one instruction (XB = 128)
+    constexpr uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((192u >> 3) << 17) | ((128u >> 4) << 24);
     int st = 0; uint32_t ph = 0;
     bool first = true;
-    for (int t = s; t < m_tiles; t += p.split) {
+    for (int t = s; t < m_tiles; t += nsplit) {
       mbar_wait(bar_full + 8 * st, ph);
       tc_fence_after();
       const uint32_t sa = s_stage + st * STAGE;
       const uint32_t a_lbo = half_m ? 0u : (uint32_t)kWgDzBytes;
       if (elect_one()) {
-        for (int tp = 0; tp < ntap; ++tp) {
-          const int tap = tap0 + tp, dy = tap / 3, dx = tap % 3;
-          const uint32_t d_tmem = tmem_base + tp * NT;
+        if (XB == 128) {
+          for (int dyi = 0; dyi < ndy; ++dyi) {
+            const uint32_t d_tmem = tmem_base + dyi * 192;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t a_lo = mn_desc_lo(sa + k * 2048, a_lbo);
-            const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy) * 10 + dx) * XB, 0);
-            umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, b_hi, idesc, (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t a_lo = mn_desc_lo(sa + k * 2048, a_lbo);
+              // three MN blocks (dx = 0, 1, 2) one halo pixel = 128 bytes apart
+              const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy0 + dyi) * 10) * 128, 128);
+              umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, b_hi, idesc3, (first && k == 0) ? 0u : 1u);
+            }
+          }
+        } else {
+          for (int tp = 0; tp < ntap; ++tp) {
+            const int tap = tap0 + tp, dy = tap / 3, dx = tap % 3;
+            const uint32_t d_tmem = tmem_base + tp * NT;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t a_lo = mn_desc_lo(sa + k * 2048, a_lbo);
+              const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy) * 10 + dx) * XB, 0);
+              umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, b_hi, idesc, (first && k == 0) ? 0u : 1u);
+            }
           }
         }
         umma_commit(bar_empty + 8 * st);
@@ -150,14 +177,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const int ctot = cbt * NT;
     const bool live = (s < m_tiles) && co < p.Cout && !(half_m && row >= 64);
     if (XB == 128) {
-      for (int tp = 0; tp < ntap; ++tp) {
+      for (int tp = 0; tp < 3 * ndy; ++tp) {         // accumulator column block tp*64 <-> tap (dy0 + tp/3, tp%3)
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + tp * 64 + c0 + ((uint32_t)(q * 32) << 16), v);
           tmem_ld_wait();
           if (live) {
-            float* dst = p.dw + ((size_t)co * 9 + tap0 + tp) * ctot + ci_blk * 64 + c0;
+            float* dst = p.dw + ((size_t)co * 9 + dy0 * 3 + tp) * ctot + ci_blk * 64 + c0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
           }
