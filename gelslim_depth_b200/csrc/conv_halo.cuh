@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_launch_dependents();      // the next layer may start its own setup while this grid drains
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
   const int m_groups = (m_tiles + MT - 1) / MT;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
       }
       int ia = 0, ib = 0;
       uint32_t pa = 0, pb = 0;
+      pdl_wait();               // activations of the previous layer are complete from here on (weights were not its output)
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         uint32_t mg, nt;
         fdivmod((uint32_t)item, p.fd_ntiles, mg, nt);
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __gr
     const int Hp = p.H >> 1, Wp = p.W >> 1;
     const bool hx = lane & 1, hy = (lane >> 3) & 1;   // which half of a pooling exchange this lane keeps
     int it = 0;
+    pdl_wait();                 // no global write before the predecessor grid has finished (it may still read our output buffers' neighbours)
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
       if (NEPI == 8 && buf != eset) continue;          // the other warp set owns this accumulator buffer

@@ -32,8 +32,26 @@ struct ConvDesc {
   int s2d = 0, s2d_Hf = 0, s2d_Wf = 0, s2d_off_y = 0, s2d_off_x = 0;
 };
 
+// launch `kernel` with `params`, optionally as a programmatic dependent launch (see gsd_ptx.cuh)
+template <class Params>
+inline int launch_maybe_pdl(void (*kernel)(Params), const Params& params, int grid, int block, int smem, cudaStream_t st, int pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  GSD_CUDA(cudaLaunchKernelEx(&cfg, kernel, params));
+  return 0;
+}
+
 struct ConvLaunch {
   ConvParams p;
+  int pdl = 0;                 // programmatic dependent launch (inference plan only)
   int bn = 0, bkb = 0, grid = 0;
   double flops = 0;            // 2*M*N*K of the real (unpadded) problem
 };
@@ -154,9 +172,7 @@ inline int launch_conv_cfg(const ConvLaunch& L, cudaStream_t st) {
     GSD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  conv_tc_kernel<BN, BKB><<<L.grid, kConvThreads, Cfg::SMEM_BYTES, st>>>(L.p);
-  GSD_CUDA(cudaGetLastError());
-  return 0;
+  return launch_maybe_pdl(conv_tc_kernel<BN, BKB>, L.p, L.grid, kConvThreads, Cfg::SMEM_BYTES, st, L.pdl);
 }
 
 inline int run_conv_launch(const ConvLaunch& L, cudaStream_t st) {
@@ -179,6 +195,7 @@ namespace gsd {
 
 struct HaloLaunch {
   HaloParams p;
+  int pdl = 0;
   int bn = 0, mt = 0, wres = 0, bkb = 0, nepi = 8, grid = 0, smem = 0;
   double flops = 0;
 };
@@ -286,9 +303,7 @@ inline int launch_halo_cfg(const HaloLaunch& L, cudaStream_t st) {
     GSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, WRES, BKB, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
     attr_smem = L.smem;
   }
-  conv_halo_kernel<BN, MT, WRES, BKB, NEPI><<<L.grid, 64 + 32 * NEPI, L.smem, st>>>(L.p);
-  GSD_CUDA(cudaGetLastError());
-  return 0;
+  return launch_maybe_pdl(conv_halo_kernel<BN, MT, WRES, BKB, NEPI>, L.p, L.grid, 64 + 32 * NEPI, L.smem, st, L.pdl);
 }
 
 inline int run_halo_launch(const HaloLaunch& L, cudaStream_t st) {

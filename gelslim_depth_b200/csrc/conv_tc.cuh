@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_launch_dependents();
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
   const int total_tiles = m_tiles * p.n_tiles;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      pdl_wait();
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         uint32_t mt, nt, trow, tx, b, ty;
         fdivmod((uint32_t)tile, p.fd_ntiles, mt, nt);
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     const int Hp = p.H >> 1, Wp = p.W >> 1;
     const bool hx = lane & 1, hy = (lane & p.tw) != 0;   // pooling needs tw in {8, 16}: both window rows in one warp
     int it = 0;
+    pdl_wait();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       if (acc != eset) continue;

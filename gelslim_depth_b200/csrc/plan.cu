@@ -301,12 +301,15 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
         return 0;
       }
       AnyLaunch A;
+      const int pdl = getenv("GSD_NO_PDL") ? 0 : 1;
       if (use_halo(d)) {
         A.halo = 1;
         GSD_TRY(build_halo_launch(d, p->num_sms, &A.hl));
+        A.hl.pdl = pdl;
         A.flops = A.hl.flops;
       } else {
         GSD_TRY(build_conv_launch(d, p->num_sms, &A.tc));
+        A.tc.pdl = pdl;
         A.flops = A.tc.flops;
       }
       p->conv_flops += A.flops;
