@@ -2,6 +2,9 @@
 #pragma once
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <mutex>
+#include <vector>
 
 #include "conv_tc.cuh"
 #include "host_util.h"
@@ -331,6 +334,65 @@ struct WgradLaunch {
   double flops = 0;
 };
 
+// Split-K plan of the XB = 128 weight-gradient kernel.  A dW block (128 co x 64 ci x 9 taps) is produced by n0 CTAs
+// that each accumulate filter rows {0,1} over 1/n0 of the pixel tiles (2 row-passes per tile) and n1 CTAs that
+// accumulate filter row {2} over 1/n1 of them.  CTAs are launched longest-first and the hardware block scheduler hands
+// the next one to whichever SM frees up, so the cost of a plan is the makespan of that greedy schedule; every CTA
+// also pays a fixed set-up + drain cost (`ovh`, in row-passes).  Exhaustive search over (n0, n1), grid <= 4 waves.
+inline double wgrad_makespan(long heavy, double c0, long light, double c1, int P) {
+  const long r = heavy / P, q = heavy % P;
+  const double t_early = r * c0, t_late = (r + 1) * c0;      // P-q SMs are free at t_early, q at t_late
+  const double heavy_end = q ? t_late : t_early;
+  if (light == 0) return heavy_end;
+  auto fits = [&](double T) {
+    long n = 0;
+    if (T > t_early) n += (P - q) * (long)((T - t_early) / c1 + 1e-9);
+    if (T > t_late) n += q * (long)((T - t_late) / c1 + 1e-9);
+    return n >= light;
+  };
+  double lo = t_early, hi = t_late + (double)((light + P - 1) / P + 1) * c1;
+  for (int it = 0; it < 60; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (fits(mid)) hi = mid; else lo = mid;
+  }
+  return hi > heavy_end ? hi : heavy_end;
+}
+
+inline void wgrad_choose_split(int blocks, long m_tiles, int num_sms, int* n0_out, int* n1_out) {
+  if (const char* e = getenv("GSD_WG_SPLIT")) {            // experiments: "n0,n1"
+    int a = 0, b = 0;
+    if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { *n0_out = a; *n1_out = b; return; }
+  }
+  struct Key { int blocks; long m_tiles; int sms; int n0, n1; };
+  static std::mutex mu;
+  static std::vector<Key> cache;                           // the search costs ~10 ms: once per layer shape
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (const Key& k : cache)
+      if (k.blocks == blocks && k.m_tiles == m_tiles && k.sms == num_sms) { *n0_out = k.n0; *n1_out = k.n1; return; }
+  }
+  double ovh = 12.0, lf = 1.0;
+  if (const char* e = getenv("GSD_WG_OVH")) ovh = atof(e);
+  if (const char* e = getenv("GSD_WG_LF")) lf = atof(e);
+  const long max_grid = 4L * num_sms;
+  double best = 1e300;
+  int bn0 = 1, bn1 = 1;
+  for (int n0 = 1; n0 <= m_tiles && (long)blocks * (n0 + 1) <= (max_grid > blocks * 2L ? max_grid : blocks * 2L); ++n0) {
+    const double c0 = 2.0 * (double)((m_tiles + n0 - 1) / n0) + ovh;
+    for (int n1 = 1; n1 <= n0 && (long)blocks * (n0 + n1) <= (max_grid > blocks * 2L ? max_grid : blocks * 2L); ++n1) {
+      const double c1 = lf * (double)((m_tiles + n1 - 1) / n1) + ovh;
+      // longest-first: the kernel launches the two-row items first; if the one-row items are the longer ones the
+      // estimate is still an upper bound of the in-order greedy schedule within one item
+      const double t = c0 >= c1 ? wgrad_makespan((long)blocks * n0, c0, (long)blocks * n1, c1, num_sms)
+                                : wgrad_makespan((long)blocks * n1, c1, (long)blocks * n0, c0, num_sms);
+      if (t < best - 1e-9) { best = t; bn0 = n0; bn1 = n1; }
+    }
+  }
+  *n0_out = bn0; *n1_out = bn1;
+  std::lock_guard<std::mutex> g(mu);
+  cache.push_back(Key{blocks, m_tiles, num_sms, bn0, bn1});
+}
+
 inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, int H1, int W1, int off_y, int off_x,
                               const void* dz, int Cout, int B, int H, int W, float* dw, int num_sms, WgradLaunch* L) {
   memset(L, 0, sizeof *L);
@@ -346,15 +408,19 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   p.Cout = Cout; p.co_blocks = (Cout + 127) / 128;
   p.dw = dw;
   p.stages = 4;
-  // XB = 128: each dW block is served by 3*split CTAs (2*split for filter rows {0,1}, split for row {2})
   const int blocks = p.co_blocks * (p.cb0 + p.cb1);
-  const int per = first ? 1 : 3;
   const long m_tiles = (long)p.tiles_x * p.tiles_y * B;
-  int split = blocks * per >= num_sms ? 1 : num_sms / (blocks * per);   // grid <= #SMs: no nearly empty second wave
-  if (split > m_tiles) split = (int)m_tiles;
-  if (split < 1) split = 1;
-  p.split = split;
-  L->grid = blocks * per * split;
+  p.blocks = blocks;
+  if (first) {
+    int split = blocks >= num_sms ? 1 : num_sms / blocks;   // grid <= #SMs: no nearly empty second wave
+    if (split > m_tiles) split = (int)m_tiles;
+    p.split = split < 1 ? 1 : split;
+    L->grid = blocks * p.split;
+  } else {
+    wgrad_choose_split(blocks, m_tiles, num_sms, &p.n0, &p.n1);
+    L->grid = blocks * (p.n0 + p.n1);
+  }
+  if (const char* e = getenv("GSD_WG_FLAGS")) p.flags = atoi(e);
   L->smem = p.stages * (2 * kWgDzBytes + (180 * xb + 1023) / 1024 * 1024) + 1024 + 512;
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};

@@ -104,36 +104,63 @@ __global__ void __launch_bounds__(256) prologue_f32_kernel(const PreParams p, fl
 }
 
 // OutConv 1x1 + bias (unet.py:54) + denormalize_depth_image (normalization_utils.py:129):
-// (B,H,W,64) bf16 NHWC -> (B,ncls,H,W) fp32 NCHW.  One thread per pixel: 128 contiguous bytes in,
-// ncls coalesced floats out.
+// (B,H,W,64) bf16 NHWC -> (B,ncls,H,W) fp32 NCHW.  Eight lanes share a pixel (16 bytes each: a warp load is 512
+// contiguous bytes), a warp covers 32 pixels in 8 passes with all 8 loads in flight; the 8-lane partial dot
+// products are shuffle-reduced and routed so that lane L ends up with pixel L: one coalesced 128-byte store per class.
 template <int CIN>
 __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
                                                    const float* __restrict__ bias, int ncls, float out_scale,
                                                    float out_shift, long npix_per_img, int B, float* __restrict__ y) {
-  __shared__ float sw[4 * CIN];
-  __shared__ float sb[4];
-  for (int i = threadIdx.x; i < ncls * CIN; i += blockDim.x) sw[i] = w[i];
-  if (threadIdx.x < ncls) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
+  static_assert(CIN == 64, "head_kernel: the 1x1 head reads 64 channels");
+  const int lane = threadIdx.x & 31, grp = lane >> 3, c8 = lane & 7;
+  float wr[4][8], bk[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    bk[k] = k < ncls ? bias[k] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[k][j] = k < ncls ? w[k * CIN + c8 * 8 + j] : 0.f;
+  }
   const long total = npix_per_img * B;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const uint4* src = reinterpret_cast<const uint4*>(in + idx * CIN);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long base = (((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < total; base += nwarps * 32) {
+    uint4 u[8];
 #pragma unroll
-    for (int ch = 0; ch < CIN / 8; ++ch) {
-      const uint4 u = __ldg(src + ch);
-      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    for (int j = 0; j < 8; ++j) {
+      const long px = base + 4 * j + grp;
+      u[j] = px < total ? __ldg(reinterpret_cast<const uint4*>(in + px * CIN + c8 * 8)) : make_uint4(0, 0, 0, 0);
+    }
+    float outv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[j]));
-        const int c = ch * 8 + 2 * j;
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t uu[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+      float f[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < ncls) acc[k] += f.x * sw[k * CIN + c] + f.y * sw[k * CIN + c + 1];
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[i]));
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < ncls) {          // warp-uniform
+          float sacc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sacc = fmaf(f[i], wr[k][i], sacc);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+          // pixel base + L = base + 4*(L>>2) + (L&3): produced in pass L>>2 by lane group L&3
+          const float got = __shfl_sync(0xffffffffu, sacc, (lane & 3) * 8);
+          if ((lane >> 2) == j) outv[k] = got;
+        }
       }
     }
-    const long b = idx / npix_per_img, pix = idx - b * npix_per_img;
-    for (int k = 0; k < ncls; ++k) y[(b * ncls + k) * npix_per_img + pix] = (acc[k] + sb[k]) * out_scale + out_shift;
+    const long px = base + lane;
+    if (px < total) {
+      const long b = px / npix_per_img, pix = px - b * npix_per_img;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < ncls) y[(b * ncls + k) * npix_per_img + pix] = (outv[k] + bk[k]) * out_scale + out_shift;
+    }
   }
 }
 

@@ -102,9 +102,15 @@ extern "C" int gsd_op_bn_finalize(const float* stats, double count, const float*
 extern "C" int gsd_op_bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H, int W, int C, void* a,
                                     void* pooled, void* stream) {
   GSD_CHECK(z && scale && shift && a && C % 8 == 0, "gsd_op_bn_relu_apply: bad argument");
-  const long total = (long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  bn_relu_apply_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C, static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(pooled));
+  const int C8 = C / 8;
+  GSD_CHECK((C8 & (C8 - 1)) == 0 && C8 <= 256, "gsd_op_bn_relu_apply: C/8 must be a power of two <= 256");
+  int c8_shift = 0;
+  while ((1 << c8_shift) < C8) ++c8_shift;
+  const long rows = (long)B * ((H + 1) / 2);
+  const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+  bn_relu_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C, c8_shift, static_cast<__nv_bfloat16*>(a),
+      static_cast<__nv_bfloat16*>(pooled));
   GSD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -130,10 +136,19 @@ extern "C" int gsd_op_head_bwd(const void* a, const float* dy, const float* w, i
                                float* db, void* stream) {
   GSD_CHECK(a && dy && w && da && dw && db && ncls >= 1 && ncls <= 4, "gsd_op_head_bwd: bad argument");
   const long npix = (long)H * W;
-  long tiles = (npix * B + 127) / 128;
-  int grid = (int)(tiles < 148 * 4 ? tiles : 148 * 4);
-  head_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), dy, w, npix, B, ncls,
-                                                                      static_cast<__nv_bfloat16*>(da), dw, db);
+  GSD_CHECK(npix * B < (1L << 31), "gsd_op_head_bwd: more than 2^31 pixels");
+  long blocks = (npix * B * 8 + 255) / 256;
+  const int grid = (int)(blocks < 148 * 4 ? blocks : 148 * 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* ab = static_cast<const __nv_bfloat16*>(a);
+  __nv_bfloat16* dab = static_cast<__nv_bfloat16*>(da);
+  const unsigned np = (unsigned)npix, tot = (unsigned)(npix * B);
+  switch (ncls) {
+    case 1: head_bwd_kernel<1><<<grid, 256, 0, st>>>(ab, dy, w, np, tot, dab, dw, db); break;
+    case 2: head_bwd_kernel<2><<<grid, 256, 0, st>>>(ab, dy, w, np, tot, dab, dw, db); break;
+    case 3: head_bwd_kernel<3><<<grid, 256, 0, st>>>(ab, dy, w, np, tot, dab, dw, db); break;
+    default: head_bwd_kernel<4><<<grid, 256, 0, st>>>(ab, dy, w, np, tot, dab, dw, db); break;
+  }
   GSD_CUDA(cudaGetLastError());
   return 0;
 }

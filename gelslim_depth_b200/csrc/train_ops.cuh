@@ -59,40 +59,59 @@ __global__ void negate_f32_kernel(const float* __restrict__ in, int n, float* __
   if (i < n) out[i] = -in[i];
 }
 
-// a = relu(z * scale + shift) (+ 2x2 max-pooled copy).  One thread = one 2x2 window x 8 channels.
+// a = relu(z * scale + shift) (+ 2x2 max-pooled copy).  A block walks (image, window-row) pairs; inside a window row
+// thread j owns the 2x2 window j / (C/8) x the 8-channel chunk j % (C/8).  C/8 is a power of two dividing the block
+// size, so the chunk (and its scale/shift registers) never changes and the index math is shifts: the kernel is a pure
+// stream of 16-byte loads and stores.
 __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, int B, int H, int W, int C,
-                                                            __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ pooled) {
+                                                            int c8_shift, __nv_bfloat16* __restrict__ a,
+                                                            __nv_bfloat16* __restrict__ pooled) {
   const int Hw = (H + 1) / 2, Ww = (W + 1) / 2, Hp = H / 2, Wp = W / 2, C8 = C / 8;
-  const long total = (long)B * Hw * Ww * C8;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % C8);
-    const int wx = (int)((idx / C8) % Ww);
-    const int wy = (int)((idx / ((long)C8 * Ww)) % Hw);
-    const long b = idx / ((long)C8 * Ww * Hw);
-    float sc[8], sh[8], mx[8];
+  const int c8 = threadIdx.x & (C8 - 1);
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = scale[c8 * 8 + j]; sh[j] = shift[c8 * 8 + j]; mx[j] = 0.f; }   // relu output >= 0
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int y = 2 * wy + dy, x = 2 * wx + dx;
-        if (y < H && x < W) {
-          const long off = ((b * H + y) * W + x) * C + c8 * 8;
-          float f[8];
-          unpack8(*reinterpret_cast<const uint4*>(z + off), f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j] * sc[j] + sh[j], 0.f);
-          const uint4 o = pack8(f);
-          *reinterpret_cast<uint4*>(a + off) = o;
-          float r[8];
-          unpack8(o, r);                          // pool the ROUNDED values: pooled == max_pool2d(a) exactly
-#pragma unroll
-          for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], r[j]);
-        }
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c8 * 8 + j]; sh[j] = shift[c8 * 8 + j]; }
+  const int per_row = Ww << c8_shift;                       // (window, chunk) pairs of one window row
+  const long rows = (long)B * Hw;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / Hw), wy = (int)(row - (long)b * Hw);
+    const int y0 = 2 * wy;
+    const bool two_rows = y0 + 1 < H;
+    const __nv_bfloat16* zr = z + ((size_t)b * H + y0) * W * C;
+    __nv_bfloat16* ar = a + ((size_t)b * H + y0) * W * C;
+    __nv_bfloat16* pr = pooled ? pooled + ((size_t)b * Hp + wy) * Wp * C : nullptr;
+    const size_t rs = (size_t)W * C;
+    for (int j = threadIdx.x; j < per_row; j += 256) {
+      const int wx = j >> c8_shift;
+      const int x0 = 2 * wx;
+      const bool two_cols = x0 + 1 < W;
+      const size_t o00 = (size_t)x0 * C + c8 * 8;
+      uint4 u[4];
+      u[0] = *reinterpret_cast<const uint4*>(zr + o00);
+      if (two_cols) u[1] = *reinterpret_cast<const uint4*>(zr + o00 + C);
+      if (two_rows) {
+        u[2] = *reinterpret_cast<const uint4*>(zr + rs + o00);
+        if (two_cols) u[3] = *reinterpret_cast<const uint4*>(zr + rs + o00 + C);
       }
-    if (pooled && wy < Hp && wx < Wp) *reinterpret_cast<uint4*>(pooled + ((b * Hp + wy) * Wp + wx) * C + c8 * 8) = pack8(mx);
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = 0.f;               // relu output >= 0
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (((q & 1) && !two_cols) || ((q >> 1) && !two_rows)) continue;
+        float f[8], r[8];
+        unpack8(u[q], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i] * sc[i] + sh[i], 0.f);
+        const uint4 o = pack8(f);
+        *reinterpret_cast<uint4*>(ar + (q >> 1) * rs + o00 + (q & 1) * C) = o;
+        unpack8(o, r);                                       // pool the ROUNDED values: pooled == max_pool2d(a) exactly
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], r[i]);
+      }
+      if (pr && wy < Hp && wx < Wp) *reinterpret_cast<uint4*>(pr + (size_t)wx * C + c8 * 8) = pack8(mx);
+    }
   }
 }
 
@@ -119,89 +138,73 @@ __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ y, c
 }
 
 // OutConv backward (unet.py:54): da[pix][c] = sum_k dy[k][pix] w[k][c]; dw[k][c] += sum_pix dy a; db[k] += sum dy.
-// One thread = one pixel (its 64 channels = 8 x 16-byte loads).  dW needs sum over pixels of dy[k]*a[c]: a 31-shuffle
-// butterfly transpose-reduce per 32 channels leaves lane l with the warp total of channel l, which it keeps
-// accumulating in registers across the grid-stride loop; one atomic per lane per (k, half) at the very end.
-__device__ __forceinline__ float warp_transpose_reduce32(float (&s)[32], int lane) {
-#pragma unroll
-  for (int step = 0; step < 5; ++step) {
-    const int n = 16 >> step, mask = 16 >> step;
-    const bool upper = (lane & mask) != 0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const float send = upper ? s[i] : s[i + n];
-      const float keep = upper ? s[i + n] : s[i];
-      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-    }
-  }
-  return s[0];
-}
-
-__global__ void __launch_bounds__(128) head_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ dy,
-                                                       const float* __restrict__ w, long npix_per_img, int B, int ncls,
+// Eight threads share a pixel (16 bytes = 8 channels each: a warp reads / writes 512 contiguous bytes) and a thread
+// keeps the same 8-channel chunk for its whole pixel stride, so its 8 x ncls dW partial sums and weights live in
+// registers; four pixels are in flight per thread.  Block reduction through smem atomics, then one global atomic per
+// (class, channel) per block.
+template <int NCLS>
+__global__ void __launch_bounds__(256, 2) head_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ dy,
+                                                       const float* __restrict__ w, unsigned npix_per_img, unsigned total,
                                                        __nv_bfloat16* __restrict__ da, float* __restrict__ dw,
                                                        float* __restrict__ db) {
-  __shared__ float s_w[4 * 64];
-  for (int i = threadIdx.x; i < ncls * 64; i += 128) s_w[i] = w[i];
+  const int c8 = threadIdx.x & 7;
+  const unsigned p0 = (blockIdx.x * 256u + threadIdx.x) >> 3, pstep = (gridDim.x * 256u) >> 3;
+  constexpr int ncls = NCLS;
+  float wr[NCLS][8], acc[NCLS][8], accb[NCLS];
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) {
+    accb[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wr[k][j] = w[k * 64 + c8 * 8 + j]; acc[k][j] = 0.f; }
+  }
+  for (unsigned px0 = p0; px0 < total; px0 += 4 * pstep) {
+    uint4 ua[4];
+    float g[4][NCLS];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned px = px0 + u * pstep;
+      if (px < total) {
+        ua[u] = *reinterpret_cast<const uint4*>(a + (size_t)px * 64 + c8 * 8);
+        const unsigned b = px / npix_per_img, pp = px - b * npix_per_img;
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) g[u][k] = __ldg(dy + ((size_t)b * ncls + k) * npix_per_img + pp);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned px = px0 + u * pstep;
+      if (px >= total) break;
+      float f[8], o[8];
+      unpack8(ua[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) {
+          v = fmaf(g[u][k], wr[k][j], v);
+          acc[k][j] = fmaf(g[u][k], f[j], acc[k][j]);
+        }
+        o[j] = v;
+      }
+      *reinterpret_cast<uint4*>(da + (size_t)px * 64 + c8 * 8) = pack8(o);
+      if (c8 == 0) {
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) accb[k] += g[u][k];
+      }
+    }
+  }
+  __shared__ float red[4 * 64 + 4];
+  for (int i = threadIdx.x; i < 4 * 64 + 4; i += 256) red[i] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  float acc_w[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // [k][half]: channel lane + 32*half
-  float acc_b[4] = {0.f, 0.f, 0.f, 0.f};
-  const long total = npix_per_img * B;
-  const long total_pad = (total + 31) / 32 * 32;          // whole warps iterate together (shuffles)
-  for (long pix = blockIdx.x * 128L + threadIdx.x; pix < total_pad; pix += (long)gridDim.x * 128) {
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-    float av[64];
-    const bool live = pix < total;
-    if (live) {
-      const long b = pix / npix_per_img, pp = pix - b * npix_per_img;
-      for (int k = 0; k < ncls; ++k) g[k] = dy[(b * ncls + k) * npix_per_img + pp];
-      const uint4* src = reinterpret_cast<const uint4*>(a + pix * 64);
-      uint4* dst = reinterpret_cast<uint4*>(da + pix * 64);
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        float t[8], f[8];
-        unpack8(src[ch], t);
+  for (int k = 0; k < NCLS; ++k) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          av[ch * 8 + j] = t[j];
-          float v = 0.f;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < ncls) v = fmaf(g[k], s_w[k * 64 + ch * 8 + j], v);
-          f[j] = v;
-        }
-        dst[ch] = pack8(f);
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 64; ++c) av[c] = 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < ncls) {          // block-uniform
-        acc_b[k] += g[k];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float s[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = g[k] * av[32 * h + i];
-          acc_w[k][h] += warp_transpose_reduce32(s, lane);
-        }
-      }
-    }
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[k * 64 + c8 * 8 + j], acc[k][j]);
+    if (c8 == 0) atomicAdd(&red[256 + k], accb[k]);
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k < ncls) {
-      atomicAdd(dw + k * 64 + lane, acc_w[k][0]);
-      atomicAdd(dw + k * 64 + 32 + lane, acc_w[k][1]);
-      float sb = acc_b[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
-      if (lane == 0) atomicAdd(db + k, sb);
-    }
-  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncls * 64; i += 256) atomicAdd(dw + i, red[i]);
+  if ((int)threadIdx.x < ncls) atomicAdd(db + threadIdx.x, red[256 + threadIdx.x]);
 }
 
 // BatchNorm+ReLU backward, reduction pass: sums[c] = sum g, sums[C+c] = sum g*zhat, g = da*(a>0), zhat=(z-mean)*rstd.

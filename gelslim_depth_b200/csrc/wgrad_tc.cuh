@@ -37,8 +37,11 @@ struct WgradParams {
   int tiles_x, tiles_y, batch;
   int Cout;
   int co_blocks;         // ceil(Cout / 128)
-  int split;             // XB = 128: CTAs of tap group {2} per dW block (group {0,1} gets 2*split); XB = 32: CTAs per block
+  int split;             // XB = 32: CTAs per dW block (split-K over the pixel tiles)
+  int n0, n1;            // XB = 128: CTAs per dW block for filter rows {0,1} / for filter row {2}
+  int blocks;            // co_blocks * (cb0 + cb1)
   int stages;
+  int flags;             // bit 0 (experiments only): skip the drain
 };
 
 // MN-major, 128B-swizzled operand descriptor: LBO = distance between 64-element MN blocks, SBO = distance between
@@ -46,6 +49,11 @@ struct WgradParams {
 __device__ __forceinline__ uint32_t mn_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
 __device__ __forceinline__ uint32_t mn_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+
+__device__ __forceinline__ void red_add_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d)) : "memory");
 }
 
 // XB = bytes of one halo pixel record of X: 128 (64 channels, N = 64 per tap, taps split into 2 groups across CTAs)
@@ -84,16 +92,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  // block decode.  XB = 128: blockIdx.x = (co_blk * cbt + ci_blk) * 3*split + r, r < 2*split -> filter rows {0,1},
-  // else filter row {2};  XB = 32: blockIdx.x = block * split + s, all 9 taps.
+  // block decode.  XB = 128: the blocks*n0 two-row work items come first (they are the expensive ones: the block
+  // scheduler hands later CTAs to whichever SM frees up, so longest-first keeps the tail short), then the blocks*n1
+  // one-row items;  XB = 32: blockIdx.x = block * split + s, all 9 taps.
   const int cbt = p.cb0 + p.cb1;
   int bid = blockIdx.x;
   int s, tg = 0, nsplit = p.split;
   if (XB == 128) {
-    const int r = bid % (3 * p.split);
-    bid /= 3 * p.split;
-    if (r < 2 * p.split) { tg = 0; s = r; nsplit = 2 * p.split; }
-    else { tg = 1; s = r - 2 * p.split; nsplit = p.split; }
+    if (bid < p.blocks * p.n0) { tg = 0; nsplit = p.n0; }
+    else { tg = 1; nsplit = p.n1; bid -= p.blocks * p.n0; }
+    s = bid % nsplit;
+    bid /= nsplit;
   } else {
     s = bid % p.split;
     bid /= p.split;
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     tc_fence_after();
     const int co = co_blk * 128 + row;
     const int ctot = cbt * NT;
-    const bool live = (s < m_tiles) && co < p.Cout && !(half_m && row >= 64);
+    const bool live = (s < m_tiles) && co < p.Cout && !(half_m && row >= 64) && !(p.flags & 1);
     if (XB == 128) {
       for (int tp = 0; tp < 3 * ndy; ++tp) {         // accumulator column block tp*64 <-> tap (dy0 + tp/3, tp%3)
 #pragma unroll 1
@@ -186,7 +195,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           if (live) {
             float* dst = p.dw + ((size_t)co * 9 + dy0 * 3 + tp) * ctot + ci_blk * 64 + c0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);   // 16-byte aligned
           }
         }
       }
