@@ -228,6 +228,31 @@ def emit(line: dict):
         sys.stdout.flush()
 
 
+def bench_latency(torch, net, dev, base, frames=500):
+    """BASELINE configs[2]: batch-1 streaming through gelslim_depth_b200.streaming.DepthStream -- one interleaved uint8
+    camera frame pair in pinned host memory -> H2D -> fused forward -> D2H depth map, one CUDA-graph replay + host
+    synchronisation per frame pair; wall-clock per frame pair (host copy into the ring slot included)."""
+    import types
+    from gelslim_depth_b200.streaming import DepthStream
+    cfg = types.SimpleNamespace(input_tactile_image_size=(H, W), interp_method="area", norm_scale=0.9,
+                                image_normalization_method="0_255_to_0_1", image_normalization_parameters=None,
+                                depth_normalization_method="min_max_to_0_-1",
+                                depth_normalization_parameters=(-1.9180814027786255, 0.0))
+    ds = DepthStream(net, cfg, (H, W), base_tactile_image=base[0], output_size=(H, W), layout="hwc_u8", frame_pairs=False, slots=4)
+    g = torch.Generator().manual_seed(7)
+    cam = torch.randint(0, 256, (8, H, W, CIN), generator=g, dtype=torch.uint8)
+    for i in range(20):
+        ds(cam[i % 8])
+    ds.latencies_ms.clear()
+    for i in range(frames):
+        ds(cam[i % 8])
+    p50, p99 = ds.latency_percentiles((0.5, 0.99))
+    return {"metric": "b1_latency_ms_per_frame_pair", "p50_ms": p50, "p99_ms": p99, "frames": frames,
+            "what": "DepthStream: uint8 HWC 6x320x427 frame pair -> pinned ring slot -> CUDA-graph replay (H2D + difference image + "
+                    "U-Net + de-normalisation + D2H) -> host depth map; wall clock per frame pair incl. host sync",
+            "launches_per_replay": ds.plan.launches}
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -366,6 +391,8 @@ def main():
                 "conv_share_of_step": conv_ms / (conv_ms + other_ms),
                 "flops_per_launch_set": conv_flops, "algorithmic_gflop_per_frame": GFLOP_PER_FRAME}
 
+    latency = bench_latency(torch, net, dev, base)
+
     cpu = None
     if not args.no_cpu_baseline:
         fps, cores, sample = cpu_reference_fps(torch)
@@ -383,7 +410,8 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * CIN * H * W * 4,
                     "d2h_bytes_per_step": B * NCLS * H * W * 4, "steps": e2e_steps, "chunk_frames": chunk,
                     "api": "gsd_forward_host (pinned fp32 frames in, fp32 depth maps out, copies inside the timed region)"},
-            "gpu_launches": plan.launches * args.steps, "clocks": clocks, "train": train, "layers": table}
+            "gpu_launches": plan.launches * args.steps, "clocks": clocks, "train": train, "latency": latency,
+            "layers": table}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

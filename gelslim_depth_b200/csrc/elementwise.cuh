@@ -14,7 +14,7 @@ struct PreParams {
   int use_diff;
   int B, C, Hr, Wr, H, W;
   int split_fingers;   // general_dataset.py:71: network batch b -> finger b / (B/2) (channels [f*C, f*C+C)) of frame b % (B/2)
-  int input_u8;        // frames are uint8 (camera bytes) instead of float 0..255
+  int input_u8;        // 0: float 0..255 NCHW; 1: uint8 NCHW; 2: uint8 NHWC (interleaved camera bytes, (B, Hr, Wr, C))
   float in_scale[8], in_shift[8];
 };
 
@@ -25,6 +25,11 @@ __device__ __forceinline__ long pre_plane(const PreParams& p, int b, int c, int 
   return ((long)(batch_of_tensor == 1 ? 0 : n) * 2 * p.C + f * p.C + c);
 }
 __device__ __forceinline__ float pre_load(const PreParams& p, long plane, long off) {
+  if (p.input_u8 == 2) {             // interleaved camera frame: plane = frame * Ct + channel
+    const int ct = p.split_fingers ? 2 * p.C : p.C;
+    const long n = plane / ct;
+    return (float)__ldg(static_cast<const unsigned char*>(p.x) + (n * p.Hr * p.Wr + off) * ct + (plane - n * ct));
+  }
   const long i = plane * p.Hr * p.Wr + off;
   return p.input_u8 ? (float)__ldg(static_cast<const unsigned char*>(p.x) + i) : __ldg(static_cast<const float*>(p.x) + i);
 }

@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const int ci_blk = bid % cbt;
   const int co_blk = bid / cbt;
   const int dy0 = tg ? 2 : 0, ndy = tg ? 1 : 2;                 // XB = 128 only
-  const int tap0 = 0, ntap = 9;                                 // XB = 32 only
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
   const bool half_m = (p.Cout - co_blk * 128) < 128;      // only 64 real co rows
 
@@ -133,8 +132,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // instruction descriptor: fp32 accum, bf16 A/B, A and B MN-major (bits 15, 16), N = NT, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (((uint32_t)NT >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t b_hi = ((10u * XB) >> 4) | (1u << 14) | (XLAYOUT << 29);   // K atoms = image rows, 10 halo pixels apart
+    constexpr uint32_t idesc48 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((48u >> 3) << 17) | ((128u >> 4) << 24);
     // N = 192: the three dx taps of a filter row in one instruction (XB = 128)
     constexpr uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((192u >> 3) << 17) | ((128u >> 4) << 24);
     int st = 0; uint32_t ph = 0;
@@ -157,14 +156,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             }
           }
         } else {
-          for (int tp = 0; tp < ntap; ++tp) {
-            const int tap = tap0 + tp, dy = tap / 3, dx = tap % 3;
-            const uint32_t d_tmem = tmem_base + tp * NT;
+          // XB = 32: N = 3 x 16, the three dx taps are MN blocks one 32-byte halo pixel apart
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t d_tmem = tmem_base + dy * 3 * NT;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const uint32_t a_lo = mn_desc_lo(sa + k * 2048, a_lbo);
-              const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy) * 10 + dx) * XB, 0);
-              umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, b_hi, idesc, (first && k == 0) ? 0u : 1u);
+              const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy) * 10) * XB, XB);
+              umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, b_hi, idesc48, (first && k == 0) ? 0u : 1u);
             }
           }
         }

@@ -65,7 +65,9 @@ typedef struct gsd_prepost {
   float out_shift;              /*                          bias                                */
   int32_t split_fingers;        /* 1: x holds batch/2 frame PAIRS with 2*in_channels channels; network sample b is
                                  *    finger b/(batch/2) of pair b%(batch/2) (general_dataset.py:71: all Left, then all Right) */
-  int32_t input_u8;             /* 1: x is uint8 camera bytes instead of float 0..255 (4x less host->device traffic) */
+  int32_t input_u8;             /* 0: x is float 0..255 NCHW; 1: uint8 NCHW camera bytes (4x less host->device traffic);
+                                   2: uint8 NHWC = interleaved frames (batch, raw_height, raw_width, channels) as a camera
+                                   driver / cv2 delivers them (README.md:155: "in whatever way you acquire tactile images") */
 } gsd_prepost;
 
 typedef struct gsd_plan gsd_plan;

@@ -383,3 +383,39 @@ def test_frame_pairs_split_and_uint8_ingest():
     assert got_f.shape == (3, 2, 64, 85)
     assert torch.equal(got_f, got_u)                       # uint8 ingest is bit-identical to float frames
     assert rel_l2(got_f, ref) < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["hwc_u8", "chw_u8", "chw_f32"])
+def test_depth_stream_ring_buffer_graph_replay(layout):
+    """camera frames -> pinned ring slot -> one CUDA-graph replay -> depth map; identical to the batched
+    entry point on the same frames, for interleaved uint8 camera frames and the two planar layouts."""
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.processing_utils.complete_prediction import predict_depth_from_frame_pairs
+    from gelslim_depth_b200.streaming import DepthStream
+    torch.manual_seed(5)
+    net = UNet(3, 1)
+    sd = oracle.conditioned_state_dict(net.state_dict(), seed=9)
+    net.load_state_dict(sd)
+    net = net.to(dev()).eval()
+    g = torch.Generator().manual_seed(13)
+    raw8 = torch.randint(0, 256, (6, 6, 64, 85), generator=g, dtype=torch.uint8)
+    base = torch.randint(0, 256, (6, 64, 85), generator=g).float()
+    cfg = shipped_cfg((32, 43))
+    want = predict_depth_from_frame_pairs(raw8.to(dev()), base[None].to(dev()), net, (64, 85), cfg).cpu()
+    fingers = oracle.split_fingers(oracle.get_difference_image(raw8[:1].float(), base[None]))
+    ref0 = oracle.predict_depth_from_RGB(fingers, lambda t: oracle.unet_forward(sd, t), (64, 85), cfg)[:, 0]
+    stream = DepthStream(net, cfg, (64, 85), base_tactile_image=base, output_size=(64, 85), layout=layout, frame_pairs=True, slots=3)
+    frames = {"hwc_u8": raw8.permute(0, 2, 3, 1).contiguous(), "chw_u8": raw8, "chw_f32": raw8.float()}[layout]
+    # two frames in flight, then one at a time round the ring (6 frames over 3 slots: every slot is reused)
+    t0, t1 = stream.push(frames[0]), stream.push(frames[1])
+    got = [stream.result(t0).clone(), stream.result(t1).clone()]
+    for i in range(2, 6):
+        got.append(stream(frames[i]).clone())
+    got = torch.stack(got)
+    assert got.shape == (6, 2, 64, 85)
+    assert torch.equal(got, want)
+    assert rel_l2(got[0], ref0) < 2e-2
+    assert len(stream.latencies_ms) == 6
+    with pytest.raises(ValueError):
+        stream.push(torch.zeros(3, 3, 3))
