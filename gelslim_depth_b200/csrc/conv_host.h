@@ -404,17 +404,19 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   L->xb = xb;
   p.cb0 = C0 / nt; p.cb1 = C1 / nt;
   p.off_x = off_x; p.off_y = off_y;
-  p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16; p.batch = B;
+  const bool half_m = !first && Cout == 64;          // two filter rows per UMMA through a one-row-shifted dZ half
+  p.tiles_x = (W + 7) / 8; p.tiles_y = (H + (half_m ? 1 : 0) + 15) / 16; p.batch = B;
   p.Cout = Cout; p.co_blocks = (Cout + 127) / 128;
   p.dw = dw;
   p.stages = 4;
   const int blocks = p.co_blocks * (p.cb0 + p.cb1);
   const long m_tiles = (long)p.tiles_x * p.tiles_y * B;
   p.blocks = blocks;
-  if (first) {
+  if (first || half_m) {
     int split = blocks >= num_sms ? 1 : num_sms / blocks;   // grid <= #SMs: no nearly empty second wave
     if (split > m_tiles) split = (int)m_tiles;
     p.split = split < 1 ? 1 : split;
+    p.n0 = p.split; p.n1 = 0;                               // Cout == 64: one CTA accumulates all nine taps
     L->grid = blocks * p.split;
   } else {
     wgrad_choose_split(blocks, m_tiles, num_sms, &p.n0, &p.n1);
@@ -425,7 +427,7 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-    uint32_t box[4] = {64, 8, 16, 1};
+    uint32_t box[4] = {64, 8, half_m ? 17u : 16u, 1};
     GSD_TRY(encode_bf16_map(&p.tm_dz, const_cast<void*>(dz), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
   }
   auto src_map = [&](CUtensorMap* m, const void* base, int C, int h, int w) -> int {

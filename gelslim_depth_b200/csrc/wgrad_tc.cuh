@@ -13,7 +13,13 @@
 // per 96 tensor cycles) where three N = 64 instructions were smem-bound (3 x 48 per 96).  A CTA owns one
 // (128 co) x (64 ci) x (filter rows {0,1} or {2}) block of dW in TMEM (2 x 192 or 192 fp32 columns) while it streams
 // its share of the pixel tiles (split-K across CTAs; the {0,1} group gets twice as many CTAs), then red.global-adds it.
-// Cout == 64: the second half of the 128-row A operand re-reads the first (its accumulator rows are ignored).
+// Cout == 64: M = 128 would waste half the instruction, so the two 64-row halves of A are the SAME 64 channels of dZ one
+// image row apart (the dZ box is 17 rows; the second MN block starts 1024 bytes = one tile row later).  Against the
+// same B rows the shifted half sees the halo one row further down, i.e. it accumulates the NEXT filter row:
+// UMMA(B rows 2k)   -> lanes 64..127: filter row 0, lanes 0..63: filter row 1
+// UMMA(B rows 2k+1) -> lanes 64..127: filter row 1 (again, not drained), lanes 0..63: filter row 2
+// Two instructions instead of three cover all nine taps and one CTA owns the whole dW block (n1 = 0).  The shifted
+// half walks image rows ty*16-1 .. ty*16+14, so the tile grid has ceil((H+1)/16) rows.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -112,6 +118,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const int dy0 = tg ? 2 : 0, ndy = tg ? 1 : 2;                 // XB = 128 only
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
   const bool half_m = (p.Cout - co_blk * 128) < 128;      // only 64 real co rows
+  const bool shifted = half_m && XB == 128;                // ... used twice, one image row apart (see above)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -120,9 +127,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
         mbar_wait(bar_empty + 8 * st, ph ^ 1);
         const uint32_t sa = s_stage + st * STAGE, fb = bar_full + 8 * st;
-        mbar_arrive_expect_tx(fb, (half_m ? 1 : 2) * kWgDzBytes + HALO_BOX);
-        tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * 8, ty * 16, b);
-        if (!half_m) tma_load_4d(sa + kWgDzBytes, &p.tm_dz, fb, co_blk * 128 + 64, tx * 8, ty * 16, b);
+        mbar_arrive_expect_tx(fb, (shifted ? kWgDzBytes + 1024 : half_m ? kWgDzBytes : 2 * kWgDzBytes) + HALO_BOX);
+        if (shifted) {
+          tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * 8, ty * 16 - 1, b);        // 17-row box (host)
+        } else {
+          tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * 8, ty * 16, b);
+          if (!half_m) tma_load_4d(sa + kWgDzBytes, &p.tm_dz, fb, co_blk * 128 + 64, tx * 8, ty * 16, b);
+        }
         if (ci_blk < p.cb0)
           tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x0, fb, ci_blk * NT, tx * 8 - 1, ty * 16 - 1, b);
         else
@@ -142,7 +153,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       mbar_wait(bar_full + 8 * st, ph);
       tc_fence_after();
       const uint32_t sa = s_stage + st * STAGE;
-      const uint32_t a_lbo = half_m ? 0u : (uint32_t)kWgDzBytes;
+      // Cout == 64: second half = dZ one image row later (XB = 128) / the same 64 rows again (XB = 32)
+      const uint32_t a_lbo = shifted ? 1024u : half_m ? 0u : (uint32_t)kWgDzBytes;
       if (elect_one()) {
         if (XB == 128) {
           for (int dyi = 0; dyi < ndy; ++dyi) {
@@ -183,16 +195,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     tc_fence_after();
     const int co = co_blk * 128 + row;
     const int ctot = cbt * NT;
-    const bool live = (s < m_tiles) && co < p.Cout && !(half_m && row >= 64) && !(p.flags & 1);
+    const bool live = (s < m_tiles) && (shifted || (co < p.Cout && !(half_m && row >= 64))) && !(p.flags & 1);
     if (XB == 128) {
       for (int tp = 0; tp < 3 * ndy; ++tp) {         // accumulator column block tp*64 <-> tap (dy0 + tp/3, tp%3)
+        // Cout == 64: lanes 0..63 hold filter rows {1, 2}, lanes 64..127 rows {0, 1}; row 1 is drained once
+        const int tap = shifted ? tp + (q < 2 ? 3 : 0) : dy0 * 3 + tp;
+        if (shifted && q >= 2 && tp >= 3) continue;
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + tp * 64 + c0 + ((uint32_t)(q * 32) << 16), v);
           tmem_ld_wait();
           if (live) {
-            float* dst = p.dw + ((size_t)co * 9 + dy0 * 3 + tp) * ctot + ci_blk * 64 + c0;
+            float* dst = p.dw + ((size_t)(shifted ? (co & 63) : co) * 9 + tap) * ctot + ci_blk * 64 + c0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);   // 16-byte aligned
           }
