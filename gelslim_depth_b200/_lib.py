@@ -22,6 +22,11 @@ class Geometry(C.Structure):
                 ("dtype", C.c_int32), ("mode", C.c_int32)]
 
 
+class PackItem(C.Structure):            # gsd_pack_item
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("out_dgrad", C.c_void_p), ("mode", C.c_int32), ("O", C.c_int32), ("I", C.c_int32),
+                ("Ipad", C.c_int32), ("start", C.c_int64)]
+
+
 class PrePost(C.Structure):
     _fields_ = [("use_diff", C.c_int32), ("base_batch", C.c_int32), ("raw_height", C.c_int32), ("raw_width", C.c_int32),
                 ("out_height", C.c_int32), ("out_width", C.c_int32), ("in_scale", C.c_float * 8),
@@ -64,7 +69,7 @@ SYMBOLS = {
     "gsd_op_convt_dgrad_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gsd_op_convt_wgrad_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "gsd_op_prologue_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
-    "gsd_op_bn_finalize": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsd_op_bn_finalize": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsd_op_negate_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "gsd_op_bn_relu_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsd_op_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -75,7 +80,9 @@ SYMBOLS = {
     "gsd_op_adam_ema_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p]),
     "gsd_op_maxpool_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsd_op_pack_weight": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "gsd_op_unpack_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "gsd_op_unpack_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "gsd_op_pack_weights_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
+    "gsd_pack_item_units": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gsd_op_wgrad_first": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsd_op_adam_ema": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_longlong, C.c_float, C.c_longlong, C.c_float, C.c_void_p]),
     "gsd_op_image_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -90,11 +90,11 @@ extern "C" int gsd_op_negate_f32(const float* in, int n, float* out, void* strea
 
 extern "C" int gsd_op_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* running_mean,
                                   float* running_var, float momentum, float eps, int C, const float* neg_center, float* scale,
-                                  float* shift, float* mean, float* rstd, void* stream) {
+                                  float* shift, float* mean, float* rstd, long long* num_batches_tracked, void* stream) {
   GSD_CHECK(stats && gamma && beta && scale && shift && mean && rstd && C > 0, "gsd_op_bn_finalize: bad argument");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, (float)count, gamma, beta, running_mean,
                                                                                     running_var, momentum, eps, C, neg_center, scale, shift,
-                                                                                    mean, rstd);
+                                                                                    mean, rstd, num_batches_tracked);
   GSD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -226,9 +226,21 @@ extern "C" int gsd_op_pack_weight(int mode, const float* w, int O, int I, int Ip
   return 0;
 }
 
-extern "C" int gsd_op_unpack_wgrad(const float* dwk, int O, int I, int Ipad, float* grad, void* stream) {
+extern "C" int gsd_op_unpack_wgrad(float* dwk, int O, int I, int Ipad, float* grad, int clear, void* stream) {
   GSD_CHECK(dwk && grad, "gsd_op_unpack_wgrad: null argument");
-  unpack_wgrad_kernel<<<ew_grid((long)O * I * 9), 256, 0, static_cast<cudaStream_t>(stream)>>>(dwk, O, I, Ipad, grad);
+  unpack_wgrad_kernel<<<ew_grid((long)O * I * 9), 256, 0, static_cast<cudaStream_t>(stream)>>>(dwk, O, I, Ipad, grad, clear);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" long long gsd_pack_item_units(int mode, int O, int I, int Ipad) { return pack_item_units(mode, O, I, Ipad); }
+
+extern "C" int gsd_op_pack_weights_batched(const gsd_pack_item* items_dev, int n_items, long long total_units, void* stream) {
+  GSD_CHECK(items_dev && n_items > 0 && n_items <= 64 && total_units > 0, "gsd_op_pack_weights_batched: need 1..64 items");
+  static_assert(sizeof(gsd_pack_item) == sizeof(PackItemDev), "gsd_pack_item layout");
+  const int grid = (int)(total_units < 148 * 8 ? total_units : 148 * 8);
+  pack_weights_batched_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const PackItemDev*>(items_dev),
+                                                                                 n_items, total_units);
   GSD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -35,8 +35,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps, int C,
                                    const float* __restrict__ neg_center, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                   long long* __restrict__ num_batches_tracked) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;      // BatchNorm2d bookkeeping (unet.py:12,15)
   if (c >= C) return;
   const float mean = stats[c] / count;
   float var = stats[C + c] / count - mean * mean;
@@ -396,13 +398,107 @@ __global__ void pack_convt_dgrad_weight_kernel(const float* __restrict__ w, int 
   }
 }
 // wgrad arena [O][9][Ipad] fp32 -> parameter gradient (O,I,3,3) fp32
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwk, int O, int I, int Ipad, float* __restrict__ grad) {
+__global__ void unpack_wgrad_kernel(float* __restrict__ dwk, int O, int I, int Ipad, float* __restrict__ grad, int clear) {
   const long total = (long)O * I * 9;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int t = (int)(idx % 9);
     const int i = (int)((idx / 9) % I);
     const int o = (int)(idx / (9L * I));
-    grad[idx] = dwk[((long)o * 9 + t) * Ipad + i];
+    float* src = dwk + ((long)o * 9 + t) * Ipad + i;
+    grad[idx] = *src;
+    if (clear) *src = 0.f;          // every live element is read exactly once; padded channels are never written
+  }
+}
+
+// One launch packs every layer's bf16 GEMM operands (gsd_pack_item table in device memory).  Work is counted in
+// units: a Conv2d item (mode 0) has (O/32) x ceil(I/32) units, each a 32 co x 32 ci x 9 tap tile that is read once
+// (288 contiguous floats per output channel), staged in shared memory and written twice -- as the forward operand
+// [co][tap][ci] and, when out_dgrad is set, as the dgrad operand [ci][8-tap][co] -- with 64-byte contiguous segments
+// on both sides.  ConvTranspose2d items (modes 2/3, 4 % of the parameters) are packed 1024 elements per unit.
+struct PackItemDev {
+  const float* w;
+  __nv_bfloat16* out;
+  __nv_bfloat16* out_dgrad;
+  int mode, O, I, Ipad;
+  long long start;       // first unit of this item
+};
+__device__ __forceinline__ float pack_source(const PackItemDev& it, long idx) {
+  const float* w = it.w;
+  switch (it.mode) {
+    case 0: {   // Conv2d (O,I,3,3) -> [O][9][Ipad]
+      const int i = (int)(idx % it.Ipad);
+      const int t = (int)((idx / it.Ipad) % 9);
+      const int o = (int)(idx / ((long)it.Ipad * 9));
+      return i < it.I ? w[((long)o * it.I + i) * 9 + t] : 0.f;
+    }
+    case 1: {   // Conv2d dgrad operand [ci][9][co], taps flipped
+      const int co = (int)(idx % it.O);
+      const int t = (int)((idx / it.O) % 9);
+      const int ci = (int)(idx / ((long)it.O * 9));
+      return w[((long)co * it.I + ci) * 9 + (8 - t)];
+    }
+    case 2: {   // ConvTranspose2d (I,O,2,2) -> [(g)*O + o][I]
+      const int i = (int)(idx % it.I);
+      const int o = (int)((idx / it.I) % it.O);
+      const int g = (int)(idx / ((long)it.I * it.O));
+      return w[((long)i * it.O + o) * 4 + g];
+    }
+    default: {  // ConvTranspose2d dgrad operand [ci][(g, co)]
+      const int co = (int)(idx % it.O);
+      const int g = (int)((idx / it.O) % 4);
+      const int ci = (int)(idx / ((long)it.O * 4));
+      return w[((long)ci * it.O + co) * 4 + g];
+    }
+  }
+}
+__host__ __device__ inline long long pack_item_units(int mode, int O, int I, int Ipad) {
+  if (mode == 0) return (long long)(O / 32) * ((I + 31) / 32);
+  const long long elems = mode == 1 ? 9LL * O * I : 4LL * O * I;
+  return (elems + 1023) / 1024;
+}
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackItemDev* __restrict__ items, int n, long long total) {
+  __shared__ long long s_start[65];
+  __shared__ float tile[32][289];           // [co][ci*9 + tap], pitch 289: conflict-free for lane = ci and lane = co
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_start[i] = items[i].start;
+  if (threadIdx.x == 0) s_start[n] = total;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_start[mid] <= u) lo = mid; else hi = mid - 1;
+    }
+    const PackItemDev it = items[lo];
+    const long long lu = u - it.start;
+    if (it.mode != 0) {
+      const long count = it.mode == 1 ? 9L * it.O * it.I : 4L * it.O * it.I;
+      for (long idx = lu * 1024 + threadIdx.x; idx < (lu + 1) * 1024 && idx < count; idx += 256)
+        it.out[idx] = __float2bfloat16_rn(pack_source(it, idx));
+      continue;
+    }
+    const int ci_tiles = (it.I + 31) / 32;
+    const int co0 = (int)(lu / ci_tiles) * 32, ci0 = (int)(lu % ci_tiles) * 32;
+    const int nci = min(32, it.I - ci0);                 // real input channels in this tile
+    __syncthreads();                                     // previous tile fully consumed
+    for (int r = warp; r < 32; r += 8) {                 // row = output channel: 9*nci contiguous floats
+      const float* src = it.w + ((long)(co0 + r) * it.I + ci0) * 9;
+      for (int k = lane; k < 288; k += 32) tile[r][k] = k < 9 * nci ? src[k] : 0.f;
+    }
+    __syncthreads();
+    // forward operand [co][tap][Ipad]: lane = ci
+    const int npad = min(32, it.Ipad - ci0);             // channels to write (zero padded up to Ipad)
+    for (int rt = warp; rt < 32 * 9; rt += 8) {
+      const int r = rt / 9, t = rt - r * 9;
+      if (lane < npad) it.out[((long)(co0 + r) * 9 + t) * it.Ipad + ci0 + lane] = __float2bfloat16_rn(tile[r][lane * 9 + t]);
+    }
+    // dgrad operand [ci][8 - tap][co]: lane = co
+    if (it.out_dgrad) {
+      for (int ct = warp; ct < nci * 9; ct += 8) {
+        const int c = ct / 9, t = ct - c * 9;
+        it.out_dgrad[((long)(ci0 + c) * 9 + (8 - t)) * it.O + co0 + lane] = __float2bfloat16_rn(tile[lane][c * 9 + t]);
+      }
+    }
   }
 }
 

@@ -31,40 +31,91 @@ def _blocks(net):
 
 
 class PackedTrainWeights:
-    """bf16 GEMM operands of every layer for forward and for dgrad; rebuilt after each optimizer step."""
+    """bf16 GEMM operands of every layer for forward and for dgrad.  The operand buffers and a device table of
+    (parameter pointer, mode, shape, output pointer) records are built once; `repack()` refreshes all of them with ONE
+    kernel launch (gsd_op_pack_weights_batched) after each optimizer step."""
 
     def __init__(self, net):
+        import ctypes as C
+        from .._lib import PackItem
         enc, dec = _blocks(net)
         self.fwd, self.dgrad = {}, {}
+        from .._lib import lib
+        items = []          # (mode, param, O, I, Ipad, key, wants dgrad operand)
         for bi, seq in enumerate(enc):
             for ci in (0, 3):
-                w = seq[ci].weight.detach()
+                w = seq[ci].weight
                 O, I = w.shape[:2]
-                ipad = 16 if (bi == 0 and ci == 0) else I
-                self.fwd[id(seq[ci])] = ops.pack_weight(0, w, O, I, ipad)
-                if not (bi == 0 and ci == 0):
-                    self.dgrad[id(seq[ci])] = ops.pack_weight(1, w, O, I)
+                first = bi == 0 and ci == 0
+                items.append((0, w, O, I, 16 if first else I, id(seq[ci]), not first))
         for up, seq in dec:
-            w = up.weight.detach()
-            I, O = w.shape[:2]
-            self.fwd[id(up)] = ops.pack_weight(2, w, O, I)
-            self.dgrad[id(up)] = ops.pack_weight(3, w, O, I)
+            I, O = up.weight.shape[:2]
+            items.append((2, up.weight, O, I, I, id(up), False))
+            items.append((3, up.weight, O, I, I, id(up), False))
             for ci in (0, 3):
-                cw = seq[ci].weight.detach()
-                self.fwd[id(seq[ci])] = ops.pack_weight(0, cw, cw.shape[0], cw.shape[1])
-                self.dgrad[id(seq[ci])] = ops.pack_weight(1, cw, cw.shape[0], cw.shape[1])
+                cw = seq[ci].weight
+                items.append((0, cw, cw.shape[0], cw.shape[1], cw.shape[1], id(seq[ci]), True))
+        dev = items[0][1].device
+        al = lambda n: (n + 7) // 8 * 8                                  # every operand 16-byte aligned
+        elems = sum(al(ops.pack_out_elems(m, O, I, ip)) + (al(ops.pack_out_elems(1, O, I)) if dg else 0)
+                    for (m, _, O, I, ip, _, dg) in items)
+        self.arena = torch.empty(elems, dtype=BF16, device=dev)
+        table = (PackItem * len(items))()
+        self._ptrs = []
+        cur, units = 0, 0
+        for k, (mode, w, O, I, ipad, key, dg) in enumerate(items):
+            n = ops.pack_out_elems(mode, O, I, ipad)
+            out = self.arena[cur:cur + n]
+            cur += al(n)
+            (self.dgrad if mode == 3 else self.fwd)[key] = out
+            table[k].w, table[k].out, table[k].out_dgrad = w.data_ptr(), out.data_ptr(), None
+            if dg:
+                n2 = ops.pack_out_elems(1, O, I)
+                self.dgrad[key] = self.arena[cur:cur + n2]
+                table[k].out_dgrad = self.dgrad[key].data_ptr()
+                cur += al(n2)
+            table[k].mode, table[k].O, table[k].I, table[k].Ipad, table[k].start = mode, O, I, ipad, units
+            units += lib.gsd_pack_item_units(mode, O, I, ipad)
+            self._ptrs.append((w, w.data_ptr()))
+        self.n_items, self.total = len(items), units
+        self.table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
+        self.repack()
+
+    def valid_for(self, net) -> bool:
+        return all(w.data_ptr() == ptr for w, ptr in self._ptrs)
+
+    def repack(self):
+        ops.pack_weights_batched(self.table, self.n_items, self.total, self.arena.device)
 
 
-def _unit_forward(conv: nn.Conv2d, bn: nn.BatchNorm2d, pw: PackedTrainWeights, src0, src1=None, off=(0, 0), pool=False, first=False):
+class StepEnv:
+    """Per-step scratch policy.  Default: fresh zeroed tensors and one negate launch per BatchNorm (autograd bridge);
+    FusedTrainer substitutes persistent arenas (one memset + one negate per step, no per-layer fills)."""
+
+    def zeros(self, n, dev):
+        return torch.zeros(n, dtype=torch.float32, device=dev)
+
+    def neg_center(self, bn):
+        return ops.negate(bn.running_mean)
+
+    def dwk(self, conv, cin_total):
+        return None
+
+
+_DEFAULT_ENV = StepEnv()
+
+
+def _unit_forward(conv: nn.Conv2d, bn: nn.BatchNorm2d, pw: PackedTrainWeights, src0, src1=None, off=(0, 0), pool=False, first=False,
+                  env: StepEnv = _DEFAULT_ENV):
     B, H, W, _ = src0.shape
     cout = conv.out_channels
-    stats = torch.zeros(2 * cout, dtype=torch.float32, device=src0.device)
+    stats = env.zeros(2 * cout, src0.device)
     # z is stored centred on the running mean (bf16 then rounds relative to the fluctuation of z, not to its mean);
     # the batch statistics are taken from the raw fp32 accumulators in the conv epilogue.
-    neg_center = ops.negate(bn.running_mean)
+    neg_center = env.neg_center(bn)
     z = ops.conv(src0, pw.fwd[id(conv)], cout, 9, src1=src1, off=off, shift=neg_center, stats=stats)
-    scale, shift, mean, rstd = ops.bn_finalize(stats, B * H * W, bn, neg_center)              # + running stats (momentum 0.1)
-    bn.num_batches_tracked += 1
+    # batch statistics -> (scale, shift, mean, rstd); running stats (momentum 0.1) and num_batches_tracked updated in place
+    scale, shift, mean, rstd = ops.bn_finalize(stats, B * H * W, bn, neg_center)
     a, pooled = ops.bn_relu_apply(z, scale, shift, pool=pool)
     u = _Unit()
     u.src0, u.src1, u.off, u.z, u.a, u.mean, u.rstd, u.pooled, u.conv, u.bn, u.first = src0, src1, off, z, a, mean, rstd, pooled, conv, bn, first
@@ -72,7 +123,7 @@ def _unit_forward(conv: nn.Conv2d, bn: nn.BatchNorm2d, pw: PackedTrainWeights, s
     return u
 
 
-def train_forward(net, x: torch.Tensor, pw: PackedTrainWeights):
+def train_forward(net, x: torch.Tensor, pw: PackedTrainWeights, env: StepEnv = _DEFAULT_ENV):
     """-> (y fp32 NCHW, saved context).  BatchNorm uses batch statistics and updates its running buffers."""
     enc, dec = _blocks(net)
     depth = len(enc) - 1
@@ -80,8 +131,8 @@ def train_forward(net, x: torch.Tensor, pw: PackedTrainWeights):
     cur = ops.prologue(x.contiguous().float())
     ctx["in16"] = cur
     for l, seq in enumerate(enc):
-        u1 = _unit_forward(seq[0], seq[1], pw, cur, first=(l == 0))
-        u2 = _unit_forward(seq[3], seq[4], pw, u1.a, pool=(l < depth))
+        u1 = _unit_forward(seq[0], seq[1], pw, cur, first=(l == 0), env=env)
+        u2 = _unit_forward(seq[3], seq[4], pw, u1.a, pool=(l < depth), env=env)
         ctx["enc"].append((u1, u2))
         cur = u2.pooled if l < depth else u2.a
     y_prev = ctx["enc"][depth][1].a
@@ -92,8 +143,8 @@ def train_forward(net, x: torch.Tensor, pw: PackedTrainWeights):
         dev = y_prev.device
         u = ops.conv(y_prev, pw.fwd[id(up)], cup, ntaps=1, groups=4, scale=ops.ones(dev, 4 * cup), shift=up.bias.detach().repeat(4))
         off = ((skip.shape[1] - u.shape[1]) // 2, (skip.shape[2] - u.shape[2]) // 2)           # F.pad left/top (unet.py:46-47)
-        u1 = _unit_forward(seq[0], seq[1], pw, skip, src1=u, off=off)
-        u2 = _unit_forward(seq[3], seq[4], pw, u1.a)
+        u1 = _unit_forward(seq[0], seq[1], pw, skip, src1=u, off=off, env=env)
+        u2 = _unit_forward(seq[3], seq[4], pw, u1.a, env=env)
         ctx["dec"].append((up, y_prev, u, off, u1, u2))
         y_prev = u2.a
     w_head = net.outc.conv.weight.detach().reshape(net.n_classes, -1)
@@ -122,18 +173,20 @@ class GradSink:
         pass
 
 
-def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: "GradSink", need_dx: bool, split: int = 0):
+def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: "GradSink", need_dx: bool, split: int = 0,
+                   env: StepEnv = _DEFAULT_ENV):
     """backward of conv -> BN -> ReLU.  Returns the input gradient(s) (None if not needed).
     split > 0: the conv input was the virtual concat [skip | up]; returns (dskip, dup_full)."""
     B, H, W, Cn = u.a.shape
-    dz, sums = ops.bn_bwd(da, u.scale, u.shift, u.z, u.mean, u.rstd, u.bn.weight.detach(), B * H * W)
+    dz, sums = ops.bn_bwd(da, u.scale, u.shift, u.z, u.mean, u.rstd, u.bn.weight.detach(), B * H * W,
+                          sums=env.zeros(2 * Cn, da.device))
     grads.put(u.bn.bias, sums[:Cn])
     grads.put(u.bn.weight, sums[Cn:])
     gw = grads.dest(u.conv.weight)
     if u.first:
-        ops.wgrad_first(u.src0, dz, u.conv.in_channels, gw)
+        ops.wgrad_first(u.src0, dz, u.conv.in_channels, gw, dwk=env.dwk(u.conv, 16))
     else:
-        ops.wgrad3x3(u.src0, dz, gw, x1=u.src1, off=u.off)
+        ops.wgrad3x3(u.src0, dz, gw, x1=u.src1, off=u.off, dwk=env.dwk(u.conv, u.conv.in_channels))
     grads.done(u.conv.weight)
     if not need_dx:
         return None
@@ -147,7 +200,8 @@ def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: "GradSink", need
     return ops.conv(dz, wd, cin, 9)
 
 
-def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "GradSink" = None) -> List[torch.Tensor]:
+def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "GradSink" = None,
+                   env: StepEnv = _DEFAULT_ENV) -> List[torch.Tensor]:
     """dy: gradient of the loss w.r.t. the network output (fp32 NCHW).  Gradients go to `grads` (a GradSink) in
     reverse parameter order; returns them in net.parameters() order when the default sink is used."""
     enc, dec = _blocks(net)
@@ -167,9 +221,9 @@ def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "G
     # ---- decoder, last block first
     for i in range(depth - 1, -1, -1):
         up, y_prev, u, off, u1, u2 = ctx["dec"][i]
-        da1 = _unit_backward(u2, da, pw, grads, need_dx=True)
+        da1 = _unit_backward(u2, da, pw, grads, need_dx=True, env=env)
         cskip = u1.src0.shape[-1]
-        dskip, dup = _unit_backward(u1, da1, pw, grads, need_dx=True, split=cskip)
+        dskip, dup = _unit_backward(u1, da1, pw, grads, need_dx=True, split=cskip, env=env)
         l = depth - 1 - i
         dskips[l] = dskip
         # transposed conv: only the (2hs x 2ws) window of dup at `off` is its output gradient (the rest is F.pad)
@@ -179,7 +233,7 @@ def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "G
             dup[:, off[0] + 2 * hs:] = 0
             dup[:, :, : off[1]] = 0
             dup[:, :, off[1] + 2 * ws:] = 0
-        grads.put(up.bias, ops.channel_sum(dup))
+        grads.put(up.bias, ops.channel_sum(dup, sums=env.zeros(2 * dup.shape[-1], dev)))
         gw = grads.dest(up.weight)
         ops.convt_wgrad(y_prev, dup, off, gw)
         grads.done(up.weight)
@@ -189,8 +243,8 @@ def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "G
         u1, u2 = ctx["enc"][l]
         if l < depth:
             da = ops.maxpool_bwd(u2.a, dpool, dskips[l])      # noqa: F821  (dpool from level l+1) + skip-connection gradient
-        da1 = _unit_backward(u2, da, pw, grads, need_dx=True)
-        dpool = _unit_backward(u1, da1, pw, grads, need_dx=(l > 0))
+        da1 = _unit_backward(u2, da, pw, grads, need_dx=True, env=env)
+        dpool = _unit_backward(u1, da1, pw, grads, need_dx=(l > 0), env=env)
     return [grads.grads[p] for p in net.parameters()] if own else None
 
 
@@ -199,7 +253,11 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(fctx, net, x, *params):
-        pw = PackedTrainWeights(net)
+        pw = getattr(net, "_train_pw", None)
+        if pw is None or not pw.valid_for(net):
+            pw = net._train_pw = PackedTrainWeights(net)      # operand buffers + pointer table, built once
+        else:
+            pw.repack()                                       # parameters changed in place (optimizer.step): one launch
         y, ctx = train_forward(net, x, pw)
         fctx.net, fctx.saved, fctx.pw = net, ctx, pw
         return y
@@ -213,6 +271,53 @@ class _TrainFn(torch.autograd.Function):
 
 def unet_train_forward(net, x):
     return _TrainFn.apply(net, x, *list(net.parameters()))
+
+
+class _ArenaEnv(StepEnv):
+    """FusedTrainer's scratch: BatchNorm running means alias one flat arena (one negate launch per step gives every
+    layer's centring constant), all small zero-initialised buffers (statistics, reduction sums, the loss) are slices of
+    one arena cleared by a single memset, and the weight-gradient accumulators persist (the unpack kernel re-zeroes
+    them)."""
+
+    def __init__(self, net):
+        bns = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d)]
+        dev = bns[0].running_mean.device
+        total = sum(m.num_features for m in bns)
+        self.flat_rm = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_neg = torch.empty_like(self.flat_rm)
+        self._neg = {}
+        off = 0
+        for m in bns:
+            c = m.num_features
+            self.flat_rm[off:off + c].copy_(m.running_mean)
+            m.running_mean.data = self.flat_rm[off:off + c]       # the buffer now aliases the arena (state_dict unchanged)
+            self._neg[id(m)] = self.flat_neg[off:off + c]
+            off += c
+        self.arena = torch.zeros(1 << 18, dtype=torch.float32, device=dev)
+        self.cursor = 0
+        self._dwk = {}
+
+    def begin_step(self):
+        self.arena.zero_()
+        self.cursor = 0
+        ops.negate(self.flat_rm, out=self.flat_neg)
+
+    def zeros(self, n, dev):
+        n4 = (n + 3) // 4 * 4
+        if self.cursor + n4 > self.arena.numel():
+            return torch.zeros(n, dtype=torch.float32, device=dev)
+        out = self.arena[self.cursor:self.cursor + n]
+        self.cursor += n4
+        return out
+
+    def neg_center(self, bn):
+        return self._neg[id(bn)]
+
+    def dwk(self, conv, cin_total):
+        t = self._dwk.get(id(conv))
+        if t is None:
+            t = self._dwk[id(conv)] = torch.zeros(conv.out_channels, 9, cin_total, dtype=torch.float32, device=conv.weight.device)
+        return t
 
 
 class _ArenaSink(GradSink):
@@ -278,6 +383,8 @@ class FusedTrainer:
         self.world = torch.distributed.get_world_size(process_group) if distributed else 1
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.buckets, self.bucket_of = plan_buckets([(p, *self.index[p]) for p in params], bucket_bytes)
+        self.pw = PackedTrainWeights(net)                          # after aliasing: the table holds arena pointers
+        self.env = _ArenaEnv(net)
 
     def average_parameters(self):
         """`with trainer.average_parameters():` == torch_ema's context manager (train_unet.py:389,428,480): the EMA
@@ -307,11 +414,11 @@ class FusedTrainer:
         use_graph=True: after two eager warm-up steps the whole step (~450 launches incl. the NCCL all-reduces)
         is captured once into a CUDA graph and replayed; shapes must then stay fixed."""
         if not self.use_graph:
-            return self._step_impl(x, target)
+            return self._step_impl(x, target).clone()        # the loss lives in the per-step scratch arena
         if self._graph is None:
             if self._warm < 2:
                 self._warm += 1
-                return self._step_impl(x, target)
+                return self._step_impl(x, target).clone()
             self._x = x.contiguous().float().clone()
             self._t = target.contiguous().float().clone()
             torch.cuda.synchronize()
@@ -326,11 +433,12 @@ class FusedTrainer:
         return self._loss.clone()
 
     def _step_impl(self, x, target) -> torch.Tensor:
-        net = self.net
-        pw = PackedTrainWeights(net)
-        y, ctx = train_forward(net, x, pw)
-        loss, dy = ops.mse(y, target.contiguous().float())
-        train_backward(net, ctx, dy, pw, grads=_ArenaSink(self))
+        net, pw, env = self.net, self.pw, self.env
+        pw.repack()                                                # every layer's bf16 operands: one launch
+        env.begin_step()                                           # one memset + one negate for all layers
+        y, ctx = train_forward(net, x, pw, env=env)
+        loss, dy = ops.mse(y, target.contiguous().float(), loss=env.zeros(1, y.device))
+        train_backward(net, ctx, dy, pw, grads=_ArenaSink(self), env=env)
         scale = 1.0
         if self.world > 1:
             torch.cuda.current_stream().wait_stream(self.comm_stream)

@@ -63,19 +63,21 @@ def conv(src0, w, cout, ntaps=9, groups=1, src1=None, off=(0, 0), scale=None, sh
     return (out, pooled) if pool else out
 
 
-def negate(v):
-    out = torch.empty_like(v)
+def negate(v, out=None):
+    out = torch.empty_like(v) if out is None else out
     check(lib.gsd_op_negate_f32(_p(v), v.numel(), _p(out), _st(v.device)), "gsd_op_negate_f32")
     return out
 
 
 def bn_finalize(stats, count, bn, neg_center=None):
+    """-> (scale, shift, mean, rstd); also updates running_mean / running_var and num_batches_tracked += 1 in place."""
     Cn = bn.num_features
     dev = stats.device
-    scale, shift, mean, rstd = (torch.empty(Cn, dtype=torch.float32, device=dev) for _ in range(4))
+    out = torch.empty(4, Cn, dtype=torch.float32, device=dev)
+    scale, shift, mean, rstd = out[0], out[1], out[2], out[3]
     check(lib.gsd_op_bn_finalize(_p(stats), float(count), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
                                  float(bn.momentum), float(bn.eps), Cn, _p(neg_center), _p(scale), _p(shift), _p(mean), _p(rstd),
-                                 _st(dev)), "gsd_op_bn_finalize")
+                                 _p(bn.num_batches_tracked), _st(dev)), "gsd_op_bn_finalize")
     return scale, shift, mean, rstd
 
 
@@ -87,8 +89,8 @@ def bn_relu_apply(z, scale, shift, pool=False):
     return a, pooled
 
 
-def mse(y, t):
-    loss = torch.zeros(1, dtype=torch.float32, device=y.device)
+def mse(y, t, loss=None):
+    loss = torch.zeros(1, dtype=torch.float32, device=y.device) if loss is None else loss   # accumulated: must be zero
     dy = torch.empty_like(y)
     check(lib.gsd_op_mse(_p(y), _p(t), y.numel(), _p(loss), _p(dy), _st(y.device)), "gsd_op_mse")
     return loss, dy
@@ -109,11 +111,12 @@ def head_bwd(a, dy, w, dw, db):
     return da
 
 
-def bn_bwd(da, scale, shift, z, mean, rstd, gamma, count):
-    """-> dz (bf16), sums = [dbeta | dgamma] (fp32, 2C).  scale/shift: the forward's BN-apply constants (ReLU mask)."""
+def bn_bwd(da, scale, shift, z, mean, rstd, gamma, count, sums=None):
+    """-> dz (bf16), sums = [dbeta | dgamma] (fp32, 2C; a zeroed buffer may be passed in).
+    scale/shift: the forward's BN-apply constants (ReLU mask)."""
     Cn = z.shape[-1]
     npix = z.numel() // Cn
-    sums = torch.zeros(2 * Cn, dtype=torch.float32, device=z.device)
+    sums = torch.zeros(2 * Cn, dtype=torch.float32, device=z.device) if sums is None else sums
     check(lib.gsd_op_bn_bwd_reduce(_p(da), _p(scale), _p(shift), _p(z), _p(mean), _p(rstd), npix, Cn, _p(sums), _st(z.device)),
           "gsd_op_bn_bwd_reduce")
     dz = torch.empty_like(z)
@@ -122,10 +125,10 @@ def bn_bwd(da, scale, shift, z, mean, rstd, gamma, count):
     return dz, sums
 
 
-def channel_sum(t):
+def channel_sum(t, sums=None):
     """per-channel sum of a dense NHWC bf16 tensor -> fp32 [C]."""
     Cn = t.shape[-1]
-    sums = torch.zeros(2 * Cn, dtype=torch.float32, device=t.device)
+    sums = torch.zeros(2 * Cn, dtype=torch.float32, device=t.device) if sums is None else sums
     check(lib.gsd_op_bn_bwd_reduce(_p(t), None, None, None, None, None, t.numel() // Cn, Cn, _p(sums), _st(t.device)),
           "gsd_op_bn_bwd_reduce")
     return sums[:Cn]
@@ -146,27 +149,42 @@ def pack_weight(mode, w, O, I, Ipad=None):
     return out
 
 
-def wgrad3x3(x0, dz, grad_out, x1=None, off=(0, 0)):
-    """conv weight gradient written into grad_out (O,I,3,3) fp32."""
+def wgrad3x3(x0, dz, grad_out, x1=None, off=(0, 0), dwk=None):
+    """conv weight gradient written into grad_out (O,I,3,3) fp32.  `dwk`: persistent ZEROED [O][9][I] fp32 accumulation
+    buffer; the unpack kernel clears it again as it reads, so it is ready for the next step (no per-step fill)."""
     B, H, W, C0 = x0.shape
     cout = dz.shape[-1]
     dev = x0.device
     C1 = H1 = W1 = 0
     if x1 is not None:
         _, H1, W1, C1 = x1.shape
-    dwk = torch.zeros(cout, 9, C0 + C1, dtype=torch.float32, device=dev)
+    clear = dwk is not None
+    if dwk is None:
+        dwk = torch.zeros(cout, 9, C0 + C1, dtype=torch.float32, device=dev)
     check(lib.gsd_op_wgrad3x3_bf16(_p(x0), C0, _p(x1), C1, H1, W1, off[0], off[1], _p(dz), cout, B, H, W, _p(dwk), dev.index or 0,
                                    _st(dev)), "gsd_op_wgrad3x3_bf16")
-    check(lib.gsd_op_unpack_wgrad(_p(dwk), cout, C0 + C1, C0 + C1, _p(grad_out), _st(dev)), "gsd_op_unpack_wgrad")
+    check(lib.gsd_op_unpack_wgrad(_p(dwk), cout, C0 + C1, C0 + C1, _p(grad_out), int(clear), _st(dev)), "gsd_op_unpack_wgrad")
 
 
-def wgrad_first(x16, dz, cin, grad_out):
+def wgrad_first(x16, dz, cin, grad_out, dwk=None):
     B, H, W, _ = x16.shape
-    dwk = torch.zeros(64, 9, 16, dtype=torch.float32, device=x16.device)
-    # tcgen05 GEMM over pixels with the 16-channel padded input as a 32-byte-row (SWIZZLE_32B, N = 16) operand
+    clear = dwk is not None
+    if dwk is None:
+        dwk = torch.zeros(64, 9, 16, dtype=torch.float32, device=x16.device)
+    # tcgen05 GEMM over pixels with the 16-channel padded input as a 32-byte-row (SWIZZLE_32B, N = 3 x 16) operand
     check(lib.gsd_op_wgrad3x3_bf16(_p(x16), 16, None, 0, 0, 0, 0, 0, _p(dz), 64, B, H, W, _p(dwk), x16.device.index or 0,
                                    _st(x16.device)), "gsd_op_wgrad3x3_bf16")
-    check(lib.gsd_op_unpack_wgrad(_p(dwk), 64, cin, 16, _p(grad_out), _st(x16.device)), "gsd_op_unpack_wgrad")
+    check(lib.gsd_op_unpack_wgrad(_p(dwk), 64, cin, 16, _p(grad_out), int(clear), _st(x16.device)), "gsd_op_unpack_wgrad")
+
+
+def pack_out_elems(mode, O, I, Ipad=None):
+    Ipad = I if Ipad is None else Ipad
+    return {0: O * 9 * Ipad, 1: O * 9 * I, 2: 4 * O * I, 3: 4 * O * I}[mode]
+
+
+def pack_weights_batched(table_dev, n_items, total, dev):
+    """one launch for every layer: table_dev = device uint8 tensor holding n_items gsd_pack_item records"""
+    check(lib.gsd_op_pack_weights_batched(_p(table_dev), n_items, total, _st(dev)), "gsd_op_pack_weights_batched")
 
 
 def convt_dgrad(du_full, off, w_dgrad, cin, hs, ws):

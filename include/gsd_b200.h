@@ -182,7 +182,8 @@ int gsd_op_prologue_bf16(const float* x, const float* base, int base_batch, int 
  * conv as shift = -center) so that bf16 rounds relative to the fluctuation; outputs then refer to the stored tensor. */
 int gsd_op_bn_finalize(const float* stats, double count, const float* gamma, const float* beta, float* running_mean,
                        float* running_var, float momentum, float eps, int C, const float* neg_center, float* scale,
-                       float* shift, float* mean, float* rstd, void* stream);
+                       float* shift, float* mean, float* rstd, long long* num_batches_tracked /* += 1, or NULL */,
+                       void* stream);
 int gsd_op_negate_f32(const float* in, int n, float* out, void* stream);
 /* a = relu(z*scale + shift) (+ MaxPool2d(2) copy, unet.py:26) */
 int gsd_op_bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H, int W, int C, void* a,
@@ -206,8 +207,22 @@ int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* dskip, int 
                        void* stream);
 /* fp32 parameter -> bf16 GEMM operand; modes: 0 conv fwd, 1 conv dgrad (flipped taps), 2 convT fwd, 3 convT dgrad */
 int gsd_op_pack_weight(int mode, const float* w, int O, int I, int Ipad, void* out, void* stream);
-/* wgrad arena [O][9][Ipad] fp32 -> Conv2d.weight.grad layout (O,I,3,3) */
-int gsd_op_unpack_wgrad(const float* dwk, int O, int I, int Ipad, float* grad, void* stream);
+/* the same for every layer of the network in ONE launch: `items_dev` is a DEVICE array of n_items records (the pointers
+ * are stable across steps because parameters alias a flat arena).  mode 0 items may carry `out_dgrad`: the dgrad
+ * operand (mode 1 layout) is then written from the same staged tile.  `start` = running sum of gsd_pack_item_units()
+ * of the preceding items, `total_units` = the sum over all items. */
+typedef struct gsd_pack_item {
+  const float* w;
+  void* out;
+  void* out_dgrad;            /* mode 0 only, may be NULL */
+  int32_t mode, O, I, Ipad;
+  int64_t start;
+} gsd_pack_item;
+long long gsd_pack_item_units(int mode, int O, int I, int Ipad);
+int gsd_op_pack_weights_batched(const gsd_pack_item* items_dev, int n_items, long long total_units, void* stream);
+/* wgrad arena [O][9][Ipad] fp32 -> Conv2d.weight.grad layout (O,I,3,3); clear != 0: the arena is zeroed as it is
+ * read, ready for the next step's accumulation */
+int gsd_op_unpack_wgrad(float* dwk, int O, int I, int Ipad, float* grad, int clear, void* stream);
 /* weight gradient of the first conv (K = 27/54), dw [64][9][16] fp32 accumulated */
 int gsd_op_wgrad_first(const void* x16, const void* dz, int B, int H, int W, int Cin, float* dw, void* stream);
 /* torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2 (train_unet.py:306,375) fused with the

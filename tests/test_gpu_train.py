@@ -313,3 +313,40 @@ def test_fused_trainer_cuda_graph_matches_eager():
     for a, b in zip(*curves):
         assert abs(a - b) < 8e-2 * abs(b) + 1e-5, curves       # atomics order differs run to run (chaotic nets); same trajectory
     assert curves[1][-1] < curves[1][0]
+
+
+def test_batched_weight_pack_matches_per_layer_pack():
+    """gsd_op_pack_weights_batched (one launch, tiled, forward + dgrad operands from one staged tile) is bit-identical
+    to the per-layer gsd_op_pack_weight modes 0-3 for every layer, including the 6->16 channel padding of inc.0."""
+    from gelslim_depth_b200.train import ops
+    from gelslim_depth_b200.train.engine import PackedTrainWeights, _blocks
+    net, _ = make_net(6, 2, 11, dims=(64, 128, 256))
+    net = net.to(dev()).train()
+    pw = PackedTrainWeights(net)
+    enc, dec = _blocks(net)
+    n = 0
+    for bi, seq in enumerate(enc):
+        for ci in (0, 3):
+            w = seq[ci].weight.detach()
+            O, I = w.shape[:2]
+            first = bi == 0 and ci == 0
+            assert torch.equal(pw.fwd[id(seq[ci])], ops.pack_weight(0, w, O, I, 16 if first else I))
+            if not first:
+                assert torch.equal(pw.dgrad[id(seq[ci])], ops.pack_weight(1, w, O, I))
+            n += 1
+    for up, seq in dec:
+        w = up.weight.detach()
+        I, O = w.shape[:2]
+        assert torch.equal(pw.fwd[id(up)], ops.pack_weight(2, w, O, I))
+        assert torch.equal(pw.dgrad[id(up)], ops.pack_weight(3, w, O, I))
+        for ci in (0, 3):
+            cw = seq[ci].weight.detach()
+            assert torch.equal(pw.fwd[id(seq[ci])], ops.pack_weight(0, cw, cw.shape[0], cw.shape[1]))
+            assert torch.equal(pw.dgrad[id(seq[ci])], ops.pack_weight(1, cw, cw.shape[0], cw.shape[1]))
+    assert n == 6
+    # in-place parameter update + repack
+    with torch.no_grad():
+        net.inc.double_conv[3].weight.mul_(2.0)
+    pw.repack()
+    w = net.inc.double_conv[3].weight.detach()
+    assert torch.equal(pw.dgrad[id(net.inc.double_conv[3])], ops.pack_weight(1, w, 64, 64))
