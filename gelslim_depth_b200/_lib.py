@@ -81,6 +81,8 @@ SYMBOLS = {
     "gsd_op_maxpool_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsd_op_pack_weight": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsd_op_unpack_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "gsd_op_bn_relu_head_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "gsd_op_head_bn_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_double] + [C.c_int] * 4 + [C.c_void_p] * 5),
     "gsd_op_pack_weights_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "gsd_pack_item_units": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gsd_op_wgrad_first": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

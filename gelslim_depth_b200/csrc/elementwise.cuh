@@ -115,10 +115,16 @@ __global__ void __launch_bounds__(256) prologue_f32_kernel(const PreParams p, fl
 template <int CIN>
 __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
                                                    const float* __restrict__ bias, int ncls, float out_scale,
-                                                   float out_shift, long npix_per_img, int B, float* __restrict__ y) {
+                                                   float out_shift, long npix_per_img, int B, float* __restrict__ y,
+                                                   const float* __restrict__ bn_scale = nullptr,
+                                                   const float* __restrict__ bn_shift = nullptr) {
+  // bn_scale/bn_shift (training): `in` is the raw conv output z and the head reads relu(z*scale + shift) rounded to
+  // bf16 -- exactly the tensor bn_relu_apply would have stored, which is then never materialised.
   static_assert(CIN == 64, "head_kernel: the 1x1 head reads 64 channels");
   const int lane = threadIdx.x & 31, grp = lane >> 3, c8 = lane & 7;
-  float wr[4][8], bk[4];
+  float wr[4][8], bk[4], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = bn_scale ? bn_scale[c8 * 8 + j] : 1.f; sh[j] = bn_scale ? bn_shift[c8 * 8 + j] : 0.f; }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     bk[k] = k < ncls ? bias[k] : 0.f;
@@ -143,6 +149,10 @@ __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restri
       for (int i = 0; i < 4; ++i) {
         const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[i]));
         f[2 * i] = t.x; f[2 * i + 1] = t.y;
+      }
+      if (bn_scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __bfloat162float(__float2bfloat16_rn(fmaxf(f[i] * sc[i] + sh[i], 0.f)));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {

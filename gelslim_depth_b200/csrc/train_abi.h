@@ -132,6 +132,48 @@ extern "C" int gsd_op_head_fwd(const void* a, const float* w, const float* bias,
   return 0;
 }
 
+// training forward of the last unit: y = OutConv(relu(BatchNorm(z))) without materialising the post-ReLU tensor
+extern "C" int gsd_op_bn_relu_head_fwd(const void* z, const float* scale, const float* shift, const float* w, const float* bias,
+                                       int ncls, int B, int H, int W, float* y, void* stream) {
+  GSD_CHECK(z && scale && shift && w && bias && y && ncls >= 1 && ncls <= 4, "gsd_op_bn_relu_head_fwd: bad argument");
+  const long npix = (long)H * W;
+  head_kernel<64><<<ew_grid(npix * B), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(z), w, bias, ncls, 1.f,
+                                                                                   0.f, npix, B, y, scale, shift);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// backward of OutConv + ReLU + BatchNorm of the last unit in two passes over z (see head_bn_bwd_kernel)
+template <int NCLS>
+static int launch_head_bn_bwd(const __nv_bfloat16* z, const float* dy, const float* w, const float* scale, const float* shift,
+                              const float* mean, const float* rstd, const float* gamma, float count, unsigned npix, unsigned total,
+                              float* sums, float* dw, float* db, __nv_bfloat16* dz, cudaStream_t st) {
+  long blocks = ((long)total * 8 + 255) / 256;
+  const int grid = (int)(blocks < 148 * 2 ? blocks : 148 * 2);
+  head_bn_bwd_kernel<NCLS, false><<<grid, 256, 0, st>>>(z, dy, w, scale, shift, mean, rstd, gamma, count, npix, total, sums, dw, db, dz);
+  head_bn_bwd_kernel<NCLS, true><<<grid, 256, 0, st>>>(z, dy, w, scale, shift, mean, rstd, gamma, count, npix, total, sums, dw, db, dz);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int gsd_op_head_bn_bwd(const void* z, const float* dy, const float* w, const float* scale, const float* shift,
+                                  const float* mean, const float* rstd, const float* gamma, double count, int ncls, int B, int H,
+                                  int W, float* sums, float* dw, float* db, void* dz, void* stream) {
+  GSD_CHECK(z && dy && w && scale && shift && mean && rstd && gamma && sums && dw && db && dz && ncls >= 1 && ncls <= 4,
+            "gsd_op_head_bn_bwd: bad argument");
+  const long npix = (long)H * W;
+  GSD_CHECK(npix * B < (1L << 31), "gsd_op_head_bn_bwd: more than 2^31 pixels");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* zb = static_cast<const __nv_bfloat16*>(z);
+  __nv_bfloat16* dzb = static_cast<__nv_bfloat16*>(dz);
+  const unsigned np = (unsigned)npix, tot = (unsigned)(npix * B);
+  switch (ncls) {
+    case 1: return launch_head_bn_bwd<1>(zb, dy, w, scale, shift, mean, rstd, gamma, (float)count, np, tot, sums, dw, db, dzb, st);
+    case 2: return launch_head_bn_bwd<2>(zb, dy, w, scale, shift, mean, rstd, gamma, (float)count, np, tot, sums, dw, db, dzb, st);
+    case 3: return launch_head_bn_bwd<3>(zb, dy, w, scale, shift, mean, rstd, gamma, (float)count, np, tot, sums, dw, db, dzb, st);
+    default: return launch_head_bn_bwd<4>(zb, dy, w, scale, shift, mean, rstd, gamma, (float)count, np, tot, sums, dw, db, dzb, st);
+  }
+}
+
 extern "C" int gsd_op_head_bwd(const void* a, const float* dy, const float* w, int ncls, int B, int H, int W, void* da, float* dw,
                                float* db, void* stream) {
   GSD_CHECK(a && dy && w && da && dw && db && ncls >= 1 && ncls <= 4, "gsd_op_head_bwd: bad argument");

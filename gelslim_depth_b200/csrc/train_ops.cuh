@@ -209,6 +209,102 @@ __global__ void __launch_bounds__(256, 2) head_bwd_kernel(const __nv_bfloat16* _
   if ((int)threadIdx.x < ncls) atomicAdd(db + threadIdx.x, red[256 + threadIdx.x]);
 }
 
+// Last unit of the network (up.3.conv.3 -> BatchNorm -> ReLU -> OutConv): its post-ReLU tensor `a` and the gradient
+// `da` are never materialised.  Both backward passes recompute a = bf16(relu(z*scale + shift)) and
+// da = bf16(sum_k dy[k] w[k][c]) from z (read once per pass) and the tiny dy planes:
+//   pass 1: sums[c] = sum g, sums[C+c] = sum g*zhat  (g = da * (z*scale+shift > 0)),  dw_head += dy a,  db_head += dy
+//   pass 2: dz = gamma*rstd*(g - sum_g/n - zhat*sum_gz/n)
+// 3 tensor passes instead of 7 (head_bwd 2 + bn_bwd_reduce 2 + bn_bwd_apply 3).  Same thread mapping as head_bwd_kernel.
+template <int NCLS, bool APPLY>
+__global__ void __launch_bounds__(256, 2) head_bn_bwd_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ dy,
+                                                             const float* __restrict__ w, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                             float count, unsigned npix_per_img, unsigned total,
+                                                             float* __restrict__ sums, float* __restrict__ dw,
+                                                             float* __restrict__ db, __nv_bfloat16* __restrict__ dz) {
+  const int c8 = threadIdx.x & 7;
+  const unsigned p0 = (blockIdx.x * 256u + threadIdx.x) >> 3, pstep = (gridDim.x * 256u) >> 3;
+  float wr[NCLS][8], sc[8], sh[8], mu[8], rs[8];
+  float acc[NCLS][8], accb[NCLS], s1[8], s2[8];      // pass 1 accumulators
+  float k1[8], k2[8], k3[8];                           // pass 2 constants
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    sc[j] = scale[c]; sh[j] = shift[c]; mu[j] = mean[c]; rs[j] = rstd[c];
+    s1[j] = 0.f; s2[j] = 0.f;
+    if (APPLY) { const float inv = 1.f / count; k1[j] = gamma[c] * rstd[c]; k2[j] = sums[c] * inv; k3[j] = sums[64 + c] * inv; }
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) { wr[k][j] = w[k * 64 + c]; acc[k][j] = 0.f; }
+  }
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) accb[k] = 0.f;
+  for (unsigned px0 = p0; px0 < total; px0 += 4 * pstep) {
+    uint4 uz[4];
+    float g[4][NCLS];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned px = px0 + u * pstep;
+      if (px < total) {
+        uz[u] = *reinterpret_cast<const uint4*>(z + (size_t)px * 64 + c8 * 8);
+        const unsigned b = px / npix_per_img, pp = px - b * npix_per_img;
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) g[u][k] = __ldg(dy + ((size_t)b * NCLS + k) * npix_per_img + pp);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned px = px0 + u * pstep;
+      if (px >= total) break;
+      float zv[8], o[8];
+      unpack8(uz[u], zv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = zv[j] * sc[j] + sh[j];
+        float dav = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) dav = fmaf(g[u][k], wr[k][j], dav);
+        dav = __bfloat162float(__float2bfloat16_rn(dav));              // the rounding head_bwd's stored da had
+        const float gg = pre > 0.f ? dav : 0.f;
+        const float zh = (zv[j] - mu[j]) * rs[j];
+        if (APPLY) {
+          o[j] = k1[j] * (gg - k2[j] - zh * k3[j]);
+        } else {
+          const float av = __bfloat162float(__float2bfloat16_rn(fmaxf(pre, 0.f)));
+          s1[j] += gg;
+          s2[j] += gg * zh;
+#pragma unroll
+          for (int k = 0; k < NCLS; ++k) acc[k][j] = fmaf(g[u][k], av, acc[k][j]);
+        }
+      }
+      if (APPLY) *reinterpret_cast<uint4*>(dz + (size_t)px * 64 + c8 * 8) = pack8(o);
+      else if (c8 == 0) {
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) accb[k] += g[u][k];
+      }
+    }
+  }
+  if (APPLY) return;
+  __shared__ float red[4 * 64 + 4 + 128];
+  for (int i = threadIdx.x; i < 4 * 64 + 4 + 128; i += 256) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&red[260 + c8 * 8 + j], s1[j]);
+    atomicAdd(&red[260 + 64 + c8 * 8 + j], s2[j]);
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) atomicAdd(&red[k * 64 + c8 * 8 + j], acc[k][j]);
+  }
+  if (c8 == 0) {
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) atomicAdd(&red[256 + k], accb[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NCLS * 64; i += 256) atomicAdd(dw + i, red[i]);
+  if ((int)threadIdx.x < NCLS) atomicAdd(db + threadIdx.x, red[256 + threadIdx.x]);
+  if (threadIdx.x < 128) atomicAdd(sums + threadIdx.x, red[260 + threadIdx.x]);
+}
+
 // BatchNorm+ReLU backward, reduction pass: sums[c] = sum g, sums[C+c] = sum g*zhat, g = da*(a>0), zhat=(z-mean)*rstd.
 // With `a == nullptr` there is no ReLU (plain per-channel sum of da: transposed-conv bias gradient).
 // The ReLU mask is recomputed from the stored z (z*scale + shift > 0, the very expression bn_relu_apply rounded), so

@@ -106,7 +106,7 @@ _DEFAULT_ENV = StepEnv()
 
 
 def _unit_forward(conv: nn.Conv2d, bn: nn.BatchNorm2d, pw: PackedTrainWeights, src0, src1=None, off=(0, 0), pool=False, first=False,
-                  env: StepEnv = _DEFAULT_ENV):
+                  env: StepEnv = _DEFAULT_ENV, apply=True):
     B, H, W, _ = src0.shape
     cout = conv.out_channels
     stats = env.zeros(2 * cout, src0.device)
@@ -116,7 +116,8 @@ def _unit_forward(conv: nn.Conv2d, bn: nn.BatchNorm2d, pw: PackedTrainWeights, s
     z = ops.conv(src0, pw.fwd[id(conv)], cout, 9, src1=src1, off=off, shift=neg_center, stats=stats)
     # batch statistics -> (scale, shift, mean, rstd); running stats (momentum 0.1) and num_batches_tracked updated in place
     scale, shift, mean, rstd = ops.bn_finalize(stats, B * H * W, bn, neg_center)
-    a, pooled = ops.bn_relu_apply(z, scale, shift, pool=pool)
+    # apply=False (last unit): the consumer (the 1x1 head) applies BatchNorm + ReLU itself, `a` is never stored
+    a, pooled = ops.bn_relu_apply(z, scale, shift, pool=pool) if apply else (None, None)
     u = _Unit()
     u.src0, u.src1, u.off, u.z, u.a, u.mean, u.rstd, u.pooled, u.conv, u.bn, u.first = src0, src1, off, z, a, mean, rstd, pooled, conv, bn, first
     u.scale, u.shift = scale, shift
@@ -144,11 +145,16 @@ def train_forward(net, x: torch.Tensor, pw: PackedTrainWeights, env: StepEnv = _
         u = ops.conv(y_prev, pw.fwd[id(up)], cup, ntaps=1, groups=4, scale=ops.ones(dev, 4 * cup), shift=up.bias.detach().repeat(4))
         off = ((skip.shape[1] - u.shape[1]) // 2, (skip.shape[2] - u.shape[2]) // 2)           # F.pad left/top (unet.py:46-47)
         u1 = _unit_forward(seq[0], seq[1], pw, skip, src1=u, off=off, env=env)
-        u2 = _unit_forward(seq[3], seq[4], pw, u1.a, env=env)
+        u2 = _unit_forward(seq[3], seq[4], pw, u1.a, env=env, apply=(i < len(dec) - 1))
         ctx["dec"].append((up, y_prev, u, off, u1, u2))
         y_prev = u2.a
     w_head = net.outc.conv.weight.detach().reshape(net.n_classes, -1)
-    y = ops.head_fwd(y_prev, w_head, net.outc.conv.bias.detach())
+    last = ctx["dec"][-1][5] if dec else None
+    if last is not None:
+        # OutConv reads relu(BatchNorm(z)) of the last unit directly from z (unet.py:17,54-57 in one pass)
+        y = ops.bn_relu_head_fwd(last.z, last.scale, last.shift, w_head, net.outc.conv.bias.detach())
+    else:
+        y = ops.head_fwd(y_prev, w_head, net.outc.conv.bias.detach())
     ctx["a_last"] = y_prev
     return y, ctx
 
@@ -174,12 +180,18 @@ class GradSink:
 
 
 def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: "GradSink", need_dx: bool, split: int = 0,
-                   env: StepEnv = _DEFAULT_ENV):
+                   env: StepEnv = _DEFAULT_ENV, head=None):
     """backward of conv -> BN -> ReLU.  Returns the input gradient(s) (None if not needed).
-    split > 0: the conv input was the virtual concat [skip | up]; returns (dskip, dup_full)."""
-    B, H, W, Cn = u.a.shape
-    dz, sums = ops.bn_bwd(da, u.scale, u.shift, u.z, u.mean, u.rstd, u.bn.weight.detach(), B * H * W,
-                          sums=env.zeros(2 * Cn, da.device))
+    split > 0: the conv input was the virtual concat [skip | up]; returns (dskip, dup_full).
+    head = (dy, w_head, dw_head, db_head): this is the last unit, `da` is None and the OutConv backward is fused in."""
+    B, H, W, Cn = u.z.shape
+    if head is not None:
+        dy, w_head, dwh, dbh = head
+        dz, sums = ops.head_bn_bwd(u.z, dy, w_head, u.scale, u.shift, u.mean, u.rstd, u.bn.weight.detach(), dwh, dbh,
+                                   sums=env.zeros(2 * Cn, dy.device))
+    else:
+        dz, sums = ops.bn_bwd(da, u.scale, u.shift, u.z, u.mean, u.rstd, u.bn.weight.detach(), B * H * W,
+                              sums=env.zeros(2 * Cn, da.device))
     grads.put(u.bn.bias, sums[:Cn])
     grads.put(u.bn.weight, sums[Cn:])
     gw = grads.dest(u.conv.weight)
@@ -214,14 +226,21 @@ def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "G
     dwh = grads.dest(net.outc.conv.weight)
     dbh.zero_()
     dwh.zero_()
-    da = ops.head_bwd(ctx["a_last"], dy.contiguous().float(), w_head, dwh, dbh)
-    grads.done(net.outc.conv.bias)
-    grads.done(net.outc.conv.weight)
+    dy = dy.contiguous().float()
+    fused_head = depth > 0                                   # the last unit's activation was never stored
+    da = None if fused_head else ops.head_bwd(ctx["a_last"], dy, w_head, dwh, dbh)
+    if not fused_head:
+        grads.done(net.outc.conv.bias)
+        grads.done(net.outc.conv.weight)
     dskips = [None] * (depth + 1)
     # ---- decoder, last block first
     for i in range(depth - 1, -1, -1):
         up, y_prev, u, off, u1, u2 = ctx["dec"][i]
-        da1 = _unit_backward(u2, da, pw, grads, need_dx=True, env=env)
+        last = fused_head and i == depth - 1
+        da1 = _unit_backward(u2, da, pw, grads, need_dx=True, env=env, head=(dy, w_head, dwh, dbh) if last else None)
+        if last:
+            grads.done(net.outc.conv.bias)
+            grads.done(net.outc.conv.weight)
         cskip = u1.src0.shape[-1]
         dskip, dup = _unit_backward(u1, da1, pw, grads, need_dx=True, split=cskip, env=env)
         l = depth - 1 - i

@@ -104,6 +104,26 @@ def head_fwd(a, w, bias):
     return y
 
 
+def bn_relu_head_fwd(z, scale, shift, w, bias):
+    """y = OutConv(relu(z*scale + shift)) from the raw conv output of the last unit (its activation is never stored)."""
+    B, H, W, _ = z.shape
+    ncls = w.shape[0]
+    y = torch.empty(B, ncls, H, W, dtype=torch.float32, device=z.device)
+    check(lib.gsd_op_bn_relu_head_fwd(_p(z), _p(scale), _p(shift), _p(w), _p(bias), ncls, B, H, W, _p(y), _st(z.device)),
+          "gsd_op_bn_relu_head_fwd")
+    return y
+
+
+def head_bn_bwd(z, dy, w, scale, shift, mean, rstd, gamma, dw, db, sums=None):
+    """backward of OutConv + ReLU + BatchNorm of the last unit -> (dz bf16, sums = [dbeta | dgamma]); dw / db accumulated."""
+    B, H, W, Cn = z.shape
+    sums = torch.zeros(2 * Cn, dtype=torch.float32, device=z.device) if sums is None else sums
+    dz = torch.empty_like(z)
+    check(lib.gsd_op_head_bn_bwd(_p(z), _p(dy), _p(w), _p(scale), _p(shift), _p(mean), _p(rstd), _p(gamma), float(B * H * W),
+                                 w.shape[0], B, H, W, _p(sums), _p(dw), _p(db), _p(dz), _st(z.device)), "gsd_op_head_bn_bwd")
+    return dz, sums
+
+
 def head_bwd(a, dy, w, dw, db):
     B, H, W, _ = a.shape
     da = torch.empty_like(a)

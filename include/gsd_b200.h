@@ -202,6 +202,16 @@ int gsd_op_bn_bwd_reduce(const void* da, const float* scale, const float* shift,
 int gsd_op_bn_bwd_apply(const void* da, const float* scale, const float* shift, const void* z, const float* mean,
                         const float* rstd, const float* gamma, const float* sums, double count, long long npix, int C,
                         void* dz, void* stream);
+/* Last unit of the network (up.3.conv.3 -> BatchNorm2d -> ReLU -> OutConv, unet.py:17,54-57) without materialising
+ * the post-ReLU tensor: forward y = OutConv(relu(z*scale + shift)) from the raw conv output z ... */
+int gsd_op_bn_relu_head_fwd(const void* z, const float* scale, const float* shift, const float* w, const float* bias,
+                            int ncls, int B, int H, int W, float* y, void* stream);
+/* ... and its backward in two passes over z: sums[128] (zeroed by the caller) = [dbeta | dgamma], dw/db (accumulated)
+ * = OutConv weight / bias gradients, dz = gradient of the raw conv output.  Equals gsd_op_head_bwd followed by
+ * gsd_op_bn_bwd_reduce / _apply on the materialised tensors (3 tensor passes instead of 7). */
+int gsd_op_head_bn_bwd(const void* z, const float* dy, const float* w, const float* scale, const float* shift,
+                       const float* mean, const float* rstd, const float* gamma, double count, int ncls, int B, int H,
+                       int W, float* sums, float* dw, float* db, void* dz, void* stream);
 /* MaxPool2d(2) backward fused with the skip-connection gradient add (dskip may be NULL) */
 int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* dskip, int B, int H, int W, int C, void* dfull,
                        void* stream);

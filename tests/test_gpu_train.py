@@ -350,3 +350,39 @@ def test_batched_weight_pack_matches_per_layer_pack():
     pw.repack()
     w = net.inc.double_conv[3].weight.detach()
     assert torch.equal(pw.dgrad[id(net.inc.double_conv[3])], ops.pack_weight(1, w, 64, 64))
+
+
+@pytest.mark.parametrize("ncls", [1, 2])
+def test_fused_last_unit_matches_unfused_ops(ncls):
+    """gsd_op_bn_relu_head_fwd / gsd_op_head_bn_bwd (last unit without a stored activation) against the chain of
+    bn_relu_apply -> head_fwd and head_bwd -> bn_bwd on materialised tensors: identical roundings, fp32 sums differ only
+    in accumulation order."""
+    from gelslim_depth_b200.train import ops
+    d = dev()
+    g = torch.Generator().manual_seed(20 + ncls)
+    B, H, W, C = 3, 21, 27, 64
+    z = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16).to(d)
+    scale = (torch.rand(C, generator=g) + 0.5).to(d) * torch.where(torch.arange(C) % 7 == 0, -1.0, 1.0).to(d)
+    shift = (0.2 * torch.randn(C, generator=g)).to(d)
+    mean = (0.1 * torch.randn(C, generator=g)).to(d)
+    rstd = (torch.rand(C, generator=g) + 0.5).to(d)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(d)
+    w = (0.2 * torch.randn(ncls, C, generator=g)).to(d)
+    bias = torch.randn(ncls, generator=g).to(d)
+    dy = torch.randn(B, ncls, H, W, generator=g).to(d)
+    # forward
+    a, _ = ops.bn_relu_apply(z, scale, shift)
+    y_ref = ops.head_fwd(a, w, bias)
+    y = ops.bn_relu_head_fwd(z, scale, shift, w, bias)
+    assert torch.equal(y, y_ref)
+    # backward
+    dw_ref, db_ref = torch.zeros(ncls, C, device=d), torch.zeros(ncls, device=d)
+    da = ops.head_bwd(a, dy, w, dw_ref, db_ref)
+    dz_ref, sums_ref = ops.bn_bwd(da, scale, shift, z, mean, rstd, gamma, B * H * W)
+    dw, db = torch.zeros(ncls, C, device=d), torch.zeros(ncls, device=d)
+    dz, sums = ops.head_bn_bwd(z, dy, w, scale, shift, mean, rstd, gamma, dw, db)
+    torch.cuda.synchronize()
+    assert torch.allclose(dw, dw_ref, rtol=1e-5, atol=1e-4) and torch.allclose(db, db_ref, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(sums, sums_ref, rtol=1e-5, atol=1e-4)
+    diff = (dz.float() - dz_ref.float()).abs()
+    assert float((diff > 2 ** -7 * dz_ref.float().abs() + 1e-6).float().mean()) == 0.0   # at most one bf16 ulp (sums order)
