@@ -332,7 +332,8 @@ def main():
 
     # ---------------- end to end through the C ABI with HOST buffers (e2e)
     chunk = args.chunk or max(1, B // 4)      # 16-frame chunks measured best (profiles/r1_sweep_1gpu.jsonl)
-    plan.set_chunk(chunk)
+    ramp = max(1, chunk // 2) if not args.chunk else 0   # smaller first / last chunk: less exposed upload / download
+    plan.set_chunk(chunk, first=ramp, last=ramp)
     for _ in range(2):
         plan.forward_host(raw_h, base_dev, pp, y_host, x_dev, y_dev, packed)
     barrier()
@@ -409,6 +410,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * CIN * H * W * 4,
                     "d2h_bytes_per_step": B * NCLS * H * W * 4, "steps": e2e_steps, "chunk_frames": chunk,
+                    "first_last_chunk_frames": ramp,
                     "api": "gsd_forward_host (pinned fp32 frames in, fp32 depth maps out, copies inside the timed region)"},
             "gpu_launches": plan.launches * args.steps, "clocks": clocks, "train": train, "latency": latency,
             "layers": table}

@@ -38,11 +38,12 @@ __device__ __forceinline__ float pre_load(const PreParams& p, long plane, long o
 // normalize_tactile_image (normalization_utils.py:29-34) -> NHWC bf16 with channels padded to 16
 // (the first conv's K-block).  One thread per output pixel; reads are coalesced along x per channel
 // plane, the 32-byte pixel record is written as two 16-byte stores.
+template <bool IDENT>   // IDENT: raw size == network size (G1/G2): no resampling loops, all 2*C loads of a pixel in flight
 __global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_bfloat16* __restrict__ out) {
   // one block = 256 consecutive pixels of one image row segment; 32-bit index arithmetic, no per-pixel division
   const int tiles_per_row = (p.W + 255) / 256;
   const int rows = p.B * p.H;
-  const bool identity = (p.Hr == p.H) && (p.Wr == p.W);
+  constexpr bool identity = IDENT;
   for (int t = blockIdx.x; t < rows * tiles_per_row; t += gridDim.x) {
     const int r = t / tiles_per_row;                    // block-uniform
     const int x = (t - r * tiles_per_row) * 256 + threadIdx.x;
@@ -57,6 +58,25 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_b
     float v[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (IDENT) {
+      float tv[8], bv[8];
+      const long off = (long)y * p.Wr + x;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < p.C) {
+          tv[c] = pre_load(p, pre_plane(p, b, c, 0), off);
+          bv[c] = p.use_diff ? __ldg(p.base + pre_plane(p, b, c, p.base_batch) * p.Hr * p.Wr + off) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < p.C) {
+          float t = tv[c];
+          if (p.use_diff) t = (t - bv[c] + 255.0f) * 0.5f;
+          v[c] = p.in_scale[c] * (t * inv) + p.in_shift[c];
+        }
+      }
+    } else
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       if (c < p.C) {

@@ -55,6 +55,7 @@ struct gsd_plan {
   std::vector<size_t> a_off, s_off, p_off, u_off, da_off, db_off;
   // bound state
   int chunk = 0;
+  int chunk_first = 0, chunk_last = 0;   // host pipeline ramp: smaller first / last chunk (0 = same as chunk)
   void* bound_ws = nullptr;
   const void* bound_packed = nullptr;
   std::vector<ChunkLaunches> chunks;
@@ -191,15 +192,38 @@ extern "C" size_t gsd_plan_workspace_bytes(const gsd_plan* p) { return p ? p->ws
 extern "C" size_t gsd_plan_packed_bytes(const gsd_plan* p) { return p ? p->packed_bytes : 0; }
 extern "C" int gsd_plan_num_params(const gsd_plan* p) { return p ? 6 * (p->depth + 1) + 8 * p->depth + 2 : 0; }
 extern "C" int gsd_plan_num_bn_buffers(const gsd_plan* p) { return p ? 2 * (2 * (p->depth + 1) + 2 * p->depth) : 0; }
+// Frames per chunk, in order.  gsd_forward_host pipelines H2D(c+1) | compute(c) | D2H(c-1): only the first chunk's
+// upload and the last chunk's download are exposed, so those two chunks may be made smaller (the ramp).
+static std::vector<int> chunk_schedule(const gsd_plan* p) {
+  std::vector<int> v;
+  int left = p->g.batch;
+  const int last = (p->chunk_last > 0 && p->chunk_last < p->chunk) ? p->chunk_last : 0;
+  if (p->chunk_first > 0 && p->chunk_first < p->chunk && left > p->chunk_first + last) {
+    v.push_back(p->chunk_first);
+    left -= p->chunk_first;
+  }
+  const int body = left - ((last && left > last) ? last : 0);
+  for (int done = 0; done < body; done += p->chunk) v.push_back(body - done < p->chunk ? body - done : p->chunk);
+  if (left - body > 0) v.push_back(left - body);
+  return v;
+}
 extern "C" int gsd_plan_forward_launches(const gsd_plan* p) {
   if (!p) return 0;
-  const int nchunks = (p->g.batch + p->chunk - 1) / p->chunk;
+  const int nchunks = (int)chunk_schedule(p).size();
   return nchunks * (1 + 2 * (p->depth + 1) + 3 * p->depth + (p->head_fused ? 0 : 1));   // + area resample when sizes differ
 }
 extern "C" int gsd_plan_set_chunk(gsd_plan* p, int frames_per_chunk) {
   GSD_CHECK(p && frames_per_chunk >= 1, "gsd_plan_set_chunk: bad argument");
   p->chunk = frames_per_chunk > p->g.batch ? p->g.batch : frames_per_chunk;
+  p->chunk_first = p->chunk_last = 0;
   p->bound_ws = nullptr;   // force re-binding
+  return 0;
+}
+extern "C" int gsd_plan_set_chunk_ramp(gsd_plan* p, int first_frames, int last_frames) {
+  GSD_CHECK(p && first_frames >= 0 && last_frames >= 0, "gsd_plan_set_chunk_ramp: bad argument");
+  p->chunk_first = first_frames;
+  p->chunk_last = last_frames;
+  p->bound_ws = nullptr;
   return 0;
 }
 extern "C" double gsd_plan_conv_flops(const gsd_plan* p) { return p ? p->conv_flops : 0; }
@@ -268,10 +292,12 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
   char* W = static_cast<char*>(ws);
   const char* P = static_cast<const char*>(packed);
   auto fptr = [&](size_t off) { return reinterpret_cast<const float*>(P + off); };
-  for (int b0 = 0; b0 < g.batch; b0 += p->chunk) {
+  const std::vector<int> schedule = chunk_schedule(p);
+  int b0 = 0;
+  for (size_t ci = 0; ci < schedule.size(); b0 += schedule[ci], ++ci) {
     ChunkLaunches ch;
     ch.b0 = b0;
-    ch.nb = (b0 + p->chunk <= g.batch) ? p->chunk : g.batch - b0;
+    ch.nb = schedule[ci];
     const size_t es = g.dtype == GSD_DTYPE_FP32 ? 4 : 2;
     auto act = [&](size_t off, int l_h, int l_w, int c) {   // address of frame b0 inside a (B,h,w,c) tensor
       return static_cast<void*>(W + off + (size_t)b0 * l_h * l_w * c * es);
@@ -470,7 +496,11 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const 
     return 0;
   }
   __nv_bfloat16* in16 = reinterpret_cast<__nv_bfloat16*>(W + p->in16_off + (size_t)ch.b0 * g.height * g.width * 16 * 2);
-  prologue_kernel<<<ew_grid((long)ch.nb * g.height * ((g.width + 255) / 256) * 256, 256, 148 * 32), 256, 0, st>>>(pre, in16);
+  {
+    const int pg = ew_grid((long)ch.nb * g.height * ((g.width + 255) / 256) * 256, 256, 148 * 32);
+    if (pre.Hr == pre.H && pre.Wr == pre.W) prologue_kernel<true><<<pg, 256, 0, st>>>(pre, in16);
+    else prologue_kernel<false><<<pg, 256, 0, st>>>(pre, in16);
+  }
   GSD_CUDA(cudaGetLastError());
   GSD_TRY(mark());
   for (const AnyLaunch& L : ch.convs) {

@@ -76,7 +76,9 @@ extern "C" int gsd_op_prologue_bf16(const float* x, const float* base, int base_
   p.x = x; p.base = use_diff ? base : nullptr; p.base_batch = base_batch; p.use_diff = use_diff;
   p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W; p.split_fingers = 0; p.input_u8 = 0;
   for (int c = 0; c < 8; ++c) { p.in_scale[c] = scale8_host[c]; p.in_shift[c] = shift8_host[c]; }
-  prologue_kernel<<<ew_grid((long)B * H * ((W + 255) / 256) * 256, 256, 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<__nv_bfloat16*>(out16));
+  const int pg = ew_grid((long)B * H * ((W + 255) / 256) * 256, 256, 148 * 32);
+  if (Hr == H && Wr == W) prologue_kernel<true><<<pg, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<__nv_bfloat16*>(out16));
+  else prologue_kernel<false><<<pg, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<__nv_bfloat16*>(out16));
   GSD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -57,8 +57,10 @@ class Plan:
         self.workspace = torch.empty(lib.gsd_plan_workspace_bytes(self.handle), dtype=torch.uint8, device=device)
         self.packed_bytes = lib.gsd_plan_packed_bytes(self.handle)
 
-    def set_chunk(self, frames: int):
+    def set_chunk(self, frames: int, first: int = 0, last: int = 0):
         check(lib.gsd_plan_set_chunk(self.handle, int(frames)), "gsd_plan_set_chunk")
+        if first or last:
+            check(lib.gsd_plan_set_chunk_ramp(self.handle, int(first), int(last)), "gsd_plan_set_chunk_ramp")
 
     @property
     def launches(self) -> int:

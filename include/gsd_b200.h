@@ -92,6 +92,9 @@ int gsd_plan_forward_launches(const gsd_plan* p);
 /* Process the batch as independent chunks of `frames_per_chunk` frames (default: the whole batch).
  * Chunks are what gsd_forward_host pipelines against the host<->device copies. */
 int gsd_plan_set_chunk(gsd_plan* p, int frames_per_chunk);
+/* gsd_forward_host pipelines upload | compute | download chunk by chunk, so only the first upload and the last
+ * download are exposed: a smaller first / last chunk (0 = same as frames_per_chunk) shortens them. */
+int gsd_plan_set_chunk_ramp(gsd_plan* p, int first_frames, int last_frames);
 /* 2*M*N*K summed over the conv / transposed-conv GEMMs of one gsd_forward (valid after the first
  * forward); the denominator-free numerator of bench.py's tensor roofline. */
 double gsd_plan_conv_flops(const gsd_plan* p);

@@ -259,6 +259,13 @@ def test_forward_host_pipelined_matches_device_path():
     xd, yd = torch.empty_like(x, device=dev()), torch.empty(5, 2, 32, 43, device=dev())
     plan.forward_host(xh, None, pp, yh, xd, yd, net.packed_weights(plan))
     assert torch.equal(yh, y_ref)
+    one_chunk_launches = plan.launches
+    # ramp: smaller first / last chunk (1 + 2 + 1 + 1 frames) must cover every frame exactly once
+    yh.zero_()
+    plan.set_chunk(2, first=1, last=1)
+    assert plan.launches == 4 * (one_chunk_launches // 3)       # 3 chunks before, 4 now
+    plan.forward_host(xh, None, pp, yh, xd, yd, net.packed_weights(plan))
+    assert torch.equal(yh, y_ref)
 
 
 @pytest.mark.parametrize("cin,cin1,cout,h,w,b,pool", [(64, 0, 64, 19, 23, 2, False), (64, 0, 64, 40, 53, 2, True),
