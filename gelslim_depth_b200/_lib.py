@@ -90,7 +90,8 @@ SYMBOLS = {
     "gsd_op_adam_ema": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_longlong, C.c_float, C.c_longlong, C.c_float, C.c_void_p]),
     "gsd_op_image_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p,
-                                      C.c_int, C.c_void_p]),
+                                      C.c_int, C.c_int, C.c_void_p]),
+    "gsd_op_gaussian_blur": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
 }
 
 if not os.path.exists(LIB_PATH):

@@ -65,7 +65,7 @@ struct HaloGeom {
 // NEPI = epilogue warps (4: one per TMEM lane quadrant; 8: two sets of four that drain ALTERNATE work items, i.e.
 // one set per TMEM accumulator buffer -- the per-tile bookkeeping is then paid once per tile, not once per unit)
 template <int BN, int MT, bool WRES, int BKB, int NEPI>
-__global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr int kHaloThreads = 64 + 32 * NEPI;
   using G = HaloGeom<BKB>;
   constexpr int B_BYTES = BN * BKB;

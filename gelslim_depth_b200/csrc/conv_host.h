@@ -294,7 +294,10 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   }
   const long m_tiles = (long)p.tiles_x * p.tiles_y * d.B;
   const long items = ((m_tiles + mt - 1) / mt) * p.n_tiles;
-  L->grid = (int)(items < num_sms ? items : num_sms);
+  // the first-layer variant (16-channel rows) is epilogue-latency-bound: two co-resident CTAs per SM (78 KB smem, 96
+  // registers, 128 TMEM columns each) double the warps the schedulers can pick from
+  const long ctas = (long)num_sms * (bkb == 32 ? 2 : 1);
+  L->grid = (int)(items < ctas ? items : ctas);
   L->flops = 2.0 * d.B * d.H * d.W * (double)d.Cout * 9 * (d.C0 + d.C1);
   return 0;
 }

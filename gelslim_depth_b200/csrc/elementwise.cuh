@@ -243,6 +243,35 @@ __global__ void __launch_bounds__(256) image_affine_kernel(const PreParams p, fl
   }
 }
 
+// torchvision gaussian_blur (image_utils.py:17-19, general_dataset.py:76-89): depthwise k x k Gaussian with reflect
+// padding on fp32 NCHW planes.  The separable 1-D weights (<= 31 taps) arrive by value; one thread per output pixel.
+struct BlurParams {
+  float w[32];
+  int k, planes, H, W;
+};
+__global__ void __launch_bounds__(256) gaussian_blur_kernel(const BlurParams p, const float* __restrict__ in, float* __restrict__ out) {
+  const long total = (long)p.planes * p.H * p.W;
+  const int r = p.k / 2;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.W);
+    const int y = (int)((idx / p.W) % p.H);
+    const float* src = in + (idx / ((long)p.W * p.H)) * p.H * p.W;
+    float acc = 0.f;
+    for (int j = 0; j < p.k; ++j) {
+      int yy = y + j - r;
+      yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);          // reflect (no edge repeat)
+      float row = 0.f;
+      for (int i = 0; i < p.k; ++i) {
+        int xx = x + i - r;
+        xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+        row = fmaf(p.w[i], __ldg(src + (long)yy * p.W + xx), row);
+      }
+      acc = fmaf(p.w[j], row, acc);
+    }
+    out[idx] = acc;
+  }
+}
+
 // ---------------------------------------------------------------- weight packing
 // Conv2d weight (O, I, kh, kw) fp32 -> bf16 [O][kh*kw][Ipad], zero for i >= I.
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int I, int taps, int Ipad,

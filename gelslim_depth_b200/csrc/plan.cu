@@ -616,14 +616,15 @@ extern "C" int gsd_op_conv_bf16(const void* src0, int C0, const void* src1, int 
 
 extern "C" int gsd_op_image_affine(const float* x, const float* base, int base_batch, int use_diff, int B, int Cc,
                                    int Hr, int Wr, int H, int W, const float* scale8, const float* shift8, float* out,
-                                   int device, void* stream) {
+                                   int split_fingers, int device, void* stream) {
   GSD_CHECK(x && out && scale8 && shift8, "gsd_op_image_affine: null argument");
+  GSD_CHECK(!split_fingers || B % 2 == 0, "gsd_op_image_affine: split_fingers needs an even output batch (2 x frames)");
   GSD_CHECK(!use_diff || base, "gsd_op_image_affine: use_diff without base");
   GSD_CHECK(B >= 1 && Cc >= 1 && H >= 1 && W >= 1 && Hr >= 1 && Wr >= 1, "gsd_op_image_affine: bad shape");
   GSD_CUDA(cudaSetDevice(device));
   PreParams p;
   p.x = x; p.base = use_diff ? base : nullptr; p.base_batch = base_batch; p.use_diff = use_diff;
-  p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W; p.split_fingers = 0; p.input_u8 = 0;
+  p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W; p.split_fingers = split_fingers ? 1 : 0; p.input_u8 = 0;
   for (int c = 0; c < 8; ++c) { p.in_scale[c] = scale8[c]; p.in_shift[c] = shift8[c]; }
   image_affine_kernel<<<ew_grid((long)B * Cc * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, out);
   GSD_CUDA(cudaGetLastError());
@@ -696,6 +697,26 @@ extern "C" int gsd_op_wgrad3x3_bf16(const void* x0, int C0, const void* x1, int 
   WgradLaunch L;
   GSD_TRY(build_wgrad_launch(x0, C0, x1 ? x1 : nullptr, x1 ? C1 : 0, H1, W1, off_y, off_x, dz, Cout, B, H, W, dw, sms, &L));
   return run_wgrad_launch(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gsd_op_gaussian_blur(const float* x, int planes, int H, int W, int kernel_size, float sigma, float* out, void* stream) {
+  GSD_CHECK(x && out && planes >= 1 && H >= 1 && W >= 1, "gsd_op_gaussian_blur: bad argument");
+  GSD_CHECK(kernel_size >= 1 && kernel_size <= 31 && (kernel_size & 1), "gsd_op_gaussian_blur: kernel_size must be odd and <= 31");
+  GSD_CHECK(kernel_size / 2 < H && kernel_size / 2 < W, "gsd_op_gaussian_blur: reflect padding needs kernel_size/2 < H, W");
+  BlurParams p;
+  memset(&p, 0, sizeof p);
+  p.k = kernel_size; p.planes = planes; p.H = H; p.W = W;
+  if (sigma <= 0.f) sigma = 0.3f * ((kernel_size - 1) * 0.5f - 1.f) + 0.8f;        // torchvision default
+  double sum = 0;
+  for (int i = 0; i < kernel_size; ++i) {
+    const double xx = -(kernel_size - 1) * 0.5 + i;
+    p.w[i] = (float)exp(-0.5 * (xx / sigma) * (xx / sigma));
+    sum += p.w[i];
+  }
+  for (int i = 0; i < kernel_size; ++i) p.w[i] = (float)(p.w[i] / sum);
+  gaussian_blur_kernel<<<ew_grid((long)planes * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, x, out);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
 }
 
 #include "train_abi.h"

@@ -254,10 +254,15 @@ int gsd_op_adam_ema_dev(float* p, const float* g, float* m, float* v, float* sha
  * Replaces (when called outside the fused forward): get_difference_image (image_utils.py:6-10),
  * sample_multi_channel_image_to_desired_size(..., 'area') (image_utils.py:12-15),
  * normalize_tactile_image / normalize_depth_image / denormalize_depth_image
- * (normalization_utils.py:4-35, 70-130).  scale8/shift8 are HOST arrays of 8 floats. */
+ * (normalization_utils.py:4-35, 70-130).  scale8/shift8 are HOST arrays of 8 floats.
+ * split_fingers != 0: x is (B/2, 2C, Hr, Wr) Left|Right frame pairs and out is (B, C, H, W) = all Left fingers, then
+ * all Right fingers (torch.cat((x[:, :C], x[:, C:]), dim=0), general_dataset.py:71-74); base likewise. */
 int gsd_op_image_affine(const float* x, const float* base, int base_batch, int use_diff, int B, int C,
                         int Hr, int Wr, int H, int W, const float* scale8_host, const float* shift8_host,
-                        float* out, int device, void* stream);
+                        float* out, int split_fingers, int device, void* stream);
+/* blur_depth_images (image_utils.py:17-19) = torchvision gaussian_blur: depthwise kernel_size x kernel_size Gaussian,
+ * reflect padding, on `planes` fp32 H x W planes; sigma <= 0 selects torchvision's default for the kernel size. */
+int gsd_op_gaussian_blur(const float* x, int planes, int H, int W, int kernel_size, float sigma, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ from .unet_oracle import (unet_forward, unet_forward_with_taps, conditioned_stat
                           trainer_init_state_dict, state_dict_digest)
 from .processing_oracle import (get_difference_image, area_resample, normalize_tactile_image,
                                 denormalize_depth_image, normalize_depth_image,
-                                predict_depth_from_RGB, split_fingers)
+                                predict_depth_from_RGB, split_fingers, blur_depth_images,
+                                preprocess_object_tensors)
 from .train_oracle import TrainOracle, mse_loss
 from .bf16_sim import loss_and_grads_bf16

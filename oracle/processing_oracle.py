@@ -120,3 +120,47 @@ def predict_depth_from_RGB(images, model_fn, output_size, config):
     d = denormalize_depth_image(d, config.depth_normalization_method, config.norm_scale,
                                 config.depth_normalization_parameters)
     return area_resample(d, tuple(output_size))
+
+
+def blur_depth_images(depth, kernel_size: int):
+    """image_utils.py:17-19 -> torchvision gaussian_blur(kernel_size=k) restated: separable Gaussian with
+    sigma = 0.3*((k-1)*0.5-1)+0.8 (torchvision's default), reflect padding, applied per plane with explicit loops over
+    the taps (independent of torchvision and of F.conv2d)."""
+    k = int(kernel_size)
+    sigma = 0.3 * ((k - 1) * 0.5 - 1) + 0.8
+    xs = torch.linspace(-(k - 1) * 0.5, (k - 1) * 0.5, k, dtype=torch.float64)
+    w = torch.exp(-0.5 * (xs / sigma) ** 2)
+    w = (w / w.sum()).to(depth.dtype)
+    r = k // 2
+    h, wd = depth.shape[-2:]
+
+    def reflect(i, n):
+        return -i if i < 0 else (2 * n - 2 - i if i >= n else i)
+
+    rows = torch.zeros_like(depth)
+    for t in range(k):                                   # horizontal pass
+        idx = torch.tensor([reflect(x + t - r, wd) for x in range(wd)])
+        rows = rows + w[t] * depth[..., idx]
+    out = torch.zeros_like(depth)
+    for t in range(k):                                   # vertical pass
+        idx = torch.tensor([reflect(y + t - r, h) for y in range(h)])
+        out = out + w[t] * rows[..., idx, :]
+    return out
+
+
+def preprocess_object_tensors(tactile_image, depth_image, base_tactile_image, input_tactile_image_size, image_normalization_method,
+                              image_normalization_parameters, depth_normalization_method, depth_normalization_parameters, norm_scale,
+                              separate_fingers=True, use_difference_image=True, depth_image_blur_kernel=1):
+    """general_dataset.py:61-97 (`load_object_dataset`) followed by :211-215 (`normalize_sample`) on whole tensors."""
+    size = tuple(input_tactile_image_size)
+    x = get_difference_image(tactile_image, base_tactile_image) if use_difference_image else tactile_image
+    d = depth_image
+    if separate_fingers:
+        x = split_fingers(x)
+        d = torch.cat((d[:, 0:1], d[:, 1:2]), dim=0)
+    x = area_resample(x, size)
+    d = area_resample(d, size)
+    if depth_image_blur_kernel > 1:
+        d = blur_depth_images(d, depth_image_blur_kernel)
+    return {"tactile_image": normalize_tactile_image(x, image_normalization_method, norm_scale, image_normalization_parameters),
+            "depth_image": normalize_depth_image(d, depth_normalization_method, norm_scale, depth_normalization_parameters)}

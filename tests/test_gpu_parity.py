@@ -427,3 +427,29 @@ def test_depth_stream_ring_buffer_graph_replay(layout):
     assert len(stream.latencies_ms) == 6
     with pytest.raises(ValueError):
         stream.push(torch.zeros(3, 3, 3))
+
+
+@pytest.mark.gpu
+def test_dataset_preprocessing_vs_reference_generaldataset():
+    """Left/Right split + difference image + area down-sampling + normalisation of a whole object tensor in
+    one launch per tensor (+ the Gaussian depth blur), against samples served by the unmodified reference GeneralDataset."""
+    import os
+    from gelslim_depth_b200.processing_utils.dataset_utils import preprocess_object_tensors
+    from gelslim_depth_b200.processing_utils.image_utils import blur_depth_images
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "dataset_preprocess.pt"), weights_only=False)
+    data = {k: v.to(dev()) for k, v in fx["data"].items()}
+    for name, case in fx["cases"].items():
+        kw = case["kwargs"]
+        got = preprocess_object_tensors(
+            data["tactile_image"], data["depth_image"], data["base_tactile_image"], case["input_tactile_image_size"],
+            kw["image_normalization_method"], case["image_normalization_parameters"], kw["depth_normalization_method"],
+            case["depth_normalization_parameters"], kw["norm_scale"], separate_fingers=kw["separate_fingers"],
+            use_difference_image=kw["use_difference_image"], interp_method=kw["interp_method"],
+            depth_image_blur_kernel=kw["depth_image_blur_kernel"])
+        assert got["tactile_image"].shape == case["tactile_image"].shape, name
+        assert torch.allclose(got["tactile_image"].cpu(), case["tactile_image"], rtol=1e-5, atol=1e-5), name
+        assert torch.allclose(got["depth_image"].cpu(), case["depth_image"], rtol=1e-5, atol=2e-6), name
+    d = torch.rand(2, 1, 9, 7, generator=torch.Generator().manual_seed(1))
+    assert torch.allclose(blur_depth_images(d.to(dev()), 7).cpu(), oracle.blur_depth_images(d, 7), rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        blur_depth_images(d.to(dev()), 4)            # even kernel sizes have no centre tap (the library rejects them)
