@@ -49,14 +49,51 @@ def traffic_from_profile():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: an NVML polling thread (every 5 ms; the timed region
+    of the default run is ~120 ms, shorter than nvidia-smi's start-up), nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+               (0x80, "hw_power_brake_slowdown"))
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.handle, self.samples, self._stop = None, None, [], threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            phys = int(ids[index]) if ids and all(v.isdigit() for v in ids) and index < len(ids) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def mark(self):
+        """drop what was sampled so far: called at the start of the timed region (the sampler is started earlier so
+        that NVML's first, slow calls are over by then)"""
+        self.samples, self.lines = [], []
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -71,6 +108,20 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1)
+            n = self.nvml
+            try:
+                mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            sm = [float(s) for s, _ in self.samples]
+            mask = 0
+            for _, m in self.samples:
+                mask |= m
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": mx,
+                    "reasons": sorted(name for bit, name in self.REASONS if mask & bit), "samples": len(sm), "source": "nvml 5 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -92,7 +143,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 50"}
 
 
 def synthetic_frames(torch, batch, seed):
@@ -148,17 +199,23 @@ def bench_train(torch, dist, dev, rank, world, batch, steps):
     t = (-0.9 * torch.rand(batch, NCLS, H, W, generator=g)).to(dev)
     stream = torch.cuda.current_stream(dev)
     losses = []
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(3):
         losses.append(ft.step(x, t))
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
+    if sampler:
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
         losses.append(ft.step(x, t))
     e1.record(stream)
     torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if sampler else None
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
@@ -171,7 +228,7 @@ def bench_train(torch, dist, dev, rank, world, batch, steps):
     return {"metric": "train_samples_per_s_6x320x427", "value": sps, "unit": "samples/s", "ms_per_step": ms / steps,
             "batch_per_gpu": batch, "steps": steps, "gflop_per_sample": 599.41,
             "tensor_frac_whole_step": sps / world * 599.41 / 1e3 / sustained,
-            "losses": [float(v) for v in torch.cat(losses).cpu()],
+            "losses": [float(v) for v in torch.cat(losses).cpu()], "clocks": clocks,
             "what": "fwd (train-mode BN) + MSE + bwd (dgrad/wgrad on tcgen05) + bucketed NCCL all-reduce + fused Adam/EMA, "
                     "whole step replayed as one CUDA graph"}
 
@@ -310,12 +367,13 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---------------- device-resident throughput (value)
-    for _ in range(args.warmup):
-        plan.forward(x_dev, base_dev, pp, y_dev, packed)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        plan.forward(x_dev, base_dev, pp, y_dev, packed)
+    barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
