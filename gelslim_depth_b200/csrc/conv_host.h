@@ -254,6 +254,13 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     bn = 128; mt = 2; wres = 0;
     if (((mtl + 1) / 2) * (d.Cout / 128) < num_sms) mt = 1;
     if (mt == 1 && mtl * (d.Cout / 128) < num_sms) bn = 64;
+    // N = 256 (one tile, M = 128): one UMMA reads A (32 smem wavefronts) for 256 output channels -- 96 wavefronts per
+    // 128 tensor cycles instead of 64 per 64, which leaves the smem pipe room for the epilogue.  Measured on B200
+    // (tools/exp_bn256.py, batch 64): +7..10 % for 256->512, 512->256, 1024->512, +2 % for 512->512, no gain for
+    // 256->256 and 128->256, hence the rule below.
+    const bool big = (d.C0 + d.C1 >= 512) || d.Cout >= 512;
+    const bool want256 = d.block_n == 256 || (d.block_n == 0 && big && !getenv("GSD_NO_BN256"));
+    if (want256 && d.Cout % 256 == 0 && mtl * (d.Cout / 256) >= num_sms) { bn = 256; mt = 1; }
   }
   GSD_CHECK(bkb == 128 || wres, "halo conv: first-layer path needs resident weights");
   const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
@@ -320,6 +327,7 @@ inline int run_halo_launch(const HaloLaunch& L, cudaStream_t st) {
   if (L.bn == 64 && L.mt == 1 && !L.wres) return launch_halo_cfg<64, 1, false, 128, 8>(L, st);
   if (L.bn == 128 && L.mt == 1 && !L.wres) return launch_halo_cfg<128, 1, false, 128, 8>(L, st);
   if (L.bn == 128 && L.mt == 2 && !L.wres) return launch_halo_cfg<128, 2, false, 128, 8>(L, st);
+  if (L.bn == 256 && L.mt == 1 && !L.wres) return launch_halo_cfg<256, 1, false, 128, 8>(L, st);
   return fail(-1, "halo conv: no kernel for bn=%d mt=%d wres=%d nepi=%d", L.bn, L.mt, L.wres, L.nepi);
 }
 
