@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(s_tmem_slot);
   for (int i = threadIdx.x; i < p.Cout; i += kHaloThreads) {
-    g_scale[i] = __ldg(p.scale + i);
-    g_shift[i] = __ldg(p.shift + i);
+    if (p.scale) g_scale[i] = __ldg(p.scale + i);      // null: scale == 1 / shift == 0, the epilogue skips the loads
+    if (p.shift) g_shift[i] = __ldg(p.shift + i);
     g_stats[i] = 0.f;
     g_stats[p.Cout + i] = 0.f;
   }
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32)
-          epilogue_32cols(t_row, c0, g_scale + nt * BN, g_shift + nt * BN, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc,
+          epilogue_32cols(t_row, c0, p.scale ? g_scale + nt * BN : nullptr, p.shift ? g_shift + nt * BN : nullptr, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc,
                           p.head_w ? g_head : nullptr, p.head_ncls);
         if (p.head_w && valid) {
           const size_t plane = (size_t)p.H * p.W;

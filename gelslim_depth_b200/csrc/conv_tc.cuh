@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(s_tmem_slot);
   for (int i = threadIdx.x; i < p.ntot; i += kConvThreads) {
-    g_scale[i] = __ldg(p.scale + i);
-    g_shift[i] = __ldg(p.shift + i);
+    if (p.scale) g_scale[i] = __ldg(p.scale + i);      // null: scale == 1 / shift == 0, the epilogue skips the loads
+    if (p.shift) g_shift[i] = __ldg(p.shift + i);
     g_stats[i] = 0.f;
     g_stats[p.ntot + i] = 0.f;
   }
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
           px.rp[i] = pix[i] < 0 ? nullptr : p.out + (pix[i] + goff) * p.cout_per_group + ch0 - c0;
         px.prow = p.pooled ? p.pooled + (((size_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout_per_group + ch0 - c0 + (hx ? 16 : 0) + (hy ? 8 : 0)
                            : nullptr;
-        epilogue_32cols(t_row, c0, g_scale + n0, g_shift + n0, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc, nullptr, 0);
+        epilogue_32cols(t_row, c0, p.scale ? g_scale + n0 : nullptr, p.shift ? g_shift + n0 : nullptr, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc, nullptr, 0);
       }
       // accumulator fully read -> hand it back to the MMA warp
       tc_fence_before();

@@ -74,16 +74,40 @@ __device__ __forceinline__ void epilogue_32cols(uint32_t t_row, int c0, const fl
   }
   // per-channel constants are warp-uniform smem reads: fetch them as 128-bit broadcasts (one smem wavefront per
   // 4 channels) -- the smem data pipe is shared with the tensor core's operand reads and is the scarce resource.
+  // A broadcast LDS.128 still costs two smem wavefronts, so the constants of a 32-column unit cost as much smem
+  // bandwidth as the bf16 transposition below: callers pass sc == nullptr for "scale is 1" (training forward, dgrad) and
+  // sh == nullptr for "shift is 0" (dgrad), and those loads disappear.
   float f[32];
-  const float4* sc4 = reinterpret_cast<const float4*>(sc + c0);
-  const float4* sh4 = reinterpret_cast<const float4*>(sh + c0);
+  if (sc && sh) {
+    const float4* sc4 = reinterpret_cast<const float4*>(sc + c0);
+    const float4* sh4 = reinterpret_cast<const float4*>(sh + c0);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 a = sc4[i], b = sh4[i];
-    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) * a.x + b.x;
-    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) * a.y + b.y;
-    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) * a.z + b.z;
-    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) * a.w + b.w;
+    for (int i = 0; i < 8; ++i) {
+      const float4 a = sc4[i], b = sh4[i];
+      f[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), a.x, b.x);
+      f[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), a.y, b.y);
+      f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), a.z, b.z);
+      f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), a.w, b.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    if (sc) {
+      const float4* sc4 = reinterpret_cast<const float4*>(sc + c0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = sc4[i];
+        f[4 * i + 0] *= a.x; f[4 * i + 1] *= a.y; f[4 * i + 2] *= a.z; f[4 * i + 3] *= a.w;
+      }
+    }
+    if (sh) {
+      const float4* sh4 = reinterpret_cast<const float4*>(sh + c0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = sh4[i];
+        f[4 * i + 0] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+      }
+    }
   }
   if (relu) {
 #pragma unroll

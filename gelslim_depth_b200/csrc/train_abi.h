@@ -23,7 +23,7 @@ extern "C" int gsd_op_conv_auto_bf16(const void* src0, int C0, const void* src1,
                                      int off_x, int B, int H, int W, const void* w, int Cout, int ntaps, int groups,
                                      const float* scale, const float* shift, int relu, void* out, void* pooled,
                                      float* stats, int device, void* stream) {
-  GSD_CHECK(src0 && w && scale && shift && out, "gsd_op_conv_auto_bf16: null argument");
+  GSD_CHECK(src0 && w && out, "gsd_op_conv_auto_bf16: null argument");     // scale / shift may be NULL (= 1 / 0)
   GSD_TRY(check_dev(device, "gsd_op_conv_auto_bf16"));
   ConvDesc d;
   d.src0 = src0; d.C0 = C0; d.src1 = src1; d.C1 = src1 ? C1 : 0; d.H1 = H1; d.W1 = W1; d.off_y = off_y; d.off_x = off_x;
@@ -47,7 +47,7 @@ extern "C" int gsd_op_conv_auto_bf16(const void* src0, int C0, const void* src1,
 extern "C" int gsd_op_convt_dgrad_bf16(const void* du, int Cs, int Hf, int Wf, int off_y, int off_x, const void* w, int Cin,
                                        int B, int H, int W, const float* scale, const float* shift, void* out, int device,
                                        void* stream) {
-  GSD_CHECK(du && w && out && scale && shift, "gsd_op_convt_dgrad_bf16: null argument");
+  GSD_CHECK(du && w && out, "gsd_op_convt_dgrad_bf16: null argument");        // scale / shift may be NULL (= 1 / 0)
   GSD_TRY(check_dev(device, "gsd_op_convt_dgrad_bf16"));
   ConvDesc d;
   d.src0 = du; d.C0 = 2 * Cs; d.B = B; d.H = H; d.W = W; d.w = w; d.Cout = Cin; d.groups = 1; d.ntaps = 2;

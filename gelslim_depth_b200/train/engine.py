@@ -142,7 +142,7 @@ def train_forward(net, x: torch.Tensor, pw: PackedTrainWeights, env: StepEnv = _
         skip = ctx["enc"][l][1].a
         cup = up.out_channels
         dev = y_prev.device
-        u = ops.conv(y_prev, pw.fwd[id(up)], cup, ntaps=1, groups=4, scale=ops.ones(dev, 4 * cup), shift=up.bias.detach().repeat(4))
+        u = ops.conv(y_prev, pw.fwd[id(up)], cup, ntaps=1, groups=4, shift=up.bias.detach().repeat(4))
         off = ((skip.shape[1] - u.shape[1]) // 2, (skip.shape[2] - u.shape[2]) // 2)           # F.pad left/top (unet.py:46-47)
         u1 = _unit_forward(seq[0], seq[1], pw, skip, src1=u, off=off, env=env)
         u2 = _unit_forward(seq[3], seq[4], pw, u1.a, env=env, apply=(i < len(dec) - 1))

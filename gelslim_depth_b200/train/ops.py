@@ -49,9 +49,6 @@ def prologue(x):
 def conv(src0, w, cout, ntaps=9, groups=1, src1=None, off=(0, 0), scale=None, shift=None, relu=False, pool=False, stats=None):
     B, H, W, C0 = src0.shape
     dev = src0.device
-    ntot = groups * cout
-    scale = ones(dev, ntot) if scale is None else scale
-    shift = zeros(dev, ntot) if shift is None else shift
     out = torch.empty((B, H, W, cout) if groups == 1 else (B, 2 * H, 2 * W, cout), dtype=BF16, device=dev)
     pooled = torch.empty(B, H // 2, W // 2, cout, dtype=BF16, device=dev) if pool else None
     C1 = H1 = W1 = 0
@@ -211,8 +208,8 @@ def convt_dgrad(du_full, off, w_dgrad, cin, hs, ws):
     B, Hf, Wf, Cs = du_full.shape
     dev = du_full.device
     out = torch.empty(B, hs, ws, cin, dtype=BF16, device=dev)
-    check(lib.gsd_op_convt_dgrad_bf16(_p(du_full), Cs, Hf, Wf, off[0], off[1], _p(w_dgrad), cin, B, hs, ws, _p(ones(dev, cin)),
-                                      _p(zeros(dev, cin)), _p(out), dev.index or 0, _st(dev)), "gsd_op_convt_dgrad_bf16")
+    check(lib.gsd_op_convt_dgrad_bf16(_p(du_full), Cs, Hf, Wf, off[0], off[1], _p(w_dgrad), cin, B, hs, ws, None, None,
+                                      _p(out), dev.index or 0, _st(dev)), "gsd_op_convt_dgrad_bf16")
     return out
 
 

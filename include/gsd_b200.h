@@ -162,7 +162,9 @@ int gsd_op_wgrad3x3_bf16(const void* x0, int C0, const void* x1, int C1, int H1,
 /* --- training-step operators (train_utils/train_unet.py:346-377); one kernel launch each ------------------ */
 /* conv with automatic kernel choice (halo-resident / tap-streaming) + optional batch statistics:
  * stats[0..N) += sum over valid pixels of the raw accumulator, stats[N..2N) += sum of squares (train-mode
- * BatchNorm2d, unet.py:12,15).  ntaps: 9 (3x3, pad 1) or 1; groups 4 = transposed-conv scatter. */
+ * BatchNorm2d, unet.py:12,15).  ntaps: 9 (3x3, pad 1) or 1; groups 4 = transposed-conv scatter.
+ * scale == NULL means 1, shift == NULL means 0 (training forward / dgrad): the epilogue then skips the per-channel
+ * constant loads, which cost as much shared-memory bandwidth as its bf16 transposition. */
 int gsd_op_conv_auto_bf16(const void* src0, int C0, const void* src1, int C1, int H1, int W1, int off_y,
                           int off_x, int B, int H, int W, const void* w, int Cout, int ntaps, int groups,
                           const float* scale, const float* shift, int relu, void* out, void* pooled,
