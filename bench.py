@@ -285,6 +285,37 @@ def emit(line: dict):
         sys.stdout.flush()
 
 
+def bench_g3_pairs(torch, dev, pairs=64, steps=10):
+    """The reference's SHIPPED pipeline (config_unet_bigdata.py, general_dataset.py:71): UNet(3,1) on the two fingers of a
+    320x427 frame pair, area-down-sampled to 160x213, depth up-sampled back to 320x427 -- through
+    predict_depth_from_frame_pairs (one gsd_forward per batch: split + difference + resampling + normalisation fused)."""
+    import types
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.processing_utils.complete_prediction import predict_depth_from_frame_pairs
+    cfg = types.SimpleNamespace(input_tactile_image_size=(160, 213), interp_method="area", norm_scale=0.9,
+                                image_normalization_method="0_255_to_0_1", image_normalization_parameters=None,
+                                depth_normalization_method="min_max_to_0_-1",
+                                depth_normalization_parameters=(-1.9180814027786255, 0.0))
+    torch.manual_seed(0)
+    net3 = UNet(3, 1, layer_dimensions=DIMS).to(dev).eval()
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, (pairs, 6, H, W), generator=g, dtype=torch.uint8).to(dev)
+    base = torch.randint(0, 256, (1, 6, H, W), generator=g, dtype=torch.uint8).float().to(dev)
+    for _ in range(3):
+        y = predict_depth_from_frame_pairs(frames, base, net3, (H, W), cfg)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        y = predict_depth_from_frame_pairs(frames, base, net3, (H, W), cfg)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "g3_frame_pairs_per_s", "value": pairs / (ms / 1e3), "ms_per_step": ms, "pairs_per_step": pairs,
+            "gflop_per_pair": 99.21, "out_shape": list(y.shape),
+            "what": "predict_depth_from_frame_pairs: uint8 6x320x427 pairs -> UNet(3,1) @160x213 on 2 fingers -> 2x320x427 depth (mm)"}
+
+
 def bench_latency(torch, net, dev, base, frames=500):
     """BASELINE configs[2]: batch-1 streaming through gelslim_depth_b200.streaming.DepthStream -- one interleaved uint8
     camera frame pair in pinned host memory -> H2D -> fused forward -> D2H depth map, one CUDA-graph replay + host
@@ -471,6 +502,7 @@ def main():
                 "flops_per_launch_set": conv_flops, "algorithmic_gflop_per_frame": GFLOP_PER_FRAME}
 
     latency = bench_latency(torch, net, dev, base)
+    g3 = bench_g3_pairs(torch, dev)
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -492,7 +524,7 @@ def main():
                     "uint8_frames": {"value": e2e_u8, "h2d_bytes_per_step": B * CIN * H * W,
                                      "what": "same call with uint8 camera bytes as the host input (gsd_prepost.input_u8)"},
                     "api": "gsd_forward_host (pinned fp32 frames in, fp32 depth maps out, copies inside the timed region)"},
-            "gpu_launches": plan.launches * args.steps, "clocks": clocks, "train": train, "latency": latency,
+            "gpu_launches": plan.launches * args.steps, "clocks": clocks, "train": train, "latency": latency, "g3_pipeline": g3,
             "layers": table}
     emit(line)
     if world > 1:
