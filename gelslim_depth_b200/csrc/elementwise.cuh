@@ -50,9 +50,10 @@ __global__ void __launch_bounds__(256) prologue_kernel(const PreParams p, __nv_b
     if (x >= p.W) continue;
     const int b = r / p.H, y = r - b * p.H;
     int ys = y, ye = y + 1, xs = x, xe = x + 1;
-    if (!identity) {   // adaptive-average-pool bin: [floor(i*in/out), ceil((i+1)*in/out))
-      ys = (int)(((long)y * p.Hr) / p.H); ye = (int)((((long)y + 1) * p.Hr + p.H - 1) / p.H);
-      xs = (int)(((long)x * p.Wr) / p.W); xe = (int)((((long)x + 1) * p.Wr + p.W - 1) / p.W);
+    if (!identity) {   // adaptive-average-pool bin: [floor(i*in/out), ceil((i+1)*in/out)); 32-bit (sizes < 65536)
+      const unsigned uH = p.H, uW = p.W, uHr = p.Hr, uWr = p.Wr;
+      ys = (int)(((unsigned)y * uHr) / uH); ye = (int)((((unsigned)y + 1u) * uHr + uH - 1u) / uH);
+      xs = (int)(((unsigned)x * uWr) / uW); xe = (int)((((unsigned)x + 1u) * uWr + uW - 1u) / uW);
     }
     const float inv = 1.0f / (float)((ye - ys) * (xe - xs));
     float v[16];
@@ -200,20 +201,38 @@ __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restri
 }
 
 // F.interpolate(mode='area') == adaptive average pooling, fp32 NCHW planes (complete_prediction.py:9).
+// A block walks output rows (one 64-bit division per row, none per pixel); bins of at most 2 x 2 source pixels (every
+// up-sampling, e.g. the 160x213 -> 320x427 depth of the shipped pipeline) are read as four predicated loads in flight.
 __global__ void __launch_bounds__(256) area_resample_kernel(const float* __restrict__ in, int planes, int Hi, int Wi,
                                                             int Ho, int Wo, float* __restrict__ out) {
-  const long total = (long)planes * Ho * Wo;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % Wo);
-    const int y = (int)((idx / Wo) % Ho);
-    const long pl = idx / ((long)Wo * Ho);
-    const int ys = (int)(((long)y * Hi) / Ho), ye = (int)((((long)y + 1) * Hi + Ho - 1) / Ho);
-    const int xs = (int)(((long)x * Wi) / Wo), xe = (int)((((long)x + 1) * Wi + Wo - 1) / Wo);
+  const long rows = (long)planes * Ho;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const long pl = row / Ho;
+    const int y = (int)(row - pl * Ho);
+    const int ys = (int)(((unsigned)y * (unsigned)Hi) / (unsigned)Ho);
+    const int ye = (int)((((unsigned)y + 1u) * (unsigned)Hi + (unsigned)Ho - 1u) / (unsigned)Ho);
     const float* src = in + pl * Hi * Wi;
-    float acc = 0.f;
-    for (int yy = ys; yy < ye; ++yy)
-      for (int xx = xs; xx < xe; ++xx) acc += __ldg(src + (long)yy * Wi + xx);
-    out[idx] = acc / (float)((ye - ys) * (xe - xs));
+    float* dst = out + row * Wo;
+    for (int x = threadIdx.x; x < Wo; x += 256) {
+      const int xs = (int)(((unsigned)x * (unsigned)Wi) / (unsigned)Wo);
+      const int xe = (int)((((unsigned)x + 1u) * (unsigned)Wi + (unsigned)Wo - 1u) / (unsigned)Wo);
+      const int ny = ye - ys, nx = xe - xs;
+      float acc = 0.f;
+      if (ny <= 2 && nx <= 2) {
+        const float* p0 = src + (long)ys * Wi + xs;
+        const float v00 = __ldg(p0);
+        const float v01 = nx == 2 ? __ldg(p0 + 1) : 0.f;
+        const float v10 = ny == 2 ? __ldg(p0 + Wi) : 0.f;
+        const float v11 = (ny == 2 && nx == 2) ? __ldg(p0 + Wi + 1) : 0.f;
+        acc = v00;                                   // same accumulation order as the generic loops
+        if (nx == 2) acc += v01;
+        if (ny == 2) { acc += v10; if (nx == 2) acc += v11; }
+      } else {
+        for (int yy = ys; yy < ye; ++yy)
+          for (int xx = xs; xx < xe; ++xx) acc += __ldg(src + (long)yy * Wi + xx);
+      }
+      dst[x] = acc / (float)(ny * nx);
+    }
   }
 }
 

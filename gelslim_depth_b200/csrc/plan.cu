@@ -283,6 +283,8 @@ static void taps3x3(ConvDesc* d) {
   for (int t = 0; t < 9; ++t) { d->dy[t] = (int8_t)(t / 3 - 1); d->dx[t] = (int8_t)(t % 3 - 1); }
 }
 
+static inline int resample_grid(long rows) { return (int)(rows < 148 * 8 ? (rows < 1 ? 1 : rows) : 148 * 8); }
+
 // (Re)build every tensor map / launch record for the given workspace + packed-weight addresses.
 static int bind(gsd_plan* p, void* ws, const void* packed) {
   if (p->bound_ws == ws && p->bound_packed == packed && !p->chunks.empty()) return 0;
@@ -419,6 +421,8 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
 
 static int check_prepost(const gsd_plan* p, const gsd_prepost* pp, const float* base) {
   GSD_CHECK(pp != nullptr, "gsd_forward: gsd_prepost is required");
+  GSD_CHECK(pp->raw_height < 65536 && pp->raw_width < 65536 && pp->out_height < 65536 && pp->out_width < 65536,
+            "gsd_forward: image sides must be < 65536 (32-bit resampling arithmetic)");
   GSD_CHECK(pp->raw_height >= p->g.height && pp->raw_width >= p->g.width,
             "gsd_forward: raw frames (%dx%d) smaller than the network input (%dx%d) are not supported", pp->raw_height,
             pp->raw_width, p->g.height, p->g.width);
@@ -487,7 +491,7 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const 
     GSD_CUDA(cudaGetLastError());
     if (resample) {
       const long opix = (long)pp->out_height * pp->out_width;
-      area_resample_kernel<<<ew_grid(opix * ch.nb * g.n_classes), 256, 0, st>>>(
+      area_resample_kernel<<<resample_grid((long)ch.nb * g.n_classes * pp->out_height), 256, 0, st>>>(
           head_out, ch.nb * g.n_classes, g.height, g.width, pp->out_height, pp->out_width,
           y + (size_t)ch.b0 * g.n_classes * opix);
       GSD_CUDA(cudaGetLastError());
@@ -526,7 +530,7 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const 
   }
   if (resample) {
     const long opix = (long)pp->out_height * pp->out_width;
-    area_resample_kernel<<<ew_grid(opix * ch.nb * g.n_classes), 256, 0, st>>>(
+    area_resample_kernel<<<resample_grid((long)ch.nb * g.n_classes * pp->out_height), 256, 0, st>>>(
         head_out, ch.nb * g.n_classes, g.height, g.width, pp->out_height, pp->out_width,
         y + (size_t)ch.b0 * g.n_classes * opix);
     GSD_CUDA(cudaGetLastError());
