@@ -233,6 +233,14 @@ def bench_train(torch, dist, dev, rank, world, batch, steps):
                     "whole step replayed as one CUDA graph"}
 
 
+def workload_config(batch):
+    """the same `config` on both arms (b200 / reference): BASELINE.json configs[1]"""
+    return {"workload": "configs[1]: UNet(6,2) inference, batch %d frame pairs of 6x320x427 per GPU, difference image + "
+                        "normalisation + depth de-normalisation inside the timed call" % batch,
+            "geometry": "G2", "batch_per_gpu": batch,
+            "l2": "inputs_larger_than_l2 (210 MB frames, 22 GB activations per step at batch 64)", "weights": "random init seed 0"}
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -264,8 +272,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "unet_frames_per_s_6x320x427", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: UNet(6,2) inference 6x320x427, batch 64 per GPU (reference arm: 1-frame sample per step)",
-                       "geometry": "G2"},
+            "config": workload_config(args.batch),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
@@ -512,10 +519,7 @@ def main():
     line = {"metric": "unet_frames_per_s_6x320x427", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: UNet(6,2) inference bf16, batch 64 frames of 6x320x427 per GPU, "
-                                   "difference image + normalisation + depth de-normalisation fused",
-                       "geometry": "G2", "batch_per_gpu": B, "l2": "inputs_larger_than_l2 (210 MB frames, 22 GB activations per step)",
-                       "weights": "random init seed 0"},
+            "config": workload_config(B),
             "tensor_frac_whole_step": value / world * GFLOP_PER_FRAME / 1e3 / sustained,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * CIN * H * W * 4,
