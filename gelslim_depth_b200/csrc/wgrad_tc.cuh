@@ -301,7 +301,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pw_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    // ONE N = 256 UMMA per K step: the four stride-2 views of dU are four 64-column MN blocks exactly one 16 KB tile
+    // apart (= the descriptor's leading-byte-offset), so A is read once for all four (dy,dx) groups
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
     int st = 0; uint32_t ph = 0;
     bool first = true;
     for (int t = s; t < m_tiles; t += p.split) {
@@ -310,13 +312,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pw_kernel(const __grid_co
       const uint32_t sa = s_stage + st * kWpStageBytes;
       if (elect_one()) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t a_lo = mn_desc_lo(sa + k * 2048, kWgDzBytes);
-            const uint32_t b_lo = mn_desc_lo(sa + (2 + g) * kWgDzBytes + k * 2048, 0);
-            umma_bf16_lohi(tmem_base + g * 64, a_lo, mn_desc_hi(1024), b_lo, mn_desc_hi(1024), idesc, (first && k == 0) ? 0u : 1u);
-          }
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a_lo = mn_desc_lo(sa + k * 2048, kWgDzBytes);
+          const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + k * 2048, kWgDzBytes);
+          umma_bf16_lohi(tmem_base, a_lo, mn_desc_hi(1024), b_lo, mn_desc_hi(1024), idesc, (first && k == 0) ? 0u : 1u);
         }
         umma_commit(bar_empty + 8 * st);
       }
