@@ -9,6 +9,7 @@ over pixels, BatchNorm statistics in the conv epilogue, everything else as fused
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List
 
 import torch
@@ -100,6 +101,22 @@ class StepEnv:
 
     def dwk(self, conv, cin_total):
         return None
+
+    # weight-gradient kernels may run on a side stream, concurrently with the memory-bound BatchNorm-backward passes of
+    # the next unit (see _ArenaEnv); the default runs everything on the current stream
+    def mark(self):
+        """token for 'everything launched so far on the current stream'"""
+        return None
+
+    def side(self, token):
+        """context manager: kernels launched inside run after `token`, possibly on another stream"""
+        return contextlib.nullcontext()
+
+    def keep(self, *tensors):
+        """tensors read by side-stream kernels must outlive the Python scope that created them"""
+
+    def join(self):
+        """the current stream waits for everything issued under side()"""
 
 
 _DEFAULT_ENV = StepEnv()
@@ -194,22 +211,31 @@ def _unit_backward(u: _Unit, da, pw: PackedTrainWeights, grads: "GradSink", need
                               sums=env.zeros(2 * Cn, da.device))
     grads.put(u.bn.bias, sums[:Cn])
     grads.put(u.bn.weight, sums[Cn:])
-    gw = grads.dest(u.conv.weight)
-    if u.first:
-        ops.wgrad_first(u.src0, dz, u.conv.in_channels, gw, dwk=env.dwk(u.conv, 16))
-    else:
-        ops.wgrad3x3(u.src0, dz, gw, x1=u.src1, off=u.off, dwk=env.dwk(u.conv, u.conv.in_channels))
-    grads.done(u.conv.weight)
-    if not need_dx:
-        return None
-    wd = pw.dgrad[id(u.conv)]                                   # [ci][9][co]
-    cin = u.conv.in_channels
-    if split:
-        rows = split * 9 * Cn
-        dskip = ops.conv(dz, wd[:rows], split, 9)
-        dup = ops.conv(dz, wd[rows:], cin - split, 9)
-        return dskip, dup
-    return ops.conv(dz, wd, cin, 9)
+
+    def weight_grad():
+        gw = grads.dest(u.conv.weight)
+        if u.first:
+            ops.wgrad_first(u.src0, dz, u.conv.in_channels, gw, dwk=env.dwk(u.conv, 16))
+        else:
+            ops.wgrad3x3(u.src0, dz, gw, x1=u.src1, off=u.off, dwk=env.dwk(u.conv, u.conv.in_channels))
+        grads.done(u.conv.weight)
+
+    # wgrad depends only on dz: it is issued (possibly on a side stream) AFTER the dgrad launch, so that dgrad -- which the
+    # critical path waits for -- gets the SMs first, and wgrad then overlaps the next unit's HBM-bound BatchNorm passes
+    token = env.mark()
+    out = None
+    if need_dx:
+        wd = pw.dgrad[id(u.conv)]                               # [ci][9][co]
+        cin = u.conv.in_channels
+        if split:
+            rows = split * 9 * Cn
+            out = (ops.conv(dz, wd[:rows], split, 9), ops.conv(dz, wd[rows:], cin - split, 9))
+        else:
+            out = ops.conv(dz, wd, cin, 9)
+    with env.side(token):
+        weight_grad()
+    env.keep(dz)
+    return out
 
 
 def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "GradSink" = None,
@@ -252,11 +278,15 @@ def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "G
             dup[:, off[0] + 2 * hs:] = 0
             dup[:, :, : off[1]] = 0
             dup[:, :, off[1] + 2 * ws:] = 0
-        grads.put(up.bias, ops.channel_sum(dup, sums=env.zeros(2 * dup.shape[-1], dev)))
-        gw = grads.dest(up.weight)
-        ops.convt_wgrad(y_prev, dup, off, gw)
-        grads.done(up.weight)
+        token = env.mark()
         da = ops.convt_dgrad(dup, off, pw.dgrad[id(up)], up.in_channels, hs, ws)
+        sums_up = env.zeros(2 * dup.shape[-1], dev)
+        with env.side(token):
+            grads.put(up.bias, ops.channel_sum(dup, sums=sums_up))
+            gw = grads.dest(up.weight)
+            ops.convt_wgrad(y_prev, dup, off, gw)
+            grads.done(up.weight)
+        env.keep(dup)
     # ---- encoder, bottom up: `da` is now the gradient of enc[depth]'s output
     for l in range(depth, -1, -1):
         u1, u2 = ctx["enc"][l]
@@ -264,6 +294,7 @@ def train_backward(net, ctx, dy: torch.Tensor, pw: PackedTrainWeights, grads: "G
             da = ops.maxpool_bwd(u2.a, dpool, dskips[l])      # noqa: F821  (dpool from level l+1) + skip-connection gradient
         da1 = _unit_backward(u2, da, pw, grads, need_dx=True, env=env)
         dpool = _unit_backward(u1, da1, pw, grads, need_dx=(l > 0), env=env)
+    env.join()
     return [grads.grads[p] for p in net.parameters()] if own else None
 
 
@@ -298,7 +329,7 @@ class _ArenaEnv(StepEnv):
     one arena cleared by a single memset, and the weight-gradient accumulators persist (the unpack kernel re-zeroes
     them)."""
 
-    def __init__(self, net):
+    def __init__(self, net, overlap_wgrad=True):
         bns = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d)]
         dev = bns[0].running_mean.device
         total = sum(m.num_features for m in bns)
@@ -315,11 +346,40 @@ class _ArenaEnv(StepEnv):
         self.arena = torch.zeros(1 << 18, dtype=torch.float32, device=dev)
         self.cursor = 0
         self._dwk = {}
+        self.side_stream = torch.cuda.Stream(device=dev) if overlap_wgrad else None
+        self._kept, self._forked = [], False
 
     def begin_step(self):
+        self._kept = []                   # the previous step's side-stream work was joined in train_backward
         self.arena.zero_()
         self.cursor = 0
         ops.negate(self.flat_rm, out=self.flat_neg)
+
+    def mark(self):
+        if self.side_stream is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    @contextlib.contextmanager
+    def side(self, token):
+        if self.side_stream is None:
+            yield
+            return
+        self.side_stream.wait_event(token)
+        self._forked = True
+        with torch.cuda.stream(self.side_stream):
+            yield
+
+    def keep(self, *tensors):
+        if self.side_stream is not None:
+            self._kept.extend(tensors)
+
+    def join(self):
+        if self._forked:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+            self._forked = False
 
     def zeros(self, n, dev):
         n4 = (n + 3) // 4 * 4
@@ -373,7 +433,7 @@ class FusedTrainer:
     (per-replica BatchNorm statistics, like stock DistributedDataParallel)."""
 
     def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, ema_decay=0.995, process_group=None,
-                 bucket_bytes=25 << 20, distributed=None, use_graph=False):
+                 bucket_bytes=25 << 20, distributed=None, use_graph=False, overlap_wgrad=True):
         self.net = net
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         params = list(net.parameters())
@@ -403,7 +463,10 @@ class FusedTrainer:
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.buckets, self.bucket_of = plan_buckets([(p, *self.index[p]) for p in params], bucket_bytes)
         self.pw = PackedTrainWeights(net)                          # after aliasing: the table holds arena pointers
-        self.env = _ArenaEnv(net)
+        # overlap_wgrad: weight-gradient GEMMs (tensor-bound) run on a side stream concurrently with the next unit's
+        # BatchNorm-backward passes (HBM-bound)
+        import os
+        self.env = _ArenaEnv(net, overlap_wgrad=overlap_wgrad and not os.environ.get("GSD_NO_WGRAD_OVERLAP"))
 
     def average_parameters(self):
         """`with trainer.average_parameters():` == torch_ema's context manager (train_unet.py:389,428,480): the EMA
