@@ -86,7 +86,6 @@ SYMBOLS = {
     "gsd_op_head_bn_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_double] + [C.c_int] * 4 + [C.c_void_p] * 5),
     "gsd_op_pack_weights_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "gsd_pack_item_units": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
-    "gsd_op_wgrad_first": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsd_op_adam_ema": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_longlong, C.c_float, C.c_longlong, C.c_float, C.c_void_p]),
     "gsd_op_image_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p,

@@ -289,17 +289,6 @@ extern "C" int gsd_op_pack_weights_batched(const gsd_pack_item* items_dev, int n
   return 0;
 }
 
-// first conv (K = 27/54): dw[64][9][16] += ...   (x16: NHWC bf16 padded to 16 channels, dz: (B,H,W,64))
-extern "C" int gsd_op_wgrad_first(const void* x16, const void* dz, int B, int H, int W, int Cin, float* dw, void* stream) {
-  GSD_CHECK(x16 && dz && dw && Cin >= 1 && Cin <= 8, "gsd_op_wgrad_first: bad argument");
-  long rows = (long)B * H;
-  int grid = (int)(rows < 148 * 4 ? rows : 148 * 4);
-  wgrad_first_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x16),
-                                                                         static_cast<const __nv_bfloat16*>(dz), B, H, W, Cin, dw);
-  GSD_CUDA(cudaGetLastError());
-  return 0;
-}
-
 // Adam (coupled L2) + EMA over a flat fp32 arena of n elements; step is 1-based; shadow may be NULL (no EMA).
 // grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
 // Graph-replayable variant: `counter` = 2 device int64 (Adam steps and EMA updates done so far); the kernel derives

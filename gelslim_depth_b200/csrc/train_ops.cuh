@@ -598,51 +598,6 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackIte
   }
 }
 
-// First-layer weight gradient (K = 27/54): dw[co][tap][c] += sum_pix dz[pix][co] * x16[pix+tap][c], c < Cin <= 8.
-// 256 threads = 64 output channels x 4 pixel lanes; a block walks image rows (no per-pixel divisions); every thread
-// keeps its 9 x 8 partial sums in registers; one smem + one global reduction per block.
-__global__ void __launch_bounds__(256) wgrad_first_kernel(const __nv_bfloat16* __restrict__ x16, const __nv_bfloat16* __restrict__ dz,
-                                                          int B, int H, int W, int Cin, float* __restrict__ dw /*[64][9][16]*/) {
-  const int co = threadIdx.x & 63, sub = threadIdx.x >> 6;
-  float acc[9][8];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
-  const long rows = (long)B * H;
-  for (long r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int y = (int)(r % H);
-    const __nv_bfloat16* xrow = x16 + r * W * 16;
-    const __nv_bfloat16* drow = dz + r * W * 64;
-    for (int x = sub; x < W; x += 4) {
-      const float d = __bfloat162float(drow[x * 64 + co]);
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int dy = t / 3 - 1, dx = t % 3 - 1;
-        const int ys = y + dy, xs = x + dx;
-        if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
-          float xv[8];
-          unpack8(*reinterpret_cast<const uint4*>(xrow + ((long)dy * W + xs) * 16), xv);   // channels 0..7 (warp-uniform address)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[t][c] = fmaf(d, xv[c], acc[t][c]);
-        }
-      }
-    }
-  }
-  __shared__ float sh[64 * 9 * 8];
-  for (int i = threadIdx.x; i < 64 * 72; i += 256) sh[i] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) atomicAdd(&sh[(co * 9 + t) * 8 + c], acc[t][c]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 72; i += 256) {
-    const int c = i & 7, ct = i >> 3;
-    if (c < Cin) atomicAdd(dw + (long)ct * 16 + c, sh[i]);
-  }
-}
-
 // Adam with coupled L2 (torch.optim.Adam(lr, betas, eps, weight_decay), train_unet.py:306,375) fused with the
 // torch_ema==0.3 shadow update (train_unet.py:309,376), over one flat fp32 arena:
 //   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)

@@ -238,8 +238,6 @@ int gsd_op_pack_weights_batched(const gsd_pack_item* items_dev, int n_items, lon
 /* wgrad arena [O][9][Ipad] fp32 -> Conv2d.weight.grad layout (O,I,3,3); clear != 0: the arena is zeroed as it is
  * read, ready for the next step's accumulation */
 int gsd_op_unpack_wgrad(float* dwk, int O, int I, int Ipad, float* grad, int clear, void* stream);
-/* weight gradient of the first conv (K = 27/54), dw [64][9][16] fp32 accumulated */
-int gsd_op_wgrad_first(const void* x16, const void* dz, int B, int H, int W, int Cin, float* dw, void* stream);
 /* torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2 (train_unet.py:306,375) fused with the
  * torch_ema==0.3 update (train_unet.py:309,376) over one flat fp32 arena; `step` is 1-based, shadow may be NULL */
 int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, float* shadow, long long n, float lr, float beta1,
