@@ -253,14 +253,29 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     const long mtl = (long)((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
     bn = 128; mt = 2; wres = 0;
     if (((mtl + 1) / 2) * (d.Cout / 128) < num_sms) mt = 1;
-    if (mt == 1 && mtl * (d.Cout / 128) < num_sms) bn = 64;
+    bool small = false;
+    if (mt == 1) {
+      // small batches: pick N by the makespan of the grid, waves x measured cycles per UMMA (~62 for N = 64, ~98 for
+      // N = 128, ~170 for N = 256): a smaller N means more work items, worth it only while they fit the same waves
+      small = true;
+      const int ns[3] = {64, 128, 256};
+      const long cyc[3] = {62, 98, 170};
+      long best = -1;
+      for (int i = 0; i < 3; ++i) {
+        if (d.Cout % ns[i]) continue;
+        const long items_i = mtl * (d.Cout / ns[i]);
+        const long t = ((items_i + num_sms - 1) / num_sms) * cyc[i];
+        if (best < 0 || t < best) { best = t; bn = ns[i]; }
+      }
+    }
     // N = 256 (one tile, M = 128): one UMMA reads A (32 smem wavefronts) for 256 output channels -- 96 wavefronts per
     // 128 tensor cycles instead of 64 per 64, which leaves the smem pipe room for the epilogue.  Measured on B200
     // (tools/exp_bn256.py, batch 64): +7..10 % for 256->512, 512->256, 1024->512, +2 % for 512->512, no gain for
     // 256->256 and 128->256, hence the rule below.
     const bool big = (d.C0 + d.C1 >= 512) || d.Cout >= 512;
     const bool want256 = d.block_n == 256 || (d.block_n == 0 && big && !getenv("GSD_NO_BN256"));
-    if (want256 && d.Cout % 256 == 0 && mtl * (d.Cout / 256) >= num_sms) { bn = 256; mt = 1; }
+    if (!small && want256 && d.Cout % 256 == 0 && mtl * (d.Cout / 256) >= num_sms) { bn = 256; mt = 1; }
+    if (d.block_n == 256 && d.Cout % 256 == 0) { bn = 256; mt = 1; }
   }
   GSD_CHECK(bkb == 128 || wres, "halo conv: first-layer path needs resident weights");
   const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
