@@ -9,7 +9,7 @@ unsupported configuration or a missing library raises.
 """
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import List
 
 import torch
 import torch.nn as nn

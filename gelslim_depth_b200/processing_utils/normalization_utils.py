@@ -7,8 +7,6 @@ from __future__ import annotations
 
 from typing import Sequence
 
-import torch
-
 from .image_utils import _affine
 
 

@@ -37,7 +37,6 @@ class PackedTrainWeights:
     kernel launch (gsd_op_pack_weights_batched) after each optimizer step."""
 
     def __init__(self, net):
-        import ctypes as C
         from .._lib import PackItem
         enc, dec = _blocks(net)
         self.fwd, self.dgrad = {}, {}

@@ -4,7 +4,6 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Citations relative to /root/
 """
 from __future__ import annotations
 
-import math
 from typing import Sequence, Tuple
 
 import torch

@@ -10,7 +10,7 @@ All ``file:line`` citations are relative to /root/reference/.
 from __future__ import annotations
 
 import hashlib
-from typing import Dict, List, Tuple
+from typing import Dict, List
 
 import torch
 import torch.nn.functional as F

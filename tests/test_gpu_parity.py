@@ -243,7 +243,6 @@ def test_processing_helpers_vs_golden(golden_processing):
 
 
 def test_forward_host_pipelined_matches_device_path():
-    import ctypes as C
     from gelslim_depth_b200.models.unet import UNet
     from gelslim_depth_b200.engine import make_prepost
     torch.manual_seed(2)

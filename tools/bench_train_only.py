@@ -1,5 +1,5 @@
 """Training step only (BASELINE configs[3]) with more timed steps than bench.py's default: python tools/bench_train_only.py [steps] [batch]"""
-import os, sys, json, types
+import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench

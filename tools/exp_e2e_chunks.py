@@ -1,4 +1,4 @@
-import os, sys, time
+import sys, time
 sys.path.insert(0, "/root/repo")
 import torch
 from gelslim_depth_b200.models.unet import UNet

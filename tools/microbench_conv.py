@@ -1,5 +1,5 @@
 """Time single tcgen05 conv launches (tuning aid).  python tools/microbench_conv.py cin cout H W B [bn] [pool]"""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gelslim_depth_b200.engine import conv_op
