@@ -208,6 +208,20 @@ inline double halo_tile_efficiency(int H, int W) {
   return (double)H * W / ((double)((H + 15) / 16) * 16 * ((W + 7) / 8) * 8);
 }
 
+inline bool halo_supported(const ConvDesc& d);
+
+// Halo-resident kernel or tap-streaming kernel?  The fixed 16x8 tiling of the halo kernel wastes MMA rows on small
+// images (51 % useful at 20x26 or 10x13), so large batches use the tap-streaming kernel there (free choice of tile
+// shape).  When the whole layer is a single wave of CTAs anyway (batch 1-2: latency, not throughput), each CTA's time is
+// set by the L2->SM fabric, and the halo kernel moves 2.3x fewer bytes per UMMA (one halo box per 9 taps): measured
+// 41 -> 20 us for the 1024-channel bottleneck conv at batch 1.
+inline bool prefer_halo(const ConvDesc& d, int num_sms) {
+  if (getenv("GSD_NO_HALO") || !halo_supported(d)) return false;
+  const long mtl = (long)((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
+  const bool single_wave = d.Cout >= 128 && mtl * (d.Cout / 128) <= num_sms;
+  return (double)d.H * d.W / ((double)((d.H + 15) / 16) * 16 * ((d.W + 7) / 8) * 8) >= 0.75 || single_wave;
+}
+
 inline bool halo_supported(const ConvDesc& d) {
   if (d.ntaps != 9 || d.groups != 1) return false;
   const bool first = (d.C0 == 16 && d.C1 == 0 && d.Cout == 64);

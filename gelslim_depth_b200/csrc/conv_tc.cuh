@@ -152,10 +152,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         fdivmod(mt, p.fd_tx, trow, tx);
         fdivmod(trow, p.fd_ty, b, ty);
         const int x0 = tx * p.tw, y0 = ty * p.th;
-        int kidx = 0;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const int xs = x0 + p.tap_dx[t], ys = y0 + p.tap_dy[t];
-          for (int cb = 0; cb < kb_per_tap; ++cb, ++kidx) {
+        // K order = (channel block, tap), the same as the halo-resident kernel: a layer's result does not depend on
+        // which of the two kernels the batch size selected (bit-identical accumulation order)
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          for (int t = 0; t < p.ntaps; ++t) {
+            const int xs = x0 + p.tap_dx[t], ys = y0 + p.tap_dy[t];
+            const int kidx = t * kb_per_tap + cb;
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const uint32_t sa = s_stage + stage * Cfg::STAGE_BYTES;
             const uint32_t sb = sa + Cfg::A_BYTES;

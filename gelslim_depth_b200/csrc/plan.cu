@@ -305,8 +305,8 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       return static_cast<void*>(W + off + (size_t)b0 * l_h * l_w * c * es);
     };
     auto use_halo = [&](const ConvDesc& d) {
-      // halo-resident kernel wherever its fixed 16x8 tiling wastes < 25 % of the MMA rows
-      return !getenv("GSD_NO_HALO") && halo_supported(d) && halo_tile_efficiency(d.H, d.W) >= 0.75;
+      // halo-resident kernel wherever its fixed 16x8 tiling wastes < 25 % of the MMA rows, or the layer is one wave anyway
+      return prefer_halo(d, p->num_sms);
     };
     auto add = [&](ConvDesc& d) -> int {
       if (g.dtype == GSD_DTYPE_FP32) {

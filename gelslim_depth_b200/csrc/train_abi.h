@@ -32,7 +32,7 @@ extern "C" int gsd_op_conv_auto_bf16(const void* src0, int C0, const void* src1,
   else { GSD_CHECK(ntaps == 1, "gsd_op_conv_auto_bf16: ntaps must be 9 or 1"); d.ntaps = 1; }
   d.scale = scale; d.shift = shift; d.relu = relu; d.out = out; d.pooled = pooled; d.stats = stats;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!getenv("GSD_NO_HALO") && halo_supported(d) && halo_tile_efficiency(H, W) >= 0.75) {
+  if (prefer_halo(d, num_sms_of(device))) {
     HaloLaunch L;
     GSD_TRY(build_halo_launch(d, num_sms_of(device), &L));
     return run_halo_launch(L, st);
