@@ -245,10 +245,15 @@ extern "C" int gsd_op_bn_bwd_apply(const void* da, const float* scale, const flo
 extern "C" int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* dskip, int B, int H, int W, int C, void* dfull,
                                   void* stream) {
   GSD_CHECK(a && dpool && dfull && C % 8 == 0, "gsd_op_maxpool_bwd: bad argument");
-  const long total = (long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  maxpool_bwd_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int C8 = C / 8;
+  GSD_CHECK((C8 & (C8 - 1)) == 0 && C8 <= 256, "gsd_op_maxpool_bwd: C/8 must be a power of two <= 256");
+  int c8_shift = 0;
+  while ((1 << c8_shift) < C8) ++c8_shift;
+  const long rows = (long)B * ((H + 1) / 2);
+  const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+  maxpool_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(dpool), static_cast<const __nv_bfloat16*>(dskip), C, B, H, W, C,
-      static_cast<__nv_bfloat16*>(dfull));
+      c8_shift, static_cast<__nv_bfloat16*>(dfull));
   GSD_CUDA(cudaGetLastError());
   return 0;
 }

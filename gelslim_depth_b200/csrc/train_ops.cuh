@@ -425,48 +425,54 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
 // argmax = FIRST maximum in row-major window order (PyTorch's tie rule).
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ dpool,
                                                           const __nv_bfloat16* __restrict__ dskip, long skip_stride, int B, int H,
-                                                          int W, int C, __nv_bfloat16* __restrict__ dfull) {
+                                                          int W, int C, int c8_shift, __nv_bfloat16* __restrict__ dfull) {
+  // a block walks (image, window-row) pairs; inside a row thread j owns window j >> c8_shift x chunk j & (C/8 - 1):
+  // shifts instead of 64-bit divisions, and the 4 + 1 (+ 4 skip) loads of a window are all in flight
   const int Hw = (H + 1) / 2, Ww = (W + 1) / 2, Hp = H / 2, Wp = W / 2, C8 = C / 8;
-  const long total = (long)B * Hw * Ww * C8;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % C8);
-    const int wx = (int)((idx / C8) % Ww);
-    const int wy = (int)((idx / ((long)C8 * Ww)) % Hw);
-    const long b = idx / ((long)C8 * Ww * Hw);
-    const bool inwin = wy < Hp && wx < Wp;
-    float av[4][8], dp[8];
-    int arg[8];
+  const int c8 = threadIdx.x & (C8 - 1);
+  const int per_row = Ww << c8_shift;
+  const long rows = (long)B * Hw;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / Hw), wy = (int)(row - (long)b * Hw);
+    for (int j = threadIdx.x; j < per_row; j += 256) {
+      const int wx = j >> c8_shift;
+      const bool inwin = wy < Hp && wx < Wp;
+      float av[4][8], dp[8], sk[4][8];
+      int arg[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { arg[j] = 0; dp[j] = 0.f; }
-    if (inwin) {
-      unpack8(*reinterpret_cast<const uint4*>(dpool + ((b * Hp + wy) * Wp + wx) * C + c8 * 8), dp);
+      for (int i = 0; i < 8; ++i) { arg[i] = 0; dp[i] = 0.f; }
+      uint4 ua[4], us[4], ud = make_uint4(0, 0, 0, 0);
+      bool live[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        unpack8(*reinterpret_cast<const uint4*>(a + ((b * H + 2 * wy + (q >> 1)) * W + 2 * wx + (q & 1)) * C + c8 * 8), av[q]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float m = av[0][j];
-#pragma unroll
-        for (int q = 1; q < 4; ++q)
-          if (av[q][j] > m) { m = av[q][j]; arg[j] = q; }
+      for (int q = 0; q < 4; ++q) {
+        const int y = 2 * wy + (q >> 1), x = 2 * wx + (q & 1);
+        live[q] = y < H && x < W;
+        const size_t pix = ((size_t)b * H + y) * W + x;
+        ua[q] = (inwin) ? *reinterpret_cast<const uint4*>(a + pix * C + c8 * 8) : make_uint4(0, 0, 0, 0);
+        us[q] = (live[q] && dskip) ? *reinterpret_cast<const uint4*>(dskip + pix * skip_stride + c8 * 8) : make_uint4(0, 0, 0, 0);
       }
-    }
+      if (inwin) ud = *reinterpret_cast<const uint4*>(dpool + (((size_t)b * Hp + wy) * Wp + wx) * C + c8 * 8);
+      if (inwin) {
+        unpack8(ud, dp);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int y = 2 * wy + (q >> 1), x = 2 * wx + (q & 1);
-      if (y < H && x < W) {
-        const long pix = (b * H + y) * W + x;
+        for (int q = 0; q < 4; ++q) unpack8(ua[q], av[q]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float m = av[0][i];
+#pragma unroll
+          for (int q = 1; q < 4; ++q)
+            if (av[q][i] > m) { m = av[q][i]; arg[i] = q; }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!live[q]) continue;
+        const int y = 2 * wy + (q >> 1), x = 2 * wx + (q & 1);
+        const size_t pix = ((size_t)b * H + y) * W + x;
+        unpack8(us[q], sk[q]);
         float o[8];
-        if (dskip) unpack8(*reinterpret_cast<const uint4*>(dskip + pix * skip_stride + c8 * 8), o);
-        else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = 0.f;
-        }
-        if (inwin) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (arg[j] == q) o[j] += dp[j];
-        }
+        for (int i = 0; i < 8; ++i) o[i] = sk[q][i] + ((inwin && arg[i] == q) ? dp[i] : 0.f);
         *reinterpret_cast<uint4*>(dfull + pix * C + c8 * 8) = pack8(o);
       }
     }
