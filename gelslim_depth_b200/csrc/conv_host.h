@@ -167,14 +167,28 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
   return 0;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember, per device of this
+// process, the largest value already set (a process normally drives one GPU, but nothing here depends on it).
+struct SmemAttrCache {
+  int set[64] = {0};
+  template <typename K>
+  int ensure(K kernel, int smem) {
+    int dev = 0;
+    GSD_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (set[dev] < smem) {
+      GSD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      set[dev] = smem;
+    }
+    return 0;
+  }
+};
+
 template <int BN, int BKB>
 inline int launch_conv_cfg(const ConvLaunch& L, cudaStream_t st) {
   using Cfg = ConvCfg<BN, BKB>;
-  static bool attr_set = false;   // per process; one device family
-  if (!attr_set) {
-    GSD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemAttrCache attr_cache;
+  GSD_TRY(attr_cache.ensure(conv_tc_kernel<BN, BKB>, Cfg::SMEM_BYTES));
   return launch_maybe_pdl(conv_tc_kernel<BN, BKB>, L.p, L.grid, kConvThreads, Cfg::SMEM_BYTES, st, L.pdl);
 }
 
@@ -340,11 +354,8 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
 
 template <int BN, int MT, bool WRES, int BKB, int NEPI>
 inline int launch_halo_cfg(const HaloLaunch& L, cudaStream_t st) {
-  static int attr_smem = 0;
-  if (attr_smem < L.smem) {
-    GSD_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, WRES, BKB, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
-    attr_smem = L.smem;
-  }
+  static SmemAttrCache attr_cache;
+  GSD_TRY(attr_cache.ensure(conv_halo_kernel<BN, MT, WRES, BKB, NEPI>, L.smem));
   return launch_maybe_pdl(conv_halo_kernel<BN, MT, WRES, BKB, NEPI>, L.p, L.grid, 64 + 32 * NEPI, L.smem, st, L.pdl);
 }
 
@@ -486,11 +497,8 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
 
 template <int XB>
 inline int launch_wgrad_cfg(const WgradLaunch& L, cudaStream_t st) {
-  static int attr = 0;
-  if (attr < L.smem) {
-    GSD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
-    attr = L.smem;
-  }
+  static SmemAttrCache attr_cache;
+  GSD_TRY(attr_cache.ensure(wgrad_tc_kernel<XB>, L.smem));
   wgrad_tc_kernel<XB><<<L.grid, kWgThreads, L.smem, st>>>(L.p);
   GSD_CUDA(cudaGetLastError());
   return 0;
@@ -544,11 +552,8 @@ inline int build_wgrad_pw_launch(const void* in, int Cin, const void* du, int Co
 }
 
 inline int run_wgrad_pw_launch(const WgradPwLaunch& L, cudaStream_t st) {
-  static int attr = 0;
-  if (attr < L.smem) {
-    GSD_CUDA(cudaFuncSetAttribute(wgrad_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
-    attr = L.smem;
-  }
+  static SmemAttrCache attr_cache;
+  GSD_TRY(attr_cache.ensure(wgrad_pw_kernel, L.smem));
   wgrad_pw_kernel<<<L.grid, kWgThreads, L.smem, st>>>(L.p);
   GSD_CUDA(cudaGetLastError());
   return 0;
