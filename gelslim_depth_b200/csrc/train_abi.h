@@ -201,7 +201,7 @@ static int reduce_grid(int C, long npix, int* grid, int* block) {
   const int C8 = C / 8;
   *block = 256;
   // total threads must be a multiple of C8 so that a thread always sees the same channel chunk
-  long want = 148L * 4 * 256;
+  long want = 148L * 2 * 256;      // 124 registers -> 2 resident blocks per SM: exactly one wave (measured best of 2..8)
   long threads = (want / C8) * C8;
   if (threads < C8) threads = C8;
   // keep it a multiple of 256 as well: lcm(C8, 256); C8 is a power of two times {1} for C in {64..1024}
