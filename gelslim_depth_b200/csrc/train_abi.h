@@ -109,7 +109,7 @@ extern "C" int gsd_op_bn_relu_apply(const void* z, const float* scale, const flo
   int c8_shift = 0;
   while ((1 << c8_shift) < C8) ++c8_shift;
   const long rows = (long)B * ((H + 1) / 2);
-  const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+  const int grid = (int)(rows < 148 * 24 ? rows : 148 * 24);     // ~one window row per block iteration: measured best of 3..32
   bn_relu_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C, c8_shift, static_cast<__nv_bfloat16*>(a),
       static_cast<__nv_bfloat16*>(pooled));
@@ -250,7 +250,7 @@ extern "C" int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* 
   int c8_shift = 0;
   while ((1 << c8_shift) < C8) ++c8_shift;
   const long rows = (long)B * ((H + 1) / 2);
-  const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+  const int grid = (int)(rows < 148 * 24 ? rows : 148 * 24);     // measured best of 3..32
   maxpool_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(dpool), static_cast<const __nv_bfloat16*>(dskip), C, B, H, W, C,
       c8_shift, static_cast<__nv_bfloat16*>(dfull));
