@@ -283,7 +283,7 @@ static void taps3x3(ConvDesc* d) {
   for (int t = 0; t < 9; ++t) { d->dy[t] = (int8_t)(t / 3 - 1); d->dx[t] = (int8_t)(t % 3 - 1); }
 }
 
-static inline int resample_grid(long rows) { return (int)(rows < 148 * 8 ? (rows < 1 ? 1 : rows) : 148 * 8); }
+static inline int resample_grid(long rows) { return (int)(rows < 148 * 24 ? (rows < 1 ? 1 : rows) : 148 * 24); }
 
 // (Re)build every tensor map / launch record for the given workspace + packed-weight addresses.
 static int bind(gsd_plan* p, void* ws, const void* packed) {
