@@ -452,3 +452,28 @@ def test_dataset_preprocessing_vs_reference_generaldataset():
     assert torch.allclose(blur_depth_images(d.to(dev()), 7).cpu(), oracle.blur_depth_images(d, 7), rtol=1e-5, atol=1e-6)
     with pytest.raises(RuntimeError):
         blur_depth_images(d.to(dev()), 4)            # even kernel sizes have no centre tap (the library rejects them)
+
+
+@pytest.mark.gpu
+def test_integration_md_ctypes_stub_runs_as_printed():
+    """INTEGRATION.md section B shows the binding a maintainer would add to the reference; the code block is executed
+    verbatim here (only the library path is made absolute) and checked against the oracle."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\nimport ctypes as C, torch\n(.*?)```", src, re.S).group(0)
+    code = block[len("```python\n"):-3].replace('C.CDLL("libgsd_b200.so")',
+                                                'C.CDLL(%r)' % os.path.join(root, "gelslim_depth_b200", "libgsd_b200.so"))
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    from gelslim_depth_b200.models.unet import UNet
+    torch.manual_seed(0)
+    net = UNet(6, 2)
+    sd = oracle.conditioned_state_dict(net.state_dict(), seed=5)
+    net.load_state_dict(sd)
+    net = net.to(dev()).eval()
+    x = torch.rand(2, 6, 48, 59, generator=torch.Generator().manual_seed(1))
+    y = ns["unet_forward_b200"](net, x.to(dev()))
+    torch.cuda.synchronize()
+    assert rel_l2(y, oracle.unet_forward(sd, x)) < 2e-2
