@@ -122,6 +122,24 @@ class DepthStream:
             s["done"].record(self.stream)
         return i
 
+    def acquire(self):
+        """Zero-copy ingest: -> (ticket, pinned input buffer of the next ring slot).  A camera driver writes the frame
+        straight into the buffer (shape / dtype of the configured layout), then calls submit(ticket)."""
+        i = self._next
+        s = self._slots[i]
+        self._next = (i + 1) % len(self._slots)
+        s["done"].synchronize()
+        return i, s["x_host"][0]
+
+    def submit(self, ticket: int) -> int:
+        """Launch the graph of a slot whose input buffer was filled in place (see acquire())."""
+        s = self._slots[ticket]
+        s["t_push"] = time.perf_counter()
+        with torch.cuda.stream(self.stream):
+            s["graph"].replay()
+            s["done"].record(self.stream)
+        return ticket
+
     def result(self, ticket: int) -> torch.Tensor:
         """Depth map(s) in mm for the frame pushed with `ticket`: (n_classes, H, W) for single-finger frames,
         (2, H, W) [Left, Right] for frame pairs.  A view of the slot's pinned buffer, valid until the slot is reused."""

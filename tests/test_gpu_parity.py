@@ -426,6 +426,10 @@ def test_depth_stream_ring_buffer_graph_replay(layout):
     assert len(stream.latencies_ms) == 6
     with pytest.raises(ValueError):
         stream.push(torch.zeros(3, 3, 3))
+    # zero-copy ingest: the producer writes into the pinned slot itself
+    ticket, buf = stream.acquire()
+    buf.copy_(frames[4])
+    assert torch.equal(stream.result(stream.submit(ticket)), want[4])
 
 
 @pytest.mark.gpu
