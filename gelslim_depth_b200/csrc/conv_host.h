@@ -456,7 +456,12 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   p.cb0 = C0 / nt; p.cb1 = C1 / nt;
   p.off_x = off_x; p.off_y = off_y;
   const bool half_m = !first && Cout == 64;          // two filter rows per UMMA through a one-row-shifted dZ half
-  p.tiles_x = (W + 7) / 8; p.tiles_y = (H + (half_m ? 1 : 0) + 15) / 16; p.batch = B;
+  // pixel tile 8 x 16 or 16 x 8: whichever wastes fewer UMMA rows on this image size (20x26: 51 % -> 68 % useful)
+  const int hs = H + (half_m ? 1 : 0);
+  const long pad8 = (long)((W + 7) / 8 * 8) * ((hs + 15) / 16 * 16), pad16 = (long)((W + 15) / 16 * 16) * ((hs + 7) / 8 * 8);
+  p.tw16 = (!first && pad16 * 21 < pad8 * 20 && !getenv("GSD_WG_NO_TW16")) ? 1 : 0;
+  const int TW = p.tw16 ? 16 : 8, TH = 128 / TW;
+  p.tiles_x = (W + TW - 1) / TW; p.tiles_y = (hs + TH - 1) / TH; p.batch = B;
   p.Cout = Cout; p.co_blocks = (Cout + 127) / 128;
   p.dw = dw;
   p.stages = 4;
@@ -478,13 +483,13 @@ inline int build_wgrad_launch(const void* x0, int C0, const void* x1, int C1, in
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-    uint32_t box[4] = {64, 8, half_m ? 17u : 16u, 1};
+    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)(TH + (half_m ? 1 : 0)), 1};
     GSD_TRY(encode_bf16_map(&p.tm_dz, const_cast<void*>(dz), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false));
   }
   auto src_map = [&](CUtensorMap* m, const void* base, int C, int h, int w) -> int {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
-    uint32_t box[4] = {(uint32_t)nt, 10, 18, 1};
+    uint32_t box[4] = {(uint32_t)nt, (uint32_t)(TW + 2), (uint32_t)(TH + 2), 1};
     return encode_bf16_map(m, const_cast<void*>(base), 4, dims, str, box,
                            first ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, false);
   };

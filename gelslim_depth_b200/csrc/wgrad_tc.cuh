@@ -48,6 +48,7 @@ struct WgradParams {
   int blocks;            // co_blocks * (cb0 + cb1)
   int stages;
   int flags;             // bit 0 (experiments only): skip the drain
+  int tw16;              // XB = 128: pixel tile is 16 wide x 8 tall instead of 8 x 16 (fewer padded rows on 20x26 / 40x53)
 };
 
 // MN-major, 128B-swizzled operand descriptor: LBO = distance between 64-element MN blocks, SBO = distance between
@@ -120,6 +121,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const bool half_m = (p.Cout - co_blk * 128) < 128;      // only 64 real co rows
   const bool shifted = half_m && XB == 128;                // ... used twice, one image row apart (see above)
 
+  // pixel tile: 8 wide x 16 tall, or 16 x 8 (p.tw16); either way 128 pixels = 16 K atoms of 8 consecutive pixels
+  const int TW = (XB == 128 && p.tw16) ? 16 : 8, TH = 128 / TW;
   if (warp == 0) {
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
@@ -127,17 +130,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
         mbar_wait(bar_empty + 8 * st, ph ^ 1);
         const uint32_t sa = s_stage + st * STAGE, fb = bar_full + 8 * st;
-        mbar_arrive_expect_tx(fb, (shifted ? kWgDzBytes + 1024 : half_m ? kWgDzBytes : 2 * kWgDzBytes) + HALO_BOX);
+        mbar_arrive_expect_tx(fb, (shifted ? kWgDzBytes + TW * 128 : half_m ? kWgDzBytes : 2 * kWgDzBytes) + HALO_BOX);
         if (shifted) {
-          tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * 8, ty * 16 - 1, b);        // 17-row box (host)
+          tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * TW, ty * TH - 1, b);       // (TH + 1)-row box (host)
         } else {
-          tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * 8, ty * 16, b);
-          if (!half_m) tma_load_4d(sa + kWgDzBytes, &p.tm_dz, fb, co_blk * 128 + 64, tx * 8, ty * 16, b);
+          tma_load_4d(sa, &p.tm_dz, fb, co_blk * 128, tx * TW, ty * TH, b);
+          if (!half_m) tma_load_4d(sa + kWgDzBytes, &p.tm_dz, fb, co_blk * 128 + 64, tx * TW, ty * TH, b);
         }
         if (ci_blk < p.cb0)
-          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x0, fb, ci_blk * NT, tx * 8 - 1, ty * 16 - 1, b);
+          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x0, fb, ci_blk * NT, tx * TW - 1, ty * TH - 1, b);
         else
-          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x1, fb, (ci_blk - p.cb0) * NT, tx * 8 - 1 - p.off_x, ty * 16 - 1 - p.off_y, b);
+          tma_load_4d(sa + 2 * kWgDzBytes, &p.tm_x1, fb, (ci_blk - p.cb0) * NT, tx * TW - 1 - p.off_x, ty * TH - 1 - p.off_y, b);
         if (++st == stages) { st = 0; ph ^= 1; }
       }
     }
@@ -154,17 +157,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       tc_fence_after();
       const uint32_t sa = s_stage + st * STAGE;
       // Cout == 64: second half = dZ one image row later (XB = 128) / the same 64 rows again (XB = 32)
-      const uint32_t a_lbo = shifted ? 1024u : half_m ? 0u : (uint32_t)kWgDzBytes;
+      const uint32_t a_lbo = shifted ? (uint32_t)(TW * 128) : half_m ? 0u : (uint32_t)kWgDzBytes;
       if (elect_one()) {
         if (XB == 128) {
+          // UMMA k covers pixels 16k..16k+15 of the tile = two 8-pixel K atoms: image rows 2k, 2k+1 of an 8-wide tile
+          // (atoms one halo row = 10 pixels apart) or the two halves of row k of a 16-wide tile (atoms 8 pixels apart)
+          const uint32_t b_hi_rt = p.tw16 ? mn_desc_hi(1024) : b_hi;
+          const int row_mul = p.tw16 ? 1 : 2, row_pitch = p.tw16 ? 18 : 10;
           for (int dyi = 0; dyi < ndy; ++dyi) {
             const uint32_t d_tmem = tmem_base + dyi * 192;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const uint32_t a_lo = mn_desc_lo(sa + k * 2048, a_lbo);
               // three MN blocks (dx = 0, 1, 2) one halo pixel = 128 bytes apart
-              const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((2 * k + dy0 + dyi) * 10) * 128, 128);
-              umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, b_hi, idesc3, (first && k == 0) ? 0u : 1u);
+              const uint32_t b_lo = mn_desc_lo(sa + 2 * kWgDzBytes + ((row_mul * k + dy0 + dyi) * row_pitch) * 128, 128);
+              umma_bf16_lohi(d_tmem, a_lo, mn_desc_hi(1024), b_lo, b_hi_rt, idesc3, (first && k == 0) ? 0u : 1u);
             }
           }
         } else {

@@ -346,7 +346,9 @@ def test_fp32_parity_mode_within_1e3_mm(golden_full):
 
 @pytest.mark.parametrize("cin,cin1,cout,h,w,b", [(64, 0, 64, 19, 23, 2), (64, 0, 128, 16, 8, 1), (128, 0, 256, 21, 27, 2),
                                                  (64, 64, 64, 20, 26, 2), (256, 0, 128, 10, 13, 3),
-                                                 (64, 0, 64, 32, 16, 1), (128, 0, 64, 16, 9, 2), (64, 0, 64, 1, 1, 1)])
+                                                 (64, 0, 64, 32, 16, 1), (128, 0, 64, 16, 9, 2), (64, 0, 64, 1, 1, 1),
+                                                 (128, 0, 256, 20, 26, 2), (64, 64, 128, 40, 53, 1), (64, 0, 64, 8, 16, 2),
+                                                 (128, 0, 64, 7, 30, 1)])   # the last four select the 16 x 8 pixel tile
 def test_wgrad3x3_tcgen05(cin, cin1, cout, h, w, b):
     """conv weight gradient = GEMM over pixels with MN-major operands (csrc/wgrad_tc.cuh) vs autograd."""
     from gelslim_depth_b200.engine import wgrad3x3_op
