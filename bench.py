@@ -482,7 +482,12 @@ def main():
         del x_dev, y_dev
         net._plans.clear()
         torch.cuda.empty_cache()
-        train = bench_train(torch, dist, dev, rank, world, args.train_batch, args.train_steps)
+        try:
+            train = bench_train(torch, dist, dev, rank, world, args.train_batch, args.train_steps)
+        except Exception as e:          # noqa: BLE001
+            if world > 1:               # the other ranks are inside collectives: fail loudly rather than hang them
+                raise
+            train = {"error": f"{type(e).__name__}: {e}"}
         net.eval()
 
     if rank != 0:
@@ -517,8 +522,15 @@ def main():
                 "conv_share_of_step": conv_ms / (conv_ms + other_ms),
                 "flops_per_launch_set": conv_flops, "algorithmic_gflop_per_frame": GFLOP_PER_FRAME}
 
-    latency = bench_latency(torch, net, dev, base)
-    g3 = bench_g3_pairs(torch, dev)
+    # secondary blocks: a failure there must not take the headline line down with it
+    try:
+        latency = bench_latency(torch, net, dev, base)
+    except Exception as e:          # noqa: BLE001
+        latency = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        g3 = bench_g3_pairs(torch, dev)
+    except Exception as e:          # noqa: BLE001
+        g3 = {"error": f"{type(e).__name__}: {e}"}
 
     cpu = None
     if not args.no_cpu_baseline:
