@@ -436,44 +436,72 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
 
     # ---------------- end to end through the C ABI with HOST buffers (e2e)
-    chunk = args.chunk or max(1, B // 4)      # 16-frame chunks measured best (profiles/r1_sweep_1gpu.jsonl)
-    ramp = max(1, chunk // 2) if not args.chunk else 0   # smaller first / last chunk: less exposed upload / download
-    plan.set_chunk(chunk, first=ramp, last=ramp)
-    for _ in range(2):
-        plan.forward_host(raw_h, base_dev, pp, y_host, x_dev, y_dev, packed)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 10))
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        plan.forward_host(raw_h, base_dev, pp, y_host, x_dev, y_dev, packed)   # blocks until y_host is complete
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)     # forward_host blocks until the last D2H landed, so the events bracket it all
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t)
-    e2e = world * B * e2e_steps / (e2e_ms / 1e3)
-    # the same with uint8 camera bytes as the host input (gsd_prepost.input_u8 = 1: 4x less host->device traffic)
     pp8 = make_prepost(CIN, (H, W), (H, W), use_diff=True, base_batch=1, in_scale=[1 / 255.0], in_shift=[0.0],
                        out_scale=1.9180814027786255 / -0.9, out_shift=-1.9180814027786255, input_u8=True)
     raw8_h = raw.to(torch.uint8).pin_memory()
-    x8_dev = torch.empty(raw8_h.shape, dtype=torch.uint8, device=dev)
-    for _ in range(2):
-        plan.forward_host(raw8_h, base_dev, pp8, y_host, x8_dev, y_dev, packed)
-    barrier()
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        plan.forward_host(raw8_h, base_dev, pp8, y_host, x8_dev, y_dev, packed)
-    e1.record(stream)
-    barrier()
-    e2e8_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([e2e8_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e8_ms = float(t)
-    e2e_u8 = world * B * e2e_steps / (e2e8_ms / 1e3)
-    del x8_dev
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def timed_ms(run):
+        """max over ranks of the device time of `run()` (which must leave every result in host memory)"""
+        barrier()
+        e0.record(stream)
+        run()
+        e1.record(stream)
+        barrier()
+        t_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([t_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t)
+        return t_ms
+
+    # (1) a stream of batches: gsd_forward_host_async on rotating staging slots -- the upload of step k+1 and the
+    #     download of step k-1 overlap the compute of step k; every step still moves its own frames host -> device
+    #     and its own depth maps device -> host, and the timed region ends when the last depth map is in host memory
+    n_slots = 2
+    plan.set_chunk(args.chunk or B)
+    y_hosts = [y_host] + [torch.empty(B, NCLS, H, W).pin_memory() for _ in range(n_slots - 1)]
+    y_devs = [y_dev] + [torch.empty_like(y_dev) for _ in range(n_slots - 1)]
+
+    def stream_of_batches(src_h, pre, x_devs):
+        def run():
+            for k in range(e2e_steps):
+                s = k % n_slots
+                plan.forward_host_async(src_h, base_dev, pre, y_hosts[s], x_devs[s], y_devs[s], packed, slot=s)
+            for s in range(n_slots):
+                plan.host_wait(s)
+        return run
+
+    x_devs = [x_dev] + [torch.empty_like(x_dev) for _ in range(n_slots - 1)]
+    run = stream_of_batches(raw_h, pp, x_devs)
+    run()
+    e2e = world * B * e2e_steps / (timed_ms(run) / 1e3)
+    del x_devs
+    x8_devs = [torch.empty(raw8_h.shape, dtype=torch.uint8, device=dev) for _ in range(n_slots)]
+    run = stream_of_batches(raw8_h, pp8, x8_devs)
+    run()
+    e2e_u8 = world * B * e2e_steps / (timed_ms(run) / 1e3)
+    del y_devs[1:], y_hosts[1:]
+
+    # (2) one blocking call per batch (gsd_forward_host): upload | compute | download pipelined chunk by chunk inside
+    #     the call, the first upload and the last download are exposed every step
+    chunk = args.chunk or max(1, B // 4)      # 16-frame chunks measured best (profiles/r1_sweep_1gpu.jsonl)
+    ramp = max(1, chunk // 2) if not args.chunk else 0   # smaller first / last chunk: less exposed upload / download
+    plan.set_chunk(chunk, first=ramp, last=ramp)
+
+    def blocking(src_h, pre, xd):
+        def run():
+            for _ in range(e2e_steps):
+                plan.forward_host(src_h, base_dev, pre, y_host, xd, y_dev, packed)   # returns when y_host is complete
+        return run
+
+    run = blocking(raw_h, pp, x_dev)
+    run()
+    e2e_blk = world * B * e2e_steps / (timed_ms(run) / 1e3)
+    run = blocking(raw8_h, pp8, x8_devs[0])
+    run()
+    e2e_blk_u8 = world * B * e2e_steps / (timed_ms(run) / 1e3)
+    del x8_devs
     plan.set_chunk(B)
 
     # ---------------- training step (BASELINE configs[3]): fwd + MSE + bwd + bucketed all-reduce + Adam + EMA
@@ -518,7 +546,11 @@ def main():
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (22 launches/step: 18 conv3x3 + 4 convT as implicit GEMM)",
                 "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
-                "frac_of_burst": achieved / burst, "traffic": traffic_from_profile(),
+                "frac_of_burst": achieved / burst,
+                "traffic": (traffic_from_profile() or {}).get("dram_bytes_per_step"),
+                "traffic_what": "dram__bytes_read.sum + dram__bytes_write.sum summed over the same 22 launches that "
+                                "`achieved` / flops_per_launch_set cover (one batch-64 forward), bytes",
+                "traffic_detail": traffic_from_profile(),
                 "conv_share_of_step": conv_ms / (conv_ms + other_ms),
                 "flops_per_launch_set": conv_flops, "algorithmic_gflop_per_frame": GFLOP_PER_FRAME}
 
@@ -544,11 +576,17 @@ def main():
             "tensor_frac_whole_step": value / world * GFLOP_PER_FRAME / 1e3 / sustained,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * CIN * H * W * 4,
-                    "d2h_bytes_per_step": B * NCLS * H * W * 4, "steps": e2e_steps, "chunk_frames": chunk,
-                    "first_last_chunk_frames": ramp,
+                    "d2h_bytes_per_step": B * NCLS * H * W * 4, "steps": e2e_steps,
+                    "api": "gsd_forward_host_async + gsd_forward_host_wait: a stream of batches on 2 rotating staging "
+                           "slots (pinned fp32 frames in, fp32 depth maps out; every step's upload and download are "
+                           "inside the timed region, which ends when the last depth map is in host memory)",
+                    "slots": n_slots,
                     "uint8_frames": {"value": e2e_u8, "h2d_bytes_per_step": B * CIN * H * W,
-                                     "what": "same call with uint8 camera bytes as the host input (gsd_prepost.input_u8)"},
-                    "api": "gsd_forward_host (pinned fp32 frames in, fp32 depth maps out, copies inside the timed region)"},
+                                     "what": "same with uint8 camera bytes as the host input (gsd_prepost.input_u8)"},
+                    "blocking_call": {"value": e2e_blk, "uint8_frames": e2e_blk_u8, "chunk_frames": chunk,
+                                      "first_last_chunk_frames": ramp,
+                                      "what": "one gsd_forward_host call per batch, each returning only when its depth "
+                                              "maps are in host memory (first upload / last download exposed)"}},
             "gpu_launches": plan.launches * args.steps, "clocks": clocks, "train": train, "latency": latency, "g3_pipeline": g3,
             "layers": table}
     emit(line)

@@ -54,6 +54,9 @@ SYMBOLS = {
                               C.c_void_p, C.c_void_p]),
     "gsd_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsd_forward_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "gsd_forward_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "gsd_forward_profiled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int,
                                        C.POINTER(C.c_int)]),

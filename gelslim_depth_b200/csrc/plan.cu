@@ -40,6 +40,8 @@ struct ChunkLaunches {
 
 }  // namespace
 
+constexpr int kHostSlots = GSD_MAX_HOST_SLOTS;
+
 struct gsd_plan {
   gsd_geometry g{};
   int device = 0, num_sms = 148;
@@ -63,6 +65,9 @@ struct gsd_plan {
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
   cudaEvent_t ev_start = nullptr;
+  // gsd_forward_host_async: per staging slot, "compute has consumed x_dev" and "y_host is complete"
+  cudaEvent_t ev_slot_compute[kHostSlots] = {}, ev_slot_out[kHostSlots] = {};
+  bool slot_used[kHostSlots] = {};
   double conv_flops = 0;
   int head_fused = 0;          // 1x1 head + de-normalisation folded into the last conv's epilogue
 };
@@ -183,6 +188,10 @@ extern "C" void gsd_plan_destroy(gsd_plan* p) {
   for (auto e : p->ev_in) cudaEventDestroy(e);
   for (auto e : p->ev_done) cudaEventDestroy(e);
   if (p->ev_start) cudaEventDestroy(p->ev_start);
+  for (int i = 0; i < kHostSlots; ++i) {
+    if (p->ev_slot_compute[i]) cudaEventDestroy(p->ev_slot_compute[i]);
+    if (p->ev_slot_out[i]) cudaEventDestroy(p->ev_slot_out[i]);
+  }
   if (p->copy_in) cudaStreamDestroy(p->copy_in);
   if (p->copy_out) cudaStreamDestroy(p->copy_out);
   delete p;
@@ -550,14 +559,12 @@ extern "C" int gsd_forward(gsd_plan* p, const void* x, const float* base, const 
   return 0;
 }
 
-extern "C" int gsd_forward_host(gsd_plan* p, const void* x_host, const float* base, const gsd_prepost* pp,
-                                float* y_host, void* x_dev, float* y_dev, void* workspace, const void* packed,
-                                void* stream) {
-  GSD_CHECK(p && x_host && y_host && x_dev && y_dev && workspace && packed, "gsd_forward_host: null argument");
-  GSD_TRY(check_prepost(p, pp, base));
-  GSD_CUDA(cudaSetDevice(p->device));
-  GSD_TRY(bind(p, workspace, packed));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// Enqueue upload | compute | download of one batch, chunk by chunk.  slot < 0: the blocking call (staging buffers
+// ordered after everything already queued on `st`).  slot >= 0: the caller rotates staging sets, so the upload of
+// call k+1 only waits for the compute that last read that slot's x_dev, and the compute only waits for the download
+// that last read that slot's y_dev: consecutive calls overlap (H2D(k+1) | compute(k) | D2H(k-1)).
+static int enqueue_host(gsd_plan* p, const void* x_host, const float* base, const gsd_prepost* pp, float* y_host,
+                        void* x_dev, float* y_dev, void* workspace, const void* packed, cudaStream_t st, int slot) {
   if (!p->copy_in) {
     GSD_CUDA(cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking));
     GSD_CUDA(cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking));
@@ -573,10 +580,15 @@ extern "C" int gsd_forward_host(gsd_plan* p, const void* x_host, const float* ba
   const gsd_geometry& g = p->g;
   const size_t raw_frame = (size_t)g.in_channels * pp->raw_height * pp->raw_width;
   const size_t out_frame = (size_t)g.n_classes * pp->out_height * pp->out_width;
-  // work already queued on the caller's stream (e.g. weight packing) precedes the first copy
-  GSD_CUDA(cudaEventRecord(p->ev_start, st));
-  GSD_CUDA(cudaStreamWaitEvent(p->copy_in, p->ev_start, 0));
-  GSD_CUDA(cudaStreamWaitEvent(p->copy_out, p->ev_start, 0));
+  if (slot >= 0 && p->slot_used[slot]) {
+    GSD_CUDA(cudaStreamWaitEvent(p->copy_in, p->ev_slot_compute[slot], 0));   // x_dev[slot] has been consumed
+    GSD_CUDA(cudaStreamWaitEvent(st, p->ev_slot_out[slot], 0));               // y_dev[slot] has been downloaded
+  } else {
+    // work already queued on the caller's stream (e.g. a gsd_forward reading x_dev) precedes the first copy
+    GSD_CUDA(cudaEventRecord(p->ev_start, st));
+    GSD_CUDA(cudaStreamWaitEvent(p->copy_in, p->ev_start, 0));
+    GSD_CUDA(cudaStreamWaitEvent(p->copy_out, p->ev_start, 0));
+  }
   for (size_t c = 0; c < p->chunks.size(); ++c) {
     const ChunkLaunches& ch = p->chunks[c];
     const size_t esz = pp->input_u8 ? 1 : 4;
@@ -591,8 +603,50 @@ extern "C" int gsd_forward_host(gsd_plan* p, const void* x_host, const float* ba
     GSD_CUDA(cudaMemcpyAsync(y_host + ch.b0 * out_frame, y_dev + ch.b0 * out_frame, ch.nb * out_frame * 4,
                              cudaMemcpyDeviceToHost, p->copy_out));
   }
+  if (slot >= 0) {
+    if (!p->ev_slot_compute[slot]) {
+      GSD_CUDA(cudaEventCreateWithFlags(&p->ev_slot_compute[slot], cudaEventDisableTiming));
+      GSD_CUDA(cudaEventCreateWithFlags(&p->ev_slot_out[slot], cudaEventDisableTiming));
+    }
+    GSD_CUDA(cudaEventRecord(p->ev_slot_compute[slot], st));
+    GSD_CUDA(cudaEventRecord(p->ev_slot_out[slot], p->copy_out));
+    p->slot_used[slot] = true;
+  }
+  return 0;
+}
+
+extern "C" int gsd_forward_host(gsd_plan* p, const void* x_host, const float* base, const gsd_prepost* pp,
+                                float* y_host, void* x_dev, float* y_dev, void* workspace, const void* packed,
+                                void* stream) {
+  GSD_CHECK(p && x_host && y_host && x_dev && y_dev && workspace && packed, "gsd_forward_host: null argument");
+  GSD_TRY(check_prepost(p, pp, base));
+  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_TRY(bind(p, workspace, packed));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GSD_TRY(enqueue_host(p, x_host, base, pp, y_host, x_dev, y_dev, workspace, packed, st, -1));
   GSD_CUDA(cudaStreamSynchronize(p->copy_out));
   GSD_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int gsd_forward_host_async(gsd_plan* p, const void* x_host, const float* base, const gsd_prepost* pp,
+                                      float* y_host, void* x_dev, float* y_dev, void* workspace, const void* packed,
+                                      void* stream, int slot) {
+  GSD_CHECK(p && x_host && y_host && x_dev && y_dev && workspace && packed, "gsd_forward_host_async: null argument");
+  GSD_CHECK(slot >= 0 && slot < kHostSlots, "gsd_forward_host_async: slot %d out of range [0, %d)", slot, kHostSlots);
+  GSD_TRY(check_prepost(p, pp, base));
+  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_TRY(bind(p, workspace, packed));
+  return enqueue_host(p, x_host, base, pp, y_host, x_dev, y_dev, workspace, packed, static_cast<cudaStream_t>(stream),
+                      slot);
+}
+
+extern "C" int gsd_forward_host_wait(gsd_plan* p, int slot) {
+  GSD_CHECK(p, "gsd_forward_host_wait: null plan");
+  GSD_CHECK(slot >= 0 && slot < kHostSlots, "gsd_forward_host_wait: slot %d out of range [0, %d)", slot, kHostSlots);
+  GSD_CHECK(p->slot_used[slot], "gsd_forward_host_wait: slot %d has no call in flight", slot);
+  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_CUDA(cudaEventSynchronize(p->ev_slot_out[slot]));
   return 0;
 }
 

@@ -101,6 +101,16 @@ class Plan:
                                    _ptr(y_dev), _ptr(self.workspace), _ptr(packed), _stream(self.device)),
               "gsd_forward_host")
 
+    def forward_host_async(self, x_host, base, pp, y_host, x_dev, y_dev, packed, slot: int):
+        """Enqueue upload | compute | download on staging set `slot` and return (gsd_forward_host_async); consecutive
+        calls on rotating slots overlap.  `host_wait(slot)` blocks until that slot's y_host is complete."""
+        check(lib.gsd_forward_host_async(self.handle, _ptr(x_host), _ptr(base), C.byref(pp), _ptr(y_host), _ptr(x_dev),
+                                         _ptr(y_dev), _ptr(self.workspace), _ptr(packed), _stream(self.device),
+                                         int(slot)), "gsd_forward_host_async")
+
+    def host_wait(self, slot: int):
+        check(lib.gsd_forward_host_wait(self.handle, int(slot)), "gsd_forward_host_wait")
+
     def __del__(self):
         try:
             if self.handle:

@@ -124,6 +124,20 @@ int gsd_forward_host(gsd_plan* p, const void* x_host, const float* base, const g
                      float* y_host, void* x_dev, float* y_dev, void* workspace, const void* packed,
                      void* stream);
 
+/* Non-blocking form for a stream of batches (the serving loop around predict_depth_from_RGB,
+ * test_depth_estimation.py:75-90, where batch k+1 is already waiting in host memory while batch k computes).
+ * The caller rotates up to GSD_MAX_HOST_SLOTS staging sets (x_dev, y_dev, y_host): the call only enqueues
+ * upload | compute | download and returns; the upload of the next call on another slot overlaps this call's
+ * compute, and this call's download overlaps the next compute.  Re-using a slot waits (on the device, not the
+ * host) until that slot's previous upload was consumed and its previous download finished.
+ * gsd_forward_host_wait blocks the host until y_host of the slot's latest call is complete.
+ * All calls of one plan must use the same `stream`; x_host must stay untouched until the wait returns. */
+#define GSD_MAX_HOST_SLOTS 4
+int gsd_forward_host_async(gsd_plan* p, const void* x_host, const float* base, const gsd_prepost* pp,
+                           float* y_host, void* x_dev, float* y_dev, void* workspace, const void* packed,
+                           void* stream, int slot);
+int gsd_forward_host_wait(gsd_plan* p, int slot);
+
 /* gsd_forward with CUDA events recorded between consecutive launches (synchronises `stream`):
  * ms_host[i] / flops_host[i] = device time and 2*M*N*K of launch i in network order (index 0 = input
  * prologue, 1..n-2 = conv / transposed-conv GEMMs, n-1 = 1x1 head [+ area resample]).  Measurement aid

@@ -267,6 +267,43 @@ def test_forward_host_pipelined_matches_device_path():
     assert torch.equal(yh, y_ref)
 
 
+def test_forward_host_async_rotating_slots_match_device_path():
+    """gsd_forward_host_async: six different batches through two rotating staging slots (each slot re-used three
+    times without a host wait in between for the first four) land the same bytes as the blocking device path."""
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.engine import make_prepost
+    torch.manual_seed(2)
+    net = UNet(6, 2)
+    net.load_state_dict(oracle.conditioned_state_dict(net.state_dict(), seed=1))
+    net = net.to(dev()).eval()
+    nb, B = 6, 5
+    xs = [torch.rand(B, 6, 32, 43, generator=torch.Generator().manual_seed(10 + k)) for k in range(nb)]
+    refs = [net(x=x.to(dev())).cpu() for x in xs]
+    assert not torch.equal(refs[0], refs[1])
+    plan = net.plan_for(B, 32, 43, dev())
+    packed = net.packed_weights(plan)
+    pp = make_prepost(6, (32, 43), (32, 43))
+    xh = [x.pin_memory() for x in xs]
+    yh = [torch.zeros(B, 2, 32, 43).pin_memory() for _ in range(nb)]
+    xd = [torch.empty(B, 6, 32, 43, device=dev()) for _ in range(2)]
+    yd = [torch.empty(B, 2, 32, 43, device=dev()) for _ in range(2)]
+    for chunk in (B, 2):
+        plan.set_chunk(chunk)
+        for y in yh:
+            y.zero_()
+        for k in range(nb):
+            plan.forward_host_async(xh[k], None, pp, yh[k], xd[k % 2], yd[k % 2], packed, slot=k % 2)
+        plan.host_wait(0)
+        plan.host_wait(1)     # downloads are ordered on one copy stream: the last two waits cover all six
+        for k in range(nb):
+            assert torch.equal(yh[k], refs[k]), (chunk, k)
+    plan.set_chunk(B)
+    with pytest.raises(RuntimeError):
+        plan.host_wait(3)     # nothing in flight on that slot
+    with pytest.raises(RuntimeError):
+        plan.forward_host_async(xh[0], None, pp, yh[0], xd[0], yd[0], packed, slot=9)
+
+
 @pytest.mark.parametrize("cin,cin1,cout,h,w,b,pool", [(64, 0, 64, 19, 23, 2, False), (64, 0, 64, 40, 53, 2, True),
                                                        (64, 0, 128, 33, 20, 1, False), (128, 0, 128, 21, 27, 2, True),
                                                        (256, 0, 256, 16, 24, 3, False), (64, 64, 64, 20, 26, 2, False),
