@@ -158,6 +158,8 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
   p.pooled = static_cast<__nv_bfloat16*>(d.pooled);
   p.H = d.H; p.W = d.W; p.groups = d.groups; p.ntot = ntot;
   p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
+  p.fd_cpg = make_fastdiv(p.cout_per_group);
+  GSD_CHECK(p.cout_per_group < 4096 && (long)d.B * d.H * d.W * d.groups < (1L << 31), "conv: output too large for 32-bit pixel arithmetic");
   GSD_CHECK((long)m_tiles * p.n_tiles < (1L << 24) && p.tiles_x < 4096 && p.tiles_y < 4096 && p.n_tiles < 4096, "conv: too many tiles for the 24-bit tile index");
   p.stats = d.stats;
   GSD_CHECK(ntot <= 2048, "conv: more than 2048 output channels per launch are not supported");

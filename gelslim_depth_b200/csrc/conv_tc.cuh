@@ -37,7 +37,7 @@ struct ConvParams {
   __nv_bfloat16* pooled;  // (B, H/2, W/2, Cout) or null
   int H, W, groups, ntot;
   float* stats;           // global [2][ntot] batch statistics of the raw conv output, or null
-  FastDiv fd_ntiles, fd_tx, fd_ty;
+  FastDiv fd_ntiles, fd_tx, fd_ty, fd_cpg;   // fd_cpg: division by cout_per_group
   int src5;               // 1: tm_src0 is the 5-D space-to-depth view (2C, W, 2, H, B) of a (B,2H,2W,C) tensor and the
                           //    "tap" index is its gy coordinate (transposed-conv input gradient)
   const float* scale;     // [Ntot]
@@ -238,16 +238,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       px.stats_stride = p.ntot;
       px.pvalid = ((y >> 1) < Hp) && ((x >> 1) < Wp);
       px.hx = hx; px.hy = hy; px.ypart = p.tw;
-      // pixel index (in units of one output pixel record) of the 4 rows this lane stores after the transpose
-      long pix[4];
+      // &out[pixel][0] of the 4 rows this lane stores after the transpose (null: outside the image); the per-unit
+      // part of the address (channel, transposed-conv (dy,dx) view) is warp-uniform and added in the loop below
+      __nv_bfloat16* row_base[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int rr = q * 32 + 8 * i + (lane >> 2);
         const int yy = ty * p.th + (rr >> tw_shift), xx = tx * p.tw + (rr & (p.tw - 1));
-        if (yy >= p.H || xx >= p.W) pix[i] = -1;
-        else if (p.groups == 1) pix[i] = ((long)b * p.H + yy) * p.W + xx;
-        else pix[i] = ((long)b * 2 * p.H + 2 * yy) * (2 * p.W) + 2 * xx;
+        if (yy >= p.H || xx >= p.W) row_base[i] = nullptr;
+        else if (p.groups == 1) row_base[i] = p.out + (size_t)(((int)b * p.H + yy) * p.W + xx) * p.cout_per_group;
+        else row_base[i] = p.out + (size_t)(((int)b * 2 * p.H + 2 * yy) * (2 * p.W) + 2 * xx) * p.cout_per_group;
       }
+      __nv_bfloat16* const pool_base =
+          p.pooled ? p.pooled + (size_t)(((int)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout_per_group + (hx ? 16 : 0) + (hy ? 8 : 0)
+                   : nullptr;
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
@@ -255,14 +259,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         // a 32-column unit lies inside ONE (dy,dx) group of the transposed-conv scatter (Cout % 32 == 0)
-        const int grp_idx = (n0 + c0) / p.cout_per_group;
-        const int ch0 = n0 + c0 - grp_idx * p.cout_per_group;        // channel of column c0 inside its group
-        const long goff = (p.groups == 1) ? 0 : (long)(grp_idx >> 1) * (2 * p.W) + (grp_idx & 1);
+        uint32_t grp_idx, ch0;                                        // ch0: channel of column c0 inside its group
+        fdivmod((uint32_t)(n0 + c0), p.fd_cpg, grp_idx, ch0);
+        const int uoff = ((int)(grp_idx >> 1) * (2 * p.W) + (int)(grp_idx & 1)) * p.cout_per_group + (int)ch0 - c0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          px.rp[i] = pix[i] < 0 ? nullptr : p.out + (pix[i] + goff) * p.cout_per_group + ch0 - c0;
-        px.prow = p.pooled ? p.pooled + (((size_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout_per_group + ch0 - c0 + (hx ? 16 : 0) + (hy ? 8 : 0)
-                           : nullptr;
+        for (int i = 0; i < 4; ++i) px.rp[i] = row_base[i] ? row_base[i] + uoff : nullptr;
+        px.prow = pool_base ? pool_base + ((int)ch0 - c0) : nullptr;
         epilogue_32cols(t_row, c0, p.scale ? g_scale + n0 : nullptr, p.shift ? g_shift + n0 : nullptr, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc, nullptr, 0);
       }
       // accumulator fully read -> hand it back to the MMA warp

@@ -84,36 +84,35 @@ __device__ __forceinline__ void epilogue_32cols(uint32_t t_row, int c0, const fl
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 a = sc4[i], b = sh4[i];
-      f[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), a.x, b.x);
-      f[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), a.y, b.y);
-      f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), a.z, b.z);
-      f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), a.w, b.w);
+      ffma2(f[4 * i + 0], f[4 * i + 1], __uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]), a.x, a.y, b.x, b.y);
+      ffma2(f[4 * i + 2], f[4 * i + 3], __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), a.z, a.w, b.z, b.w);
+    }
+  } else if (sc) {
+    const float4* sc4 = reinterpret_cast<const float4*>(sc + c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 a = sc4[i];
+      fmul2(f[4 * i + 0], f[4 * i + 1], __uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]), a.x, a.y);
+      fmul2(f[4 * i + 2], f[4 * i + 3], __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), a.z, a.w);
+    }
+  } else if (sh) {
+    const float4* sh4 = reinterpret_cast<const float4*>(sh + c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = sh4[i];
+      fadd2(f[4 * i + 0], f[4 * i + 1], __uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]), b.x, b.y);
+      fadd2(f[4 * i + 2], f[4 * i + 3], __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), b.z, b.w);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-    if (sc) {
-      const float4* sc4 = reinterpret_cast<const float4*>(sc + c0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 a = sc4[i];
-        f[4 * i + 0] *= a.x; f[4 * i + 1] *= a.y; f[4 * i + 2] *= a.z; f[4 * i + 3] *= a.w;
-      }
-    }
-    if (sh) {
-      const float4* sh4 = reinterpret_cast<const float4*>(sh + c0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b = sh4[i];
-        f[4 * i + 0] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
-      }
-    }
-  }
-  if (relu) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
   }
   if (g_head) {
+    // the fused 1x1 head consumes the fp32 post-ReLU values (only the network's last conv takes this path)
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < ncls) {           // warp-uniform
@@ -131,11 +130,14 @@ __device__ __forceinline__ void epilogue_32cols(uint32_t t_row, int c0, const fl
       }
     }
   }
+  // ReLU rides on the bf16 conversion (cvt.rn.relu): no FMNMX per element
   uint32_t pk[16];
+  if (relu) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2_relu(f[2 * i], f[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
   }
   if (px.store_out) {
     // lane -> row `lane` of the patch; 16-byte chunk j lives at (j ^ ((row >> 1) & 3)): conflict-free both ways

@@ -38,6 +38,37 @@ __device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv& f, uint32_t& 
   r = n - q * f.d;
 }
 
+// ---------------------------------------------------------------- packed fp32 / bf16 arithmetic
+// Blackwell issues TWO IEEE fp32 operations per instruction slot (FFMA2 / FMUL2 / FADD2): results are bit-identical
+// to the scalar fmaf / * / +, but the epilogue warps -- two per SM sub-partition, issue-bound -- spend half the slots.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n"
+      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n"
+      " mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n"
+      " add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// {lo, hi} -> bf16x2 (lo in bits 0..15), round to nearest even; the _relu form clamps negatives to +0 first
+// (relu(round(x)) == round(relu(x)): rounding is monotonic and 0 is representable), one instruction either way.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
