@@ -1,52 +1,100 @@
-"""BASELINE configs[4]: batch-sharded inference sweep, batch 1..1024 on this GPU (run one process per GPU for N>1),
-device-resident frames, plus the pipelined host path at a few chunk sizes.  One JSON line per batch."""
+"""BASELINE configs[4]: batch-sharded inference sweep.  One process per GPU (plain `python tools/sweep.py` for one GPU,
+`python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sweep.py` for N): every rank runs the
+same plan on its own shard of the batch with no data-path collective; the time of a point is the max over ranks (NCCL is
+used for the barrier and that max only).  Device-resident frames, plus (batch 64 per GPU) the blocking and the
+rotating-slot host pipelines.  Rank 0 prints one JSON line per total batch."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+import torch.distributed as dist
 from gelslim_depth_b200.models.unet import UNet
 from gelslim_depth_b200.engine import make_prepost
 
-def run(batches=(1, 2, 4, 8, 16, 32, 64, 128, 256), host_chunks=(4, 8, 16, 32)):
-    dev = torch.device("cuda:0")
+
+def run(per_gpu=(1, 2, 4, 8, 16, 32, 64, 128, 256), host_chunks=(16,)):
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        per_gpu = tuple(b for b in per_gpu if b * world <= 1024)
+
+    def maxms(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
     torch.manual_seed(0)
     net = UNet(6, 2).to(dev).eval()
     H, W = 320, 427
     base = torch.randint(0, 256, (1, 6, H, W), dtype=torch.uint8).float().to(dev)
     pp = make_prepost(6, (H, W), (H, W), use_diff=True, in_scale=[1 / 255.0], out_scale=1.9180814027786255 / -0.9,
                       out_shift=-1.9180814027786255)
-    for B in batches:
-        x = torch.randint(0, 256, (B, 6, H, W), dtype=torch.uint8).float().to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for B in per_gpu:
+        x = torch.randint(0, 256, (B, 6, H, W), dtype=torch.uint8,
+                          generator=torch.Generator().manual_seed(100 + rank)).float().to(dev)
         y = torch.empty(B, 2, H, W, device=dev)
         plan = net.plan_for(B, H, W, dev)
         packed = net.packed_weights(plan)
         for _ in range(3):
             plan.forward(x, base, pp, y, packed)
-        torch.cuda.synchronize()
-        iters = max(5, min(200, int(2000 / B)))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = max(5, min(100, int(1000 / B)))
+        barrier()
         e0.record()
         for _ in range(iters):
             plan.forward(x, base, pp, y, packed)
         e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        rec = {"batch": B, "ms_per_batch": ms, "frames_per_s": B / ms * 1e3, "tensor_frac_of_sustained": B / ms * 1e3 * 200.117 / 1e3 / 1386.1}
+        barrier()
+        ms = maxms(e0.elapsed_time(e1)) / iters
+        fps = world * B / ms * 1e3
+        rec = {"n_gpus": world, "batch_total": world * B, "batch_per_gpu": B, "ms_per_batch": ms, "frames_per_s": fps,
+               "tensor_frac_of_sustained": fps / world * 200.117 / 1e3 / 1386.1}
         if B == 64:
-            xh, yh = x.cpu().pin_memory(), torch.empty(B, 2, H, W).pin_memory()
+            xh, yh = x.cpu().pin_memory(), [torch.empty(B, 2, H, W).pin_memory() for _ in range(2)]
+            xd, yd = [x, torch.empty_like(x)], [y, torch.empty_like(y)]
             for ch in host_chunks:
-                plan.set_chunk(ch)
+                plan.set_chunk(ch, first=ch // 2, last=ch // 2)
                 for _ in range(2):
-                    plan.forward_host(xh, base, pp, yh, x, y, packed)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
+                    plan.forward_host(xh, base, pp, yh[0], x, y, packed)
+                barrier()
+                e0.record()
                 for _ in range(5):
-                    plan.forward_host(xh, base, pp, yh, x, y, packed)
-                rec[f"e2e_fps_chunk{ch}"] = B * 5 / (time.perf_counter() - t0)
+                    plan.forward_host(xh, base, pp, yh[0], x, y, packed)
+                e1.record()
+                barrier()
+                rec[f"e2e_blocking_fps_chunk{ch}"] = world * B * 5 / (maxms(e0.elapsed_time(e1)) / 1e3)
             plan.set_chunk(B)
-        print(json.dumps(rec), flush=True)
+
+            def pipelined(n=10):
+                for k in range(n):
+                    plan.forward_host_async(xh, base, pp, yh[k % 2], xd[k % 2], yd[k % 2], packed, slot=k % 2)
+                plan.host_wait(0)
+                plan.host_wait(1)
+            pipelined(4)
+            barrier()
+            e0.record()
+            pipelined(10)
+            e1.record()
+            barrier()
+            rec["e2e_rotating_slots_fps"] = world * B * 10 / (maxms(e0.elapsed_time(e1)) / 1e3)
+            del xh, yh, xd, yd
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
         del plan, x, y
         net._plans.clear()
         torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+
 
 if __name__ == "__main__":
     run()
