@@ -64,11 +64,16 @@ struct HaloGeom {
 
 // NEPI = epilogue warps (4: one per TMEM lane quadrant; 8: two sets of four that drain ALTERNATE work items, i.e.
 // one set per TMEM accumulator buffer -- the per-tile bookkeeping is then paid once per tile, not once per unit)
-template <int BN, int MT, bool WRES, int BKB, int NEPI>
+// CTA2: thread-block cluster of two CTAs sharing every tcgen05.mma (cta_group::2, M = 256): each CTA stages and reads
+// only HALF of the weight rows, so the smem operand traffic per UMMA drops from 32 + N/4 to 32 + N/8 wavefronts and the
+// weight TMA traffic halves.  The pair walks pairs of M groups (same N tile); only the leader issues MMAs.
+template <int BN, int MT, bool WRES, int BKB, int NEPI, bool CTA2 = false>
 __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr int kHaloThreads = 64 + 32 * NEPI;
   using G = HaloGeom<BKB>;
-  constexpr int B_BYTES = BN * BKB;
+  constexpr int BN_CTA = CTA2 ? BN / 2 : BN;          // weight rows this CTA stages
+  constexpr int B_BYTES = BN_CTA * BKB;
+  constexpr uint32_t NCTA = CTA2 ? 2 : 1;
   constexpr int KEL = BKB / 2;
   constexpr int TMEM_COLS = (2 * MT * BN <= 128) ? 128 : (2 * MT * BN <= 256) ? 256 : 512;
   static_assert(2 * MT * BN <= 512, "accumulators exceed TMEM");
@@ -101,6 +106,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_src0);
@@ -110,10 +117,10 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < na; ++i) { mbar_init(bar_fullA + 8 * i, 1); mbar_init(bar_emptyA + 8 * i, 1); }
     for (int i = 0; i < (WRES ? 1 : nb); ++i) { mbar_init(bar_fullB + 8 * i, 1); mbar_init(bar_emptyB + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4 * NCTA); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(s_tmem_slot);
+  if (warp == 2) { if (CTA2) tmem_alloc_2sm<TMEM_COLS>(s_tmem_slot); else tmem_alloc<TMEM_COLS>(s_tmem_slot); }
   for (int i = threadIdx.x; i < p.Cout; i += kHaloThreads) {
     if (p.scale) g_scale[i] = __ldg(p.scale + i);      // null: scale == 1 / shift == 0, the epilogue skips the loads
     if (p.shift) g_shift[i] = __ldg(p.shift + i);
@@ -126,27 +133,34 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   pdl_launch_dependents();      // the next layer may start its own setup while this grid drains
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
   const int m_groups = (m_tiles + MT - 1) / MT;
-  const int total_items = m_groups * p.n_tiles;
+  const int total_items = (CTA2 ? (m_groups + 1) / 2 : m_groups) * p.n_tiles;   // CTA2: items are PAIRS of M groups
+  const int first_item = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       if (WRES) {
-        mbar_arrive_expect_tx(bar_fullB, (uint32_t)(nkb * B_BYTES));
-        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(s_b + kb * B_BYTES, &p.tm_w, bar_fullB, kb * KEL, 0);
+        if (leader) mbar_arrive_expect_tx(bar_fullB, (uint32_t)(nkb * B_BYTES) * NCTA);
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (CTA2) tma_load_2d_2sm(s_b + kb * B_BYTES, &p.tm_w, bar_fullB, kb * KEL, (int)rank * BN_CTA);
+          else tma_load_2d(s_b + kb * B_BYTES, &p.tm_w, bar_fullB, kb * KEL, 0);
+        }
       }
       int ia = 0, ib = 0;
       uint32_t pa = 0, pb = 0;
       pdl_wait();               // activations of the previous layer are complete from here on (weights were not its output)
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int item = first_item; item < total_items; item += item_stride) {
         uint32_t mg, nt;
         fdivmod((uint32_t)item, p.fd_ntiles, mg, nt);
+        if (CTA2) mg = 2 * mg + rank;
         for (int cb = 0; cb < cbt; ++cb) {
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
@@ -157,19 +171,20 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
             fdivmod(row, p.fd_ty, b, ty);
             const int xs = tx * 8 - 1, ys = ty * 16 - 1;
             mbar_wait(bar_emptyA + 8 * ia, pa ^ 1);
-            mbar_arrive_expect_tx(bar_fullA + 8 * ia, G::BOX_BYTES);
-            if (cb < p.cb0)
-              tma_load_4d(s_a + ia * G::BUF_BYTES, &p.tm_src0, bar_fullA + 8 * ia, cb * KEL, xs, ys, b);
-            else
-              tma_load_4d(s_a + ia * G::BUF_BYTES, &p.tm_src1, bar_fullA + 8 * ia, (cb - p.cb0) * KEL, xs - p.off_x,
-                          ys - p.off_y, b);
+            if (leader) mbar_arrive_expect_tx(bar_fullA + 8 * ia, G::BOX_BYTES * NCTA);   // both CTAs' boxes land on the leader's barrier
+            const CUtensorMap* tm = (cb < p.cb0) ? &p.tm_src0 : &p.tm_src1;
+            const int cc = (cb < p.cb0) ? cb * KEL : (cb - p.cb0) * KEL;
+            const int cx = (cb < p.cb0) ? xs : xs - p.off_x, cy = (cb < p.cb0) ? ys : ys - p.off_y;
+            if (CTA2) tma_load_4d_2sm(s_a + ia * G::BUF_BYTES, tm, bar_fullA + 8 * ia, cc, cx, cy, b);
+            else tma_load_4d(s_a + ia * G::BUF_BYTES, tm, bar_fullA + 8 * ia, cc, cx, cy, b);
             if (++ia == na) { ia = 0; pa ^= 1; }
           }
           if (!WRES) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(bar_emptyB + 8 * ib, pb ^ 1);
-              mbar_arrive_expect_tx(bar_fullB + 8 * ib, B_BYTES);
-              tma_load_2d(s_b + ib * B_BYTES, &p.tm_w, bar_fullB + 8 * ib, (tap * cbt + cb) * KEL, nt * BN);
+              if (leader) mbar_arrive_expect_tx(bar_fullB + 8 * ib, B_BYTES * NCTA);
+              if (CTA2) tma_load_2d_2sm(s_b + ib * B_BYTES, &p.tm_w, bar_fullB + 8 * ib, (tap * cbt + cb) * KEL, nt * BN + (int)rank * BN_CTA);
+              else tma_load_2d(s_b + ib * B_BYTES, &p.tm_w, bar_fullB + 8 * ib, (tap * cbt + cb) * KEL, nt * BN);
               if (++ib == nb) { ib = 0; pb ^= 1; }
             }
           }
@@ -177,13 +192,14 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
       }
     }
   } else if (warp == 1) {
+   if (leader) {
     // ===================================================== MMA issuer (whole warp converged; one elected lane issues)
-    constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
+    constexpr uint32_t idesc = CTA2 ? make_idesc_bf16_m256(BN) : make_idesc_bf16_m128(BN);
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     if (WRES) { mbar_wait(bar_fullB, 0); tc_fence_after(); }
     int it = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+    for (int item = first_item; item < total_items; item += item_stride, ++it) {
       const int buf = it & 1;
       mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -219,11 +235,16 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
                 // the swizzle XOR on absolute smem address bits, so no base-offset is needed (verified on B200)
                 const uint32_t a0 = a_lo[j] + (ty3 * 10 + tx3) * G::ROW16;
 #pragma unroll
-                for (int k = 0; k < G::KSTEPS; ++k)
-                  umma_bf16_lohi(d_tmem, (a0 + 2 * k) | (1u << 16), G::A_HI, (b_lo + 2 * k) | (1u << 16), G::B_HI, idesc,
-                                 (k != 0) ? 1u : (uint32_t)((cb | tap) != 0));
+                for (int k = 0; k < G::KSTEPS; ++k) {
+                  if (CTA2)
+                    umma_bf16_lohi_2sm(d_tmem, (a0 + 2 * k) | (1u << 16), G::A_HI, (b_lo + 2 * k) | (1u << 16), G::B_HI, idesc,
+                                       (k != 0) ? 1u : (uint32_t)((cb | tap) != 0));
+                  else
+                    umma_bf16_lohi(d_tmem, (a0 + 2 * k) | (1u << 16), G::A_HI, (b_lo + 2 * k) | (1u << 16), G::B_HI, idesc,
+                                   (k != 0) ? 1u : (uint32_t)((cb | tap) != 0));
+                }
               }
-              if (!WRES) umma_commit(bar_emptyB + 8 * ib);
+              if (!WRES) { if (CTA2) umma_commit_2sm(bar_emptyB + 8 * ib); else umma_commit(bar_emptyB + 8 * ib); }
             }
             __syncwarp();
             if (!WRES) { if (++ib == nb) { ib = 0; pb ^= 1; } }
@@ -231,13 +252,14 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
         }
         if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < MT; ++j) umma_commit(bar_emptyA + 8 * a_slot[j]);
+          for (int j = 0; j < MT; ++j) { if (CTA2) umma_commit_2sm(bar_emptyA + 8 * a_slot[j]); else umma_commit(bar_emptyA + 8 * a_slot[j]); }
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(bar_acc_full + 8 * buf);
+      if (elect_one()) { if (CTA2) umma_commit_2sm(bar_acc_full + 8 * buf); else umma_commit(bar_acc_full + 8 * buf); }
       __syncwarp();
     }
+   }
   } else {
     // ===================================================== epilogue (warps 2..): quadrant q = warp % 4, set = (warp-2)/4
     const int q = warp & 3;
@@ -248,11 +270,12 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
     const bool hx = lane & 1, hy = (lane >> 3) & 1;   // which half of a pooling exchange this lane keeps
     int it = 0;
     pdl_wait();                 // no global write before the predecessor grid has finished (it may still read our output buffers' neighbours)
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+    for (int item = first_item; item < total_items; item += item_stride, ++it) {
       const int buf = it & 1;
       if (NEPI == 8 && buf != eset) continue;          // the other warp set owns this accumulator buffer
       uint32_t mg, nt;
       fdivmod((uint32_t)item, p.fd_ntiles, mg, nt);
+      if (CTA2) mg = 2 * mg + rank;
       mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -297,16 +320,17 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+      if (lane == 0) { if (CTA2) mbar_arrive_leader(bar_acc_empty + 8 * buf); else mbar_arrive(bar_acc_empty + 8 * buf); }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();      // neither CTA exits (or frees TMEM) while the other may still signal it
   if (p.stats) {
     for (int i = threadIdx.x; i < 2 * p.Cout; i += kHaloThreads) atomicAdd(p.stats + i, g_stats[i]);
   }
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 2) { if (CTA2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base); }
 }
 
 }  // namespace gsd

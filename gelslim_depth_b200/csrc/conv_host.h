@@ -37,17 +37,29 @@ struct ConvDesc {
 
 // launch `kernel` with `params`, optionally as a programmatic dependent launch (see gsd_ptx.cuh)
 template <class Params>
-inline int launch_maybe_pdl(void (*kernel)(Params), const Params& params, int grid, int block, int smem, cudaStream_t st, int pdl) {
+inline int launch_maybe_pdl(void (*kernel)(Params), const Params& params, int grid, int block, int smem, cudaStream_t st, int pdl,
+                            int cluster = 1) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {           // thread-block cluster (CTA pair of one TPC for cta_group::2 MMAs)
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = n;
   GSD_CUDA(cudaLaunchKernelEx(&cfg, kernel, params));
   return 0;
 }
@@ -216,6 +228,7 @@ struct HaloLaunch {
   HaloParams p;
   int pdl = 0;
   int bn = 0, mt = 0, wres = 0, bkb = 0, nepi = 8, grid = 0, smem = 0;
+  int cta2 = 0;               // CTA pair per work item (cta_group::2 MMAs, half of the weight rows per CTA)
   double flops = 0;
 };
 
@@ -303,13 +316,24 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     // (tools/exp_bn256.py, batch 64): +7..10 % for 256->512, 512->256, 1024->512, +2 % for 512->512, no gain for
     // 256->256 and 128->256, hence the rule below.
     const bool big = (d.C0 + d.C1 >= 512) || d.Cout >= 512;
-    const bool want256 = d.block_n == 256 || (d.block_n == 0 && big && !getenv("GSD_NO_BN256"));
+    const bool want256 = d.block_n == 256 || (d.block_n == 0 && (big || getenv("GSD_BN256_ALL")) && !getenv("GSD_NO_BN256"));
     if (!small && want256 && d.Cout % 256 == 0 && mtl * (d.Cout / 256) >= num_sms) { bn = 256; mt = 1; }
     if (d.block_n == 256 && d.Cout % 256 == 0) { bn = 256; mt = 1; }
   }
   GSD_CHECK(bkb == 128 || wres, "halo conv: first-layer path needs resident weights");
+  // CTA pairs (cta_group::2): only where there is more than one wave of pair items (small batches keep single CTAs)
+  {
+    const long mtl = (long)((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
+    const long pair_items = (((mtl + mt - 1) / mt + 1) / 2) * (d.Cout / bn);
+    const char* e = getenv("GSD_CTA2");
+    // default (1): N >= 128 layers with at least a full wave of pair items; 0: never; 2: every 64-channel-block layer
+    // (tests).  Measured on B200, batch 64 (tools/exp_cta2.py): N = 128 / 256 layers gain 8-17 %, the resident-weight
+    // N = 64 layers lose 4-30 % (their UMMA is A-read-bound either way), so those keep single CTAs.
+    const int mode = e ? atoi(e) : 1;
+    L->cta2 = (bkb == 128 && num_sms % 2 == 0 && (mode == 2 || (mode == 1 && bn >= 128 && pair_items >= num_sms / 2))) ? 1 : 0;
+  }
   const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
-  const int b_bytes = bn * bkb;
+  const int b_bytes = (L->cta2 ? bn / 2 : bn) * bkb;
   if (wres) {
     p.nb = 0;
     p.na = (budget - aux - 9 * cbt * b_bytes) / buf_bytes;
@@ -341,11 +365,21 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     const uint64_t ktot = 9ull * (d.C0 + d.C1);
     uint64_t dims[2] = {ktot, (uint64_t)d.Cout};
     uint64_t str[1] = {ktot * 2};
-    uint32_t box[2] = {(uint32_t)kel, (uint32_t)bn};
+    uint32_t box[2] = {(uint32_t)kel, (uint32_t)(L->cta2 ? bn / 2 : bn)};
     GSD_TRY(encode_bf16_map(&p.tm_w, const_cast<void*>(d.w), 2, dims, str, box, swz, true));
   }
   const long m_tiles = (long)p.tiles_x * p.tiles_y * d.B;
   const long items = ((m_tiles + mt - 1) / mt) * p.n_tiles;
+  if (getenv("GSD_DEBUG_LAUNCH"))
+    fprintf(stderr, "halo conv %dx%d B=%d C=%d+%d->%d: bn=%d mt=%d wres=%d nepi=%d cta2=%d na=%d nb=%d smem=%d\n", d.H, d.W, d.B, d.C0,
+            d.C1, d.Cout, bn, mt, wres, nepi, L->cta2, p.na, p.nb, L->smem);
+  if (L->cta2) {
+    const long pair_items = (((m_tiles + mt - 1) / mt + 1) / 2) * p.n_tiles;
+    const long pairs = pair_items < num_sms / 2 ? pair_items : num_sms / 2;
+    L->grid = (int)(2 * pairs);
+    L->flops = 2.0 * d.B * d.H * d.W * (double)d.Cout * 9 * (d.C0 + d.C1);
+    return 0;
+  }
   // the first-layer variant (16-channel rows) is epilogue-latency-bound: two co-resident CTAs per SM (78 KB smem, 96
   // registers, 128 TMEM columns each) double the warps the schedulers can pick from
   const long ctas = (long)num_sms * (bkb == 32 ? 2 : 1);
@@ -356,6 +390,13 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
 
 template <int BN, int MT, bool WRES, int BKB, int NEPI>
 inline int launch_halo_cfg(const HaloLaunch& L, cudaStream_t st) {
+  if constexpr (BKB == 128) {
+    if (L.cta2) {
+      static SmemAttrCache attr_cache2;
+      GSD_TRY(attr_cache2.ensure(conv_halo_kernel<BN, MT, WRES, BKB, NEPI, true>, L.smem));
+      return launch_maybe_pdl(conv_halo_kernel<BN, MT, WRES, BKB, NEPI, true>, L.p, L.grid, 64 + 32 * NEPI, L.smem, st, L.pdl, 2);
+    }
+  }
   static SmemAttrCache attr_cache;
   GSD_TRY(attr_cache.ensure(conv_halo_kernel<BN, MT, WRES, BKB, NEPI>, L.smem));
   return launch_maybe_pdl(conv_halo_kernel<BN, MT, WRES, BKB, NEPI>, L.p, L.grid, 64 + 32 * NEPI, L.smem, st, L.pdl);

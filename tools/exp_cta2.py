@@ -1,0 +1,41 @@
+"""A/B of the CTA-pair (cta_group::2) halo conv: per-launch table of one batch-64 forward with GSD_CTA2=0/1 and bit-equality
+of the outputs.  usage: python tools/exp_cta2.py"""
+import os, sys, subprocess, json
+sys.path.insert(0, "/root/repo")
+if len(sys.argv) > 1:
+    import torch
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.engine import make_prepost
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    net = UNet(6, 2)
+    import oracle
+    net.load_state_dict(oracle.conditioned_state_dict(net.state_dict(), seed=1))
+    net = net.to(dev).eval()
+    H, W, B = 320, 427, 64
+    g = torch.Generator().manual_seed(5)
+    base = torch.randint(0, 256, (1, 6, H, W), dtype=torch.uint8, generator=g).float().to(dev)
+    x = torch.randint(0, 256, (B, 6, H, W), dtype=torch.uint8, generator=g).float().to(dev)
+    pp = make_prepost(6, (H, W), (H, W), use_diff=True, in_scale=[1 / 255.0], out_scale=1.9180814027786255 / -0.9, out_shift=-1.9180814027786255)
+    y = torch.empty(B, 2, H, W, device=dev)
+    plan = net.plan_for(B, H, W, dev)
+    packed = net.packed_weights(plan)
+    for _ in range(3):
+        prof = plan.forward_profiled(x, base, pp, y, packed)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        plan.forward(x, base, pp, y, packed)
+    e1.record(); torch.cuda.synchronize()
+    torch.save(y.cpu(), sys.argv[1])
+    print(json.dumps({"ms": [round(m, 4) for m, f in prof], "sum": sum(m for m, f in prof), "loop3": e0.elapsed_time(e1) / 3, "ystd": float(y.std())}))
+else:
+    out = {}
+    for mode, extra in (("0", {}), ("1", {}), ("1", {"GSD_NO_BN256": "1"}), ("1", {"GSD_BN256_ALL": "1"})):
+        env = dict(os.environ, GSD_CTA2=mode, **extra)
+        r = subprocess.run([sys.executable, __file__, f"/tmp/y{mode}.pt"], env=env, capture_output=True, text=True)
+        print("mode", mode, extra, r.stdout.strip()[-1500:], r.stderr.strip()[-1500:])
+    import torch
+    a, b = torch.load("/tmp/y0.pt"), torch.load("/tmp/y1.pt")
+    print("bit-identical:", torch.equal(a, b), "max abs diff", float((a - b).abs().max()))
