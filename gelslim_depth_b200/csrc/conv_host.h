@@ -342,8 +342,11 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     L->smem = p.na * buf_bytes + 9 * cbt * b_bytes + aux + 1024;
   } else {
     p.na = 4;
+    int nb_max = 9;
+    if (const char* e = getenv("GSD_NA")) p.na = atoi(e);            // tuning experiments only
+    if (const char* e = getenv("GSD_NB_MAX")) nb_max = atoi(e);
     p.nb = (budget - aux - p.na * buf_bytes) / b_bytes;
-    if (p.nb > 9) p.nb = 9;
+    if (p.nb > nb_max) p.nb = nb_max;
     GSD_CHECK(p.nb >= 3, "halo conv: no room for the weight ring");
     L->smem = p.na * buf_bytes + p.nb * b_bytes + aux + 1024;
   }

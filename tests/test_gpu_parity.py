@@ -331,6 +331,40 @@ def test_conv3x3_halo_kernel(cin, cin1, cout, h, w, b, pool):
         assert torch.equal(r[1].permute(0, 3, 1, 2).float().cpu(), want)
 
 
+@pytest.mark.parametrize("cin,cin1,cout,h,w,b,pool,block_n", [
+    (64, 0, 128, 33, 20, 1, False, 0),      # 3 x 3 x 1 = 9 tiles: odd number of M groups, the peer CTA of the last pair idles
+    (128, 0, 128, 21, 27, 2, True, 0),      # fused max-pool in both CTAs
+    (256, 0, 256, 16, 24, 3, False, 256),   # N = 256 UMMA (128 weight rows per CTA)
+    (128, 128, 128, 10, 13, 1, False, 0),   # two-source virtual concat, a single tile: one pair, idle peer
+    (64, 64, 256, 40, 53, 2, False, 0),     # several N tiles per M group
+    (64, 0, 64, 40, 53, 2, True, 0)])       # resident weights, 32 rows per CTA (not selected by default; must still be exact)
+def test_conv3x3_halo_kernel_cta_pair(cin, cin1, cout, h, w, b, pool, block_n, monkeypatch):
+    """CTA-pair variant of the halo conv (thread-block cluster of 2, tcgen05.mma.cta_group::2, csrc/conv_halo.cuh): the
+    launch rule only pairs CTAs when a layer has a full wave of work, so GSD_CTA2=2 forces it on small shapes.  Result
+    must match the fp32 reference AND be bit-identical to the single-CTA kernel (same accumulation order)."""
+    from gelslim_depth_b200.engine import conv3x3_halo_op
+    g = torch.Generator().manual_seed(cin + cout + h)
+    ct = cin + cin1
+    x = bf16r(torch.randn(b, ct, h, w, generator=g))
+    wt = bf16r(torch.randn(cout, ct, 3, 3, generator=g) * (2.0 / (9 * ct)) ** 0.5)
+    sc, sh = 0.5 + torch.rand(cout, generator=g), 0.3 * torch.randn(cout, generator=g)
+    ref = torch.relu(F.conv2d(x, wt, padding=1) * sc[None, :, None, None] + sh[None, :, None, None])
+    d = dev()
+    xs = nhwc(x).to(torch.bfloat16).to(d)
+    s0 = xs[..., :cin].contiguous()
+    s1 = xs[..., cin:].contiguous() if cin1 else None
+    args = (s0, pack_w3(wt).to(d), sc.to(d), sh.to(d))
+    results = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("GSD_CTA2", mode)
+        r = conv3x3_halo_op(*args, relu=True, src1=s1, pool=pool, block_n=block_n)
+        torch.cuda.synchronize()
+        results[mode] = r if pool else (r,)
+    check_close(results["2"][0].permute(0, 3, 1, 2), ref, "halo conv3x3, CTA pair")
+    for single, pair in zip(results["0"], results["2"]):
+        assert torch.equal(single, pair)
+
+
 def test_first_layer_halo_kernel():
     """inc.double_conv.0 through the SW32 / 16-channel variant of the halo kernel."""
     from gelslim_depth_b200.engine import conv3x3_halo_op

@@ -31,11 +31,16 @@ if len(sys.argv) > 1:
     torch.save(y.cpu(), sys.argv[1])
     print(json.dumps({"ms": [round(m, 4) for m, f in prof], "sum": sum(m for m, f in prof), "loop3": e0.elapsed_time(e1) / 3, "ystd": float(y.std())}))
 else:
-    out = {}
-    for mode, extra in (("0", {}), ("1", {}), ("1", {"GSD_NO_BN256": "1"}), ("1", {"GSD_BN256_ALL": "1"})):
-        env = dict(os.environ, GSD_CTA2=mode, **extra)
-        r = subprocess.run([sys.executable, __file__, f"/tmp/y{mode}.pt"], env=env, capture_output=True, text=True)
-        print("mode", mode, extra, r.stdout.strip()[-1500:], r.stderr.strip()[-1500:])
     import torch
-    a, b = torch.load("/tmp/y0.pt"), torch.load("/tmp/y1.pt")
-    print("bit-identical:", torch.equal(a, b), "max abs diff", float((a - b).abs().max()))
+    configs = [("0", {}), ("1", {})] if len(sys.argv) == 1 else []
+    configs = [("1", {}), ("1", {"GSD_NB_MAX": "18"}), ("1", {"GSD_NB_MAX": "18", "GSD_NA": "6"}),
+               ("1", {"GSD_NB_MAX": "27", "GSD_NA": "5"}), ("1", {"GSD_NB_MAX": "6"}), ("0", {})]
+    ref = None
+    for i, (mode, extra) in enumerate(configs):
+        env = dict(os.environ, GSD_CTA2=mode, **extra)
+        r = subprocess.run([sys.executable, __file__, f"/tmp/y{i}.pt"], env=env, capture_output=True, text=True)
+        y = torch.load(f"/tmp/y{i}.pt") if os.path.exists(f"/tmp/y{i}.pt") else None
+        same = None if (y is None or ref is None) else bool(torch.equal(y, ref))
+        if ref is None:
+            ref = y
+        print("mode", mode, extra, "bit-identical to first:", same, r.stdout.strip()[-1200:], r.stderr.strip()[-600:], flush=True)
