@@ -68,6 +68,7 @@ struct ConvLaunch {
   ConvParams p;
   int pdl = 0;                 // programmatic dependent launch (inference plan only)
   int bn = 0, bkb = 0, grid = 0;
+  int cta2 = 0;                // CTA pair per work item (cta_group::2)
   double flops = 0;            // 2*M*N*K of the real (unpadded) problem
 };
 
@@ -124,6 +125,13 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
             "conv: block_n %d incompatible with Cout %d (groups %d)", bn, d.Cout, d.groups);
   GSD_CHECK(!(bkb == 32 && bn != 64), "conv: first-layer path supports block_n 64 only");
   L->bn = bn; L->bkb = bkb;
+  {
+    // CTA pairs for the tensor-bound 3x3 layers (the transposed convs are HBM / epilogue-bound: no operand to save)
+    const int mode = getenv("GSD_CTA2") ? atoi(getenv("GSD_CTA2")) : 1;
+    const long pair_items = (long)((m_tiles + 1) / 2) * (ntot / bn);
+    L->cta2 = (bkb == 128 && num_sms % 2 == 0 && bn >= 128 && d.groups == 1 &&
+               (mode == 2 || (mode == 1 && d.ntaps == 9 && pair_items >= num_sms / 2))) ? 1 : 0;
+  }
   p.n_tiles = ntot / bn;
   p.cout_per_group = d.Cout;
   p.kb0 = d.C0 / kel;
@@ -163,7 +171,7 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
     const uint64_t ktot = (uint64_t)d.ntaps * (d.C0 + d.C1);
     uint64_t dims[2] = {ktot, (uint64_t)ntot};
     uint64_t str[1] = {ktot * 2};
-    uint32_t box[2] = {(uint32_t)kel, (uint32_t)bn};
+    uint32_t box[2] = {(uint32_t)kel, (uint32_t)(L->cta2 ? bn / 2 : bn)};
     GSD_TRY(encode_bf16_map(&p.tm_w, const_cast<void*>(d.w), 2, dims, str, box, swz, true));
   }
   p.out = static_cast<__nv_bfloat16*>(d.out);
@@ -177,6 +185,10 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
   GSD_CHECK(ntot <= 2048, "conv: more than 2048 output channels per launch are not supported");
   const long total = (long)m_tiles * p.n_tiles;
   L->grid = (int)(total < num_sms ? total : num_sms);
+  if (L->cta2) {
+    const long pairs_total = (long)((m_tiles + 1) / 2) * p.n_tiles;
+    L->grid = (int)(2 * (pairs_total < num_sms / 2 ? pairs_total : num_sms / 2));
+  }
   L->flops = 2.0 * d.B * d.H * d.W * (double)ntot * d.ntaps * (d.C0 + d.C1);
   return 0;
 }
@@ -200,6 +212,14 @@ struct SmemAttrCache {
 
 template <int BN, int BKB>
 inline int launch_conv_cfg(const ConvLaunch& L, cudaStream_t st) {
+  if constexpr (BKB == 128 && BN >= 128) {
+    if (L.cta2) {
+      using Cfg2 = ConvCfg<BN, BKB, true>;
+      static SmemAttrCache attr_cache2;
+      GSD_TRY(attr_cache2.ensure(conv_tc_kernel<BN, BKB, true>, Cfg2::SMEM_BYTES));
+      return launch_maybe_pdl(conv_tc_kernel<BN, BKB, true>, L.p, L.grid, kConvThreads, Cfg2::SMEM_BYTES, st, L.pdl, 2);
+    }
+  }
   using Cfg = ConvCfg<BN, BKB>;
   static SmemAttrCache attr_cache;
   GSD_TRY(attr_cache.ensure(conv_tc_kernel<BN, BKB>, Cfg::SMEM_BYTES));
@@ -288,7 +308,14 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   int bn, mt, wres, nepi = 8;
   // 64 output channels: the whole weight matrix stays resident in smem for the life of the persistent CTA
   // (4 epilogue warps instead of 8 when that leaves too little room for the halo ring)
-  if (d.Cout == 64 && 9 * cbt * 64 * bkb <= 150 * 1024) { bn = 64; mt = 1; wres = 1; nepi = (9 * cbt * 64 * bkb > 80 * 1024) ? 4 : 8; }
+  // CTA pairs (cta_group::2, conv_halo.cuh): GSD_CTA2 = 1 (default) where measured faster, 0 never, 2 everywhere (tests)
+  const int cta2_mode = getenv("GSD_CTA2") ? atoi(getenv("GSD_CTA2")) : 1;
+  const long mtl_all = (long)((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
+  // 64 output channels with K >= 1152 (up.3.conv.0): as single CTAs the resident weights (144 KB) leave room for 4
+  // epilogue warps only; a CTA pair with streamed weights (32 rows per CTA and stage) and M = 2 x 256 measured 7 % faster
+  const bool pair64 = cta2_mode == 1 && bkb == 128 && d.Cout == 64 && cbt >= 2 && num_sms % 2 == 0 &&
+                      ((mtl_all + 1) / 2 + 1) / 2 >= num_sms / 2;
+  if (d.Cout == 64 && !pair64 && 9 * cbt * 64 * bkb <= 150 * 1024 && !(bkb == 128 && getenv("GSD_WRES0"))) { bn = 64; mt = 1; wres = 1; nepi = (9 * cbt * 64 * bkb > 80 * 1024) ? 4 : 8; }
   else if (d.Cout == 64) { bn = 64; mt = 2; wres = 0; }
   else {
     // streamed weights: M = 256 (two tiles share every weight stage) x N = 128 when there is enough work to fill the
@@ -325,12 +352,11 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   {
     const long mtl = (long)((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
     const long pair_items = (((mtl + mt - 1) / mt + 1) / 2) * (d.Cout / bn);
-    const char* e = getenv("GSD_CTA2");
     // default (1): N >= 128 layers with at least a full wave of pair items; 0: never; 2: every 64-channel-block layer
     // (tests).  Measured on B200, batch 64 (tools/exp_cta2.py): N = 128 / 256 layers gain 8-17 %, the resident-weight
     // N = 64 layers lose 4-30 % (their UMMA is A-read-bound either way), so those keep single CTAs.
-    const int mode = e ? atoi(e) : 1;
-    L->cta2 = (bkb == 128 && num_sms % 2 == 0 && (mode == 2 || (mode == 1 && bn >= 128 && pair_items >= num_sms / 2))) ? 1 : 0;
+    L->cta2 = (bkb == 128 && num_sms % 2 == 0 &&
+               (cta2_mode == 2 || (cta2_mode == 1 && (bn >= 128 || pair64) && pair_items >= num_sms / 2))) ? 1 : 0;
   }
   const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
   const int b_bytes = (L->cta2 ? bn / 2 : bn) * bkb;

@@ -55,10 +55,12 @@ struct ConvParams {
   int8_t tap_dx[kMaxTaps];
 };
 
-template <int BN, int BKB>
+// CTA2: CTA pair (cta_group::2, see conv_halo.cuh): each CTA stages BN / 2 weight rows per K block
+template <int BN, int BKB, bool CTA2 = false>
 struct ConvCfg {
   static constexpr int A_BYTES = 128 * BKB;
-  static constexpr int B_BYTES = BN * BKB;
+  static constexpr int BN_CTA = CTA2 ? BN / 2 : BN;
+  static constexpr int B_BYTES = BN_CTA * BKB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int MAX_NTOT = 2048;                    // scale/shift of the whole layer live in smem
   static constexpr int AUX_BYTES = 4 * MAX_NTOT * 4 + kEpiWarps * kEpiStageBytesPerWarp + 256;   // scale/shift/stats + patches + barriers
@@ -77,9 +79,10 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
-template <int BN, int BKB>
+template <int BN, int BKB, bool CTA2 = false>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN, BKB>;
+  using Cfg = ConvCfg<BN, BKB, CTA2>;
+  constexpr uint32_t NCTA = CTA2 ? 2 : 1;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int KSTEPS = BKB / 32;   // tcgen05.mma instructions (K = 16 bf16 = 32 bytes) per K-block
 
@@ -104,6 +107,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_src0);
@@ -117,11 +122,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 4);   // one arrive per epilogue warp of the set that owns the buffer
+      mbar_init(bar_acc_empty + 8 * i, 4 * NCTA);   // one arrive per epilogue warp of the set that owns the buffer (both CTAs of a pair)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(s_tmem_slot);
+  if (warp == 2) { if (CTA2) tmem_alloc_2sm<Cfg::TMEM_COLS>(s_tmem_slot); else tmem_alloc<Cfg::TMEM_COLS>(s_tmem_slot); }
   for (int i = threadIdx.x; i < p.ntot; i += kConvThreads) {
     if (p.scale) g_scale[i] = __ldg(p.scale + i);      // null: scale == 1 / shift == 0, the epilogue skips the loads
     if (p.shift) g_shift[i] = __ldg(p.shift + i);
@@ -130,12 +135,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   pdl_launch_dependents();
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.batch;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = (CTA2 ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;     // CTA2: work items are PAIRS of M tiles
+  const int first_tile = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kb_per_tap = p.kb0 + p.kb1;
   const int num_kb = p.ntaps * kb_per_tap;
   constexpr int KELEMS = BKB / 2;   // channels per K-block
@@ -146,9 +154,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       pdl_wait();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         uint32_t mt, nt, trow, tx, b, ty;
         fdivmod((uint32_t)tile, p.fd_ntiles, mt, nt);
+        if (CTA2) { mt = 2 * mt + rank; if ((int)mt >= m_tiles) mt = m_tiles - 1; }   // odd tail: the peer re-loads the last tile
         fdivmod(mt, p.fd_tx, trow, tx);
         fdivmod(trow, p.fd_ty, b, ty);
         const int x0 = tx * p.tw, y0 = ty * p.th;
@@ -162,27 +171,38 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
             const uint32_t sa = s_stage + stage * Cfg::STAGE_BYTES;
             const uint32_t sb = sa + Cfg::A_BYTES;
             const uint32_t fb = bar_full + 8 * stage;
-            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-            if (p.src5)
-              tma_load_5d(sa, &p.tm_src0, fb, cb * KELEMS, x0, t, y0, b);
-            else if (cb < p.kb0)
-              tma_load_4d(sa, &p.tm_src0, fb, cb * KELEMS, xs, ys, b);
-            else
-              tma_load_4d(sa, &p.tm_src1, fb, (cb - p.kb0) * KELEMS, xs - p.off_x, ys - p.off_y, b);
-            tma_load_2d(sb, &p.tm_w, fb, kidx * KELEMS, nt * BN);
+            if (leader) mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES * NCTA);   // both CTAs' boxes land on the leader's barrier
+            if (CTA2) {
+              if (p.src5)
+                tma_load_5d_2sm(sa, &p.tm_src0, fb, cb * KELEMS, x0, t, y0, b);
+              else if (cb < p.kb0)
+                tma_load_4d_2sm(sa, &p.tm_src0, fb, cb * KELEMS, xs, ys, b);
+              else
+                tma_load_4d_2sm(sa, &p.tm_src1, fb, (cb - p.kb0) * KELEMS, xs - p.off_x, ys - p.off_y, b);
+              tma_load_2d_2sm(sb, &p.tm_w, fb, kidx * KELEMS, nt * BN + (int)rank * Cfg::BN_CTA);
+            } else {
+              if (p.src5)
+                tma_load_5d(sa, &p.tm_src0, fb, cb * KELEMS, x0, t, y0, b);
+              else if (cb < p.kb0)
+                tma_load_4d(sa, &p.tm_src0, fb, cb * KELEMS, xs, ys, b);
+              else
+                tma_load_4d(sa, &p.tm_src1, fb, (cb - p.kb0) * KELEMS, xs - p.off_x, ys - p.off_y, b);
+              tma_load_2d(sb, &p.tm_w, fb, kidx * KELEMS, nt * BN);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
+   if (leader) {
     // ===================================================== MMA issuer (warp converged; one elected lane issues)
-    constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
+    constexpr uint32_t idesc = CTA2 ? make_idesc_bf16_m256(BN) : make_idesc_bf16_m128(BN);
     constexpr uint32_t desc_hi = ((8u * BKB) >> 4) | (1u << 14) | ((BKB == 128 ? 2u : 6u) << 29);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
@@ -198,15 +218,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < KSTEPS; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle span: +2 in the >>4 address field
-            umma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (k != 0) ? 1u : (uint32_t)(kb != 0));
+            if (CTA2) umma_bf16_lohi_2sm(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (k != 0) ? 1u : (uint32_t)(kb != 0));
+            else umma_bf16_lohi(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (k != 0) ? 1u : (uint32_t)(kb != 0));
           }
-          umma_commit(bar_empty + 8 * stage);   // frees the smem stage once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(bar_acc_full + 8 * acc);
+          // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+          if (CTA2) umma_commit_2sm(bar_empty + 8 * stage); else umma_commit(bar_empty + 8 * stage);
+          if (kb == num_kb - 1) { if (CTA2) umma_commit_2sm(bar_acc_full + 8 * acc); else umma_commit(bar_acc_full + 8 * acc); }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+   }
   } else {
     // ===================================================== epilogue (warps 2..9): quadrant q = warp % 4, set = (warp-2)/4
     // (the two sets of four warps drain alternate tiles = one set per TMEM accumulator buffer)
@@ -220,12 +243,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     const bool hx = lane & 1, hy = (lane & p.tw) != 0;   // pooling needs tw in {8, 16}: both window rows in one warp
     int it = 0;
     pdl_wait();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;
       if (acc != eset) continue;
       const uint32_t acc_phase = (it >> 1) & 1;
       uint32_t mt, nt, trow, tx, b, ty;
       fdivmod((uint32_t)tile, p.fd_ntiles, mt, nt);
+      if (CTA2) mt = 2 * mt + rank;
+      if (CTA2 && (int)mt >= m_tiles) {       // odd tail: this CTA's half of the pair is a duplicate -- hand the buffer back
+        mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * acc);
+        continue;
+      }
       fdivmod(mt, p.fd_tx, trow, tx);
       fdivmod(trow, p.fd_ty, b, ty);
       const int y = ty * p.th + ly, x = tx * p.tw + lx;
@@ -270,16 +301,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       // accumulator fully read -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+      if (lane == 0) { if (CTA2) mbar_arrive_leader(bar_acc_empty + 8 * acc); else mbar_arrive(bar_acc_empty + 8 * acc); }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();
   if (p.stats) {
     for (int i = threadIdx.x; i < 2 * p.ntot; i += kConvThreads) atomicAdd(p.stats + i, g_stats[i]);
   }
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == 2) { if (CTA2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base); else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 
 }  // namespace gsd

@@ -365,6 +365,35 @@ def test_conv3x3_halo_kernel_cta_pair(cin, cin1, cout, h, w, b, pool, block_n, m
         assert torch.equal(single, pair)
 
 
+@pytest.mark.parametrize("cin,cin1,cout,h,w,b,pool,bn", [
+    (128, 0, 256, 20, 26, 3, False, 256),   # 20x26 bottleneck shape, N = 256: 128 weight rows per CTA
+    (64, 64, 128, 10, 13, 1, False, 128),   # virtual concat with padding, 2 tiles = one pair
+    (64, 0, 128, 21, 27, 1, True, 128),     # fused max-pool; 6 tiles... odd counts leave a duplicate peer tile
+    (128, 0, 128, 17, 9, 3, False, 128)])   # 3 x 1 x 3 = 9 tiles: the last pair's peer is a duplicate
+def test_conv_tc_kernel_cta_pair(cin, cin1, cout, h, w, b, pool, bn, monkeypatch):
+    """CTA-pair variant of the tap-streaming conv (csrc/conv_tc.cuh, cta_group::2): bit-identical to single CTAs."""
+    from gelslim_depth_b200.engine import conv_op
+    g = torch.Generator().manual_seed(cin + cout + h)
+    ct = cin + cin1
+    x = bf16r(torch.randn(b, ct, h, w, generator=g))
+    wt = bf16r(torch.randn(cout, ct, 3, 3, generator=g) * (2.0 / (9 * ct)) ** 0.5)
+    sc, sh = 0.5 + torch.rand(cout, generator=g), 0.3 * torch.randn(cout, generator=g)
+    ref = torch.relu(F.conv2d(x, wt, padding=1) * sc[None, :, None, None] + sh[None, :, None, None])
+    d = dev()
+    xs = nhwc(x).to(torch.bfloat16).to(d)
+    s0 = xs[..., :cin].contiguous()
+    s1 = xs[..., cin:].contiguous() if cin1 else None
+    results = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("GSD_CTA2", mode)
+        r = conv_op(s0, pack_w3(wt).to(d), sc.to(d), sh.to(d), TAPS3, relu=True, src1=s1, pool=pool, block_n=bn)
+        torch.cuda.synchronize()
+        results[mode] = r if pool else (r,)
+    check_close(results["2"][0].permute(0, 3, 1, 2), ref, "tap-streaming conv3x3, CTA pair")
+    for single, pair in zip(results["0"], results["2"]):
+        assert torch.equal(single, pair)
+
+
 def test_first_layer_halo_kernel():
     """inc.double_conv.0 through the SW32 / 16-channel variant of the halo kernel."""
     from gelslim_depth_b200.engine import conv3x3_halo_op

@@ -33,8 +33,7 @@ if len(sys.argv) > 1:
 else:
     import torch
     configs = [("0", {}), ("1", {})] if len(sys.argv) == 1 else []
-    configs = [("1", {}), ("1", {"GSD_NB_MAX": "18"}), ("1", {"GSD_NB_MAX": "18", "GSD_NA": "6"}),
-               ("1", {"GSD_NB_MAX": "27", "GSD_NA": "5"}), ("1", {"GSD_NB_MAX": "6"}), ("0", {})]
+    configs = [("1", {}), ("2", {"GSD_WRES0": "1"}), ("1", {"GSD_WRES0": "1"}), ("2", {})]
     ref = None
     for i, (mode, extra) in enumerate(configs):
         env = dict(os.environ, GSD_CTA2=mode, **extra)
