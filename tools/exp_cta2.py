@@ -8,10 +8,7 @@ if len(sys.argv) > 1:
     from gelslim_depth_b200.engine import make_prepost
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    net = UNet(6, 2)
-    import oracle
-    net.load_state_dict(oracle.conditioned_state_dict(net.state_dict(), seed=1))
-    net = net.to(dev).eval()
+    net = UNet(6, 2).to(dev).eval()       # default init: timing and bit-equality do not need a conditioned checkpoint
     H, W, B = 320, 427, 64
     g = torch.Generator().manual_seed(5)
     base = torch.randint(0, 256, (1, 6, H, W), dtype=torch.uint8, generator=g).float().to(dev)
