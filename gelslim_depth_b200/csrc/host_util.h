@@ -58,10 +58,17 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// gsd_debug_plan_* (CPU tests of the launch rules): plan a launch without a GPU or driver -- tensor maps are skipped
+inline bool& plan_only_mode() {
+  static thread_local bool on = false;
+  return on;
+}
+
 // bf16 tensor map, `rank` dims (innermost first), byte strides for dims 1..rank-1, all-ones element strides,
 // zero fill out of bounds.
 inline int encode_bf16_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box, CUtensorMapSwizzle swz, bool weights) {
+  if (plan_only_mode()) return 0;
   PFN_encodeTiled fn = get_encode_fn();
   GSD_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gd[5] = {1, 1, 1, 1, 1};

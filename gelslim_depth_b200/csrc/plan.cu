@@ -235,6 +235,19 @@ extern "C" int gsd_plan_set_chunk_ramp(gsd_plan* p, int first_frames, int last_f
   p->bound_ws = nullptr;
   return 0;
 }
+// chunk schedule of gsd_forward_host for (batch, chunk, first, last) without a plan or a GPU (CPU tests)
+extern "C" int gsd_debug_chunk_schedule(int batch, int chunk, int first, int last, int* out, int capacity) {
+  GSD_CHECK(out && batch >= 1 && chunk >= 1 && first >= 0 && last >= 0, "gsd_debug_chunk_schedule: bad argument");
+  gsd_plan tmp;
+  tmp.g.batch = batch;
+  tmp.chunk = chunk > batch ? batch : chunk;
+  tmp.chunk_first = first;
+  tmp.chunk_last = last;
+  const std::vector<int> v = chunk_schedule(&tmp);
+  GSD_CHECK((int)v.size() <= capacity, "gsd_debug_chunk_schedule: %d chunks do not fit %d slots", (int)v.size(), capacity);
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+  return (int)v.size();
+}
 extern "C" double gsd_plan_conv_flops(const gsd_plan* p) { return p ? p->conv_flops : 0; }
 
 extern "C" int gsd_pack_weights(gsd_plan* p, const void* const* params, const void* const* bn, void* packed,

@@ -42,6 +42,39 @@ extern "C" int gsd_op_conv_auto_bf16(const void* src0, int C0, const void* src1,
   return run_conv_launch(L, st);
 }
 
+// Launch planning without a GPU (tests/test_host_rules_cpu.py): which kernel and configuration a 3x3 conv layer gets.
+// out[0] = 1 halo-resident / 0 tap-streaming kernel, [1] N per UMMA, [2] M tiles per item, [3] resident weights,
+// [4] epilogue warps, [5] CTA pair, [6] halo ring, [7] weight ring, [8] dynamic smem bytes, [9] grid, [10] tile h, [11] tile w
+extern "C" int gsd_debug_plan_conv3x3(int B, int H, int W, int C0, int C1, int Cout, int num_sms, int* out) {
+  GSD_CHECK(out && B >= 1 && H >= 1 && W >= 1 && num_sms >= 1, "gsd_debug_plan_conv3x3: bad argument");
+  ConvDesc d;
+  void* dummy = reinterpret_cast<void*>(static_cast<uintptr_t>(256));
+  d.src0 = dummy; d.C0 = C0; d.src1 = C1 ? dummy : nullptr; d.C1 = C1; d.H1 = H; d.W1 = W;
+  d.B = B; d.H = H; d.W = W; d.w = dummy; d.Cout = Cout; d.groups = 1;
+  taps3x3(&d);
+  d.out = dummy;
+  for (int i = 0; i < 12; ++i) out[i] = 0;
+  plan_only_mode() = true;
+  int rc = 0;
+  if (prefer_halo(d, num_sms)) {
+    HaloLaunch L;
+    rc = build_halo_launch(d, num_sms, &L);
+    if (rc == 0) {
+      const int v[12] = {1, L.bn, L.mt, L.wres, L.nepi, L.cta2, L.p.na, L.p.nb, L.smem, L.grid, 16, 8};
+      for (int i = 0; i < 12; ++i) out[i] = v[i];
+    }
+  } else {
+    ConvLaunch L;
+    rc = build_conv_launch(d, num_sms, &L);
+    if (rc == 0) {
+      const int v[12] = {0, L.bn, 1, 0, kEpiWarps, L.cta2, 0, 0, 0, L.grid, L.p.th, L.p.tw};
+      for (int i = 0; i < 12; ++i) out[i] = v[i];
+    }
+  }
+  plan_only_mode() = false;
+  return rc;
+}
+
 // Transposed-conv input gradient: d_in[b,y,x,ci] = sum_{gy,gx,co} dU[b,2y+gy,2x+gx,co] Wt[ci,co,gy,gx]
 // du: dense (B,Hf,Wf,Cs) bf16 with the up-sampled map's gradient at offset (off_y, off_x); w: bf16 [Cin][(gy,gx,co)].
 extern "C" int gsd_op_convt_dgrad_bf16(const void* du, int Cs, int Hf, int Wf, int off_y, int off_x, const void* w, int Cin,

@@ -146,6 +146,16 @@ int gsd_forward_profiled(gsd_plan* p, const void* x, const float* base, const gs
                          void* workspace, const void* packed, void* stream, float* ms_host,
                          double* flops_host, int capacity, int* n_out);
 
+/* --- launch planning without a GPU (host-logic tests, tests/test_host_rules_cpu.py) -------------- */
+/* Which kernel and configuration a conv3x3 layer (C0 [+ C1 concat] -> Cout at HxW, batch B) gets on a device with
+ * `num_sms` SMs.  out[12] = {halo-resident (1) or tap-streaming (0) kernel, N per UMMA, M tiles per work item,
+ * resident weights, epilogue warps, CTA pair (cta_group::2), halo ring depth, weight ring depth, dynamic smem bytes,
+ * grid, tile height, tile width}.  Touches neither the GPU nor the driver. */
+int gsd_debug_plan_conv3x3(int B, int H, int W, int C0, int C1, int Cout, int num_sms, int* out);
+/* Chunk sizes gsd_forward_host would use for (batch, gsd_plan_set_chunk, gsd_plan_set_chunk_ramp); returns the
+ * number of chunks written to out[capacity] (negative = error). */
+int gsd_debug_chunk_schedule(int batch, int chunk, int first, int last, int* out, int capacity);
+
 /* --- single operators (used by the parity tests; the plan is built from exactly these) ---------- */
 /* conv KxK (taps given explicitly) as implicit GEMM on tcgen05, NHWC bf16.
  *   src0:(B,H,W,C0) [+ src1:(B,H1,W1,C1) placed at offset (off_y, off_x), zero elsewhere -> virtual
