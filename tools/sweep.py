@@ -3,7 +3,7 @@
 same plan on its own shard of the batch with no data-path collective; the time of a point is the max over ranks (NCCL is
 used for the barrier and that max only).  Device-resident frames, plus (batch 64 per GPU) the blocking and the
 rotating-slot host pipelines.  Rank 0 prints one JSON line per total batch."""
-import json, os, sys, time
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
