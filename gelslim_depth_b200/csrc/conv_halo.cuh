@@ -12,9 +12,12 @@
 // output channels with small K) or streamed through a ring and shared by MT=2 output tiles (M = 256
 // per CTA), which halves their traffic.
 //
-// Epilogue: tcgen05.ld -> scale/shift (folded BatchNorm) -> ReLU -> bf16 -> 16-byte global stores
-// straight from registers (each thread owns one pixel = 128 contiguous bytes per 64 channels); the
-// fused 2x2 max-pool is two warp shuffles (the 4 pixels of a window live in lanes l, l^1, l^8, l^9).
+// Epilogue (epilogue.cuh): tcgen05.ld -> scale/shift (folded BatchNorm, packed fp32) -> ReLU folded into the bf16
+// conversion -> per-warp swizzled smem transposition -> 16-byte global stores in which four lanes cover one pixel's
+// 64 bytes; the fused 2x2 max-pool is 12 warp shuffles (the 4 pixels of a window live in lanes l, l^1, l^8, l^9).
+//
+// CTA pairs (template parameter CTA2): clusters of two CTAs issue every MMA together
+// (tcgen05.mma.cta_group::2, M = 256), each CTA staging half of the weight rows.
 #pragma once
 #include <cuda_bf16.h>
 
