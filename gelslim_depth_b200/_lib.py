@@ -49,6 +49,7 @@ SYMBOLS = {
     "gsd_plan_set_chunk": (C.c_int, [C.c_void_p, C.c_int]),
     "gsd_plan_set_chunk_ramp": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "gsd_plan_conv_flops": (C.c_double, [C.c_void_p]),
+    "gsd_plan_first_fused": (C.c_int, [C.c_void_p]),
     "gsd_pack_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "gsd_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p]),

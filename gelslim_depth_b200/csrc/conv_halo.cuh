@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "bias_mma.cuh"
 #include "epilogue.cuh"
 #include "gsd_ptx.cuh"
 
@@ -34,6 +35,8 @@ struct HaloParams {
   CUtensorMap tm_w;      // (9*(C0+C1), Cout) bf16, box (BKB/2, BN)
   const float* scale;    // [Cout]
   const float* shift;    // [Cout]
+  const float* bias;     // [Cout] or null: additive constant applied by one extra UMMA per tile (bias_mma.cuh) instead of
+                         //   the epilogue; needs Cout == BN (a single N tile); scale / shift are then normally null
   __nv_bfloat16* out;    // (B, H, W, Cout) or null (head-only)
   __nv_bfloat16* pooled; // (B, H/2, W/2, Cout) or null
   // fused OutConv 1x1 + bias + depth de-normalisation (unet.py:54, normalization_utils.py:129); Cout == BN == 64
@@ -90,7 +93,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
   const int na = p.na, nb = WRES ? 0 : p.nb;
   const uint32_t s_a = smem_base;
   const uint32_t s_b = s_a + na * G::BUF_BYTES;                        // B ring, or the resident weights
-  const uint32_t s_aux = s_b + (WRES ? nkb : nb) * B_BYTES;
+  const uint32_t s_bias = s_b + (WRES ? nkb : nb) * B_BYTES;          // 1 KB aligned; present only with p.bias
+  const uint32_t s_aux = s_bias + (p.bias ? kBiasOnesBytes + 64 * 32 : 0);
   float* g_scale = reinterpret_cast<float*>(smem_gen + (s_aux - smem_base));   // [Cout] (<= 1024)
   float* g_shift = g_scale + p.Cout;
   float* g_head = g_shift + p.Cout;                                    // [4][64] + [4]
@@ -129,6 +133,10 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
     if (p.shift) g_shift[i] = __ldg(p.shift + i);
     g_stats[i] = 0.f;
     g_stats[p.Cout + i] = 0.f;
+  }
+  if (p.bias) {
+    bias_mma_fill(s_bias, p.bias + rank * BN_CTA, BN_CTA, threadIdx.x, kHaloThreads);
+    fence_proxy_async_smem();
   }
   if (p.head_w) {
     for (int i = threadIdx.x; i < p.head_ncls * 64; i += kHaloThreads) g_head[i] = __ldg(p.head_w + i);
@@ -206,6 +214,14 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
       const int buf = it & 1;
       mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
+      const bool bias_mma = p.bias != nullptr;
+      if (bias_mma) {          // D = 1 x bias^T first; every tap then accumulates
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < MT; ++j) bias_mma_issue<CTA2>(tmem_base + (buf * MT + j) * BN, s_bias, idesc);
+        }
+        __syncwarp();
+      }
       for (int cb = 0; cb < cbt; ++cb) {
         uint32_t a_lo[MT];     // low word of the halo descriptor at tap (0,0), k = 0
         int a_slot[MT];
@@ -241,10 +257,10 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
                 for (int k = 0; k < G::KSTEPS; ++k) {
                   if (CTA2)
                     umma_bf16_lohi_2sm(d_tmem, (a0 + 2 * k) | (1u << 16), G::A_HI, (b_lo + 2 * k) | (1u << 16), G::B_HI, idesc,
-                                       (k != 0) ? 1u : (uint32_t)((cb | tap) != 0));
+                                       (k != 0) ? 1u : (uint32_t)(((cb | tap) != 0) || bias_mma));
                   else
                     umma_bf16_lohi(d_tmem, (a0 + 2 * k) | (1u << 16), G::A_HI, (b_lo + 2 * k) | (1u << 16), G::B_HI, idesc,
-                                   (k != 0) ? 1u : (uint32_t)((cb | tap) != 0));
+                                   (k != 0) ? 1u : (uint32_t)(((cb | tap) != 0) || bias_mma));
                 }
               }
               if (!WRES) { if (CTA2) umma_commit_2sm(bar_emptyB + 8 * ib); else umma_commit(bar_emptyB + 8 * ib); }

@@ -13,6 +13,7 @@ namespace gsd {
 
 struct ConvDesc {
   const void* src0 = nullptr; int C0 = 0;                    // (B,H,W,C0) bf16
+  int C0_real = 0;             // channels that carry data (first layer: 3 / 6 of the 16 stored); 0 = C0.  FLOP accounting only
   const void* src1 = nullptr; int C1 = 0, H1 = 0, W1 = 0;    // (B,H1,W1,C1) bf16, placed at (off_y, off_x)
   int off_y = 0, off_x = 0;
   int B = 0, H = 0, W = 0;
@@ -30,6 +31,7 @@ struct ConvDesc {
   const float* head_w = nullptr; const float* head_b = nullptr; float* head_y = nullptr;
   float head_scale = 1.f, head_shift = 0.f; int head_ncls = 0;
   float* stats = nullptr;      // [2][groups*Cout] fp32, accumulated (caller zeroes): sum / sum of squares of the raw output
+  const float* bias = nullptr; // halo kernel, Cout == 64: additive constant applied by the tensor core (bias_mma.cuh)
   // transposed-conv INPUT gradient: src0 is a dense (B, Hf, Wf, Cs) tensor holding the gradient of the (2H x 2W)
   // up-sampled map at offset (s2d_off_y, s2d_off_x); C0 must be 2*Cs, ntaps 2 (gy), the output domain is H x W.
   int s2d = 0, s2d_Hf = 0, s2d_Wf = 0, s2d_off_y = 0, s2d_off_x = 0;
@@ -189,7 +191,7 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
     const long pairs_total = (long)((m_tiles + 1) / 2) * p.n_tiles;
     L->grid = (int)(2 * (pairs_total < num_sms / 2 ? pairs_total : num_sms / 2));
   }
-  L->flops = 2.0 * d.B * d.H * d.W * (double)ntot * d.ntaps * (d.C0 + d.C1);
+  L->flops = 2.0 * d.B * d.H * d.W * (double)ntot * d.ntaps * ((d.C0_real ? d.C0_real : d.C0) + d.C1);   // the real (unpadded) problem
   return 0;
 }
 
@@ -300,6 +302,8 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   p.head_w = d.head_w; p.head_b = d.head_b; p.head_y = d.head_y;
   p.head_scale = d.head_scale; p.head_shift = d.head_shift; p.head_ncls = d.head_ncls;
   p.stats = d.stats;
+  p.bias = d.bias;
+  GSD_CHECK(!d.bias || d.Cout == 64, "halo conv: the tensor-core bias needs Cout == 64 (one N tile)");
   GSD_CHECK(!d.head_w || (d.Cout == 64 && d.head_ncls >= 1 && d.head_ncls <= 4 && d.head_y && d.head_b),
             "halo conv: fused 1x1 head needs Cout == 64 and 1..4 classes");
   GSD_CHECK(d.out || d.head_w, "halo conv: no output requested");
@@ -358,7 +362,7 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     L->cta2 = (bkb == 128 && num_sms % 2 == 0 &&
                (cta2_mode == 2 || (cta2_mode == 1 && (bn >= 128 || pair64) && pair_items >= num_sms / 2))) ? 1 : 0;
   }
-  const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048;
+  const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048 + (d.bias ? kBiasOnesBytes + 64 * 32 : 0);
   const int b_bytes = (L->cta2 ? bn / 2 : bn) * bkb;
   if (wres) {
     p.nb = 0;
@@ -406,14 +410,14 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     const long pair_items = (((m_tiles + mt - 1) / mt + 1) / 2) * p.n_tiles;
     const long pairs = pair_items < num_sms / 2 ? pair_items : num_sms / 2;
     L->grid = (int)(2 * pairs);
-    L->flops = 2.0 * d.B * d.H * d.W * (double)d.Cout * 9 * (d.C0 + d.C1);
+    L->flops = 2.0 * d.B * d.H * d.W * (double)d.Cout * 9 * ((d.C0_real ? d.C0_real : d.C0) + d.C1);
     return 0;
   }
   // the first-layer variant (16-channel rows) is epilogue-latency-bound: two co-resident CTAs per SM (78 KB smem, 96
   // registers, 128 TMEM columns each) double the warps the schedulers can pick from
   const long ctas = (long)num_sms * (bkb == 32 ? 2 : 1);
   L->grid = (int)(items < ctas ? items : ctas);
-  L->flops = 2.0 * d.B * d.H * d.W * (double)d.Cout * 9 * (d.C0 + d.C1);
+  L->flops = 2.0 * d.B * d.H * d.W * (double)d.Cout * 9 * ((d.C0_real ? d.C0_real : d.C0) + d.C1);
   return 0;
 }
 
@@ -441,6 +445,64 @@ inline int run_halo_launch(const HaloLaunch& L, cudaStream_t st) {
   if (L.bn == 128 && L.mt == 2 && !L.wres) return launch_halo_cfg<128, 2, false, 128, 8>(L, st);
   if (L.bn == 256 && L.mt == 1 && !L.wres) return launch_halo_cfg<256, 1, false, 128, 8>(L, st);
   return fail(-1, "halo conv: no kernel for bn=%d mt=%d wres=%d nepi=%d", L.bn, L.mt, L.wres, L.nepi);
+}
+
+}  // namespace gsd
+
+// ------------------------------------------------------------------------------------------------
+// First conv with the fused input prologue (conv_first.cuh) host side
+#include "conv_first.cuh"
+
+namespace gsd {
+
+constexpr int kFirstNPRO = 7, kFirstNSET = 4;
+
+struct FirstLaunch {
+  FirstParams p;
+  int grid = 0, smem = 0, cmax = 8;
+  double flops = 0;
+};
+
+// w: bf16 [64][9][16] (the TMA-fed first layer's operand), out: (B,H,W,64) bf16.  `pre` is filled per call.
+inline int build_first_launch(const void* w, const float* bias, void* out, int B, int H, int W, int cin_real, int num_sms, FirstLaunch* L) {
+  memset(L, 0, sizeof *L);
+  FirstParams& p = L->p;
+  p.bias = bias; p.out = static_cast<__nv_bfloat16*>(out);
+  p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16; p.batch = B; p.H = H; p.W = W;
+  p.relu = 1;
+  p.na = 8;
+  if (const char* e = getenv("GSD_FIRST_NA")) p.na = atoi(e);        // tuning experiments only
+  p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
+  const long items = (long)p.tiles_x * p.tiles_y * B;
+  GSD_CHECK(items < (1L << 24) && p.tiles_x < 4096 && p.tiles_y < 4096, "first conv: too many tiles for the 24-bit tile index");
+  GSD_CHECK((long)B * H * W < (1L << 31) / 64, "first conv: output too large for 32-bit pixel arithmetic");
+  {
+    uint64_t dims[2] = {9ull * 16, 64};
+    uint64_t str[1] = {9ull * 16 * 2};
+    uint32_t box[2] = {16, 64};
+    GSD_TRY(encode_bf16_map(&p.tm_w, const_cast<void*>(w), 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B, true));
+  }
+  L->grid = (int)(items < num_sms ? items : num_sms);
+  L->smem = p.na * kFirstBuf + kFirstWBytes + kBiasOnesBytes + 64 * 32 + 4 * kFirstNSET * kEpiStageBytesPerWarp + 16 * p.na +
+            16 * kFirstNSET + 64 + 1024;
+  L->flops = 2.0 * B * H * W * 64.0 * 9 * cin_real;
+  L->cmax = cin_real;
+  GSD_CHECK(cin_real == 3 || cin_real == 6, "first conv: the fused prologue is built for 3 or 6 input channels");
+  return 0;
+}
+
+template <int C, int KIND>
+inline int launch_first_cfg(const FirstLaunch& L, cudaStream_t st) {
+  static SmemAttrCache attr_cache;
+  GSD_TRY(attr_cache.ensure(conv_first_kernel<kFirstNPRO, kFirstNSET, C, KIND>, L.smem));
+  // never a programmatic dependent launch: it is the first kernel of a forward and must see completed uploads
+  return launch_maybe_pdl(conv_first_kernel<kFirstNPRO, kFirstNSET, C, KIND>, L.p, L.grid, 32 * (1 + kFirstNPRO + 4 * kFirstNSET), L.smem, st, 0);
+}
+
+inline int run_first_launch(const FirstLaunch& L, cudaStream_t st) {
+  const int kind = L.p.pre.input_u8;
+  if (L.cmax == 3) return kind == 0 ? launch_first_cfg<3, 0>(L, st) : kind == 1 ? launch_first_cfg<3, 1>(L, st) : launch_first_cfg<3, 2>(L, st);
+  return kind == 0 ? launch_first_cfg<6, 0>(L, st) : kind == 1 ? launch_first_cfg<6, 1>(L, st) : launch_first_cfg<6, 2>(L, st);
 }
 
 }  // namespace gsd

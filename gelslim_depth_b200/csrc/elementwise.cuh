@@ -303,6 +303,19 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int 
     out[idx] = __float2bfloat16_rn(i < I ? w[((long)o * I + i) * taps + t] : 0.f);
   }
 }
+// The same with the eval-mode BatchNorm scale folded in: bf16(w * gamma[o] / sqrt(var[o] + eps)) -- conv(x, w*s) + shift ==
+// (conv(x, w) - mean) * s + beta (unet.py:11-12), so the conv epilogue only adds (plan.cu, bf16 inference plans).
+__global__ void pack_conv_weight_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ var,
+                                           float eps, int O, int I, int taps, int Ipad, __nv_bfloat16* __restrict__ out) {
+  const long total = (long)O * taps * Ipad;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % Ipad);
+    const int t = (int)((idx / Ipad) % taps);
+    const int o = (int)(idx / ((long)Ipad * taps));
+    const float sc = gamma[o] * rsqrtf(var[o] + eps);          // identical expression to fold_bn_kernel's scale
+    out[idx] = __float2bfloat16_rn(i < I ? w[((long)o * I + i) * taps + t] * sc : 0.f);
+  }
+}
 // ConvTranspose2d weight (I, O, 2, 2) fp32 -> bf16 [(dy*2+dx)*O + o][I]
 __global__ void pack_convt_weight_kernel(const float* __restrict__ w, int I, int O, __nv_bfloat16* __restrict__ out) {
   const long total = 4L * O * I;

@@ -36,6 +36,8 @@ struct ChunkLaunches {
   int b0 = 0, nb = 0;
   std::vector<AnyLaunch> convs;
   std::vector<F32Step> f32;
+  int has_first = 0;          // convs[0] also exists as the prologue-fused first conv (conv_first.cuh)
+  FirstLaunch first;
 };
 
 }  // namespace
@@ -70,6 +72,7 @@ struct gsd_plan {
   bool slot_used[kHostSlots] = {};
   double conv_flops = 0;
   int head_fused = 0;          // 1x1 head + de-normalisation folded into the last conv's epilogue
+  int first_fused = 1;         // the last forward ran the input prologue inside the first conv (no prologue launch)
 };
 
 static size_t bump(size_t* cur, size_t bytes) {
@@ -219,7 +222,7 @@ static std::vector<int> chunk_schedule(const gsd_plan* p) {
 extern "C" int gsd_plan_forward_launches(const gsd_plan* p) {
   if (!p) return 0;
   const int nchunks = (int)chunk_schedule(p).size();
-  return nchunks * (1 + 2 * (p->depth + 1) + 3 * p->depth + (p->head_fused ? 0 : 1));   // + area resample when sizes differ
+  return nchunks * ((p->first_fused ? 0 : 1) + 2 * (p->depth + 1) + 3 * p->depth + (p->head_fused ? 0 : 1));   // + area resample when sizes differ
 }
 extern "C" int gsd_plan_set_chunk(gsd_plan* p, int frames_per_chunk) {
   GSD_CHECK(p && frames_per_chunk >= 1, "gsd_plan_set_chunk: bad argument");
@@ -249,6 +252,7 @@ extern "C" int gsd_debug_chunk_schedule(int batch, int chunk, int first, int las
   return (int)v.size();
 }
 extern "C" double gsd_plan_conv_flops(const gsd_plan* p) { return p ? p->conv_flops : 0; }
+extern "C" int gsd_plan_first_fused(const gsd_plan* p) { return p ? p->first_fused : 0; }
 
 extern "C" int gsd_pack_weights(gsd_plan* p, const void* const* params, const void* const* bn, void* packed,
                                 void* stream) {
@@ -267,9 +271,9 @@ extern "C" int gsd_pack_weights(gsd_plan* p, const void* const* params, const vo
     const long total = (long)c.cout * c.taps * c.cin_pad;
     if (p->g.dtype == GSD_DTYPE_FP32)
       pack_conv_weight_f32_kernel<<<ew_grid(total), 256, 0, st>>>(w, c.cout, c.cin, c.taps, reinterpret_cast<float*>(base + c.w_off));
-    else
-      pack_conv_weight_kernel<<<ew_grid(total), 256, 0, st>>>(w, c.cout, c.cin, c.taps, c.cin_pad,
-                                                               reinterpret_cast<__nv_bfloat16*>(base + c.w_off));
+    else   // bf16: the BatchNorm scale gamma / sqrt(var + eps) is folded into the operand, only the shift is left for the conv
+      pack_conv_weight_bn_kernel<<<ew_grid(total), 256, 0, st>>>(w, gamma, var, 1e-5f, c.cout, c.cin, c.taps, c.cin_pad,
+                                                                  reinterpret_cast<__nv_bfloat16*>(base + c.w_off));
     fold_bn_kernel<<<(c.cout + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, c.cout, 1e-5f,
                                                          reinterpret_cast<float*>(base + c.scale_off),
                                                          reinterpret_cast<float*>(base + c.shift_off));
@@ -316,6 +320,9 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
   char* W = static_cast<char*>(ws);
   const char* P = static_cast<const char*>(packed);
   auto fptr = [&](size_t off) { return reinterpret_cast<const float*>(P + off); };
+  // bf16 plans carry the BatchNorm scale inside the packed weights (gsd_pack_weights) and the transposed convs' scale is
+  // 1: the epilogue applies no per-channel scale at all; the fp32 parity mode keeps the reference's order of operations
+  auto bn_scale = [&](size_t off) { return g.dtype == GSD_DTYPE_FP32 ? fptr(off) : static_cast<const float*>(nullptr); };
   const std::vector<int> schedule = chunk_schedule(p);
   int b0 = 0;
   for (size_t ci = 0; ci < schedule.size(); b0 += schedule[ci], ++ci) {
@@ -354,6 +361,9 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       const int pdl = getenv("GSD_NO_PDL") ? 0 : 1;
       if (use_halo(d)) {
         A.halo = 1;
+        // 64-channel layers are bound by the smem data pipe (operand reads + epilogue constants): their additive constant
+        // goes through one extra UMMA per tile instead (bias_mma.cuh) and the epilogue loads no constants at all
+        if (d.Cout == 64 && d.shift && !d.scale && !getenv("GSD_NO_BIAS_MMA")) { d.bias = d.shift; d.shift = nullptr; }
         GSD_TRY(build_halo_launch(d, p->num_sms, &A.hl));
         A.hl.pdl = pdl;
         A.flops = A.hl.flops;
@@ -372,19 +382,24 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       ConvDesc d0;
       taps3x3(&d0);
       d0.B = ch.nb; d0.H = h; d0.W = w;
-      if (l == 0) { d0.C0 = g.dtype == GSD_DTYPE_FP32 ? g.in_channels : 16; d0.src0 = act(p->in16_off, h, w, d0.C0); }
+      if (l == 0) { d0.C0 = g.dtype == GSD_DTYPE_FP32 ? g.in_channels : 16; d0.C0_real = g.in_channels; d0.src0 = act(p->in16_off, h, w, d0.C0); }
       else { d0.src0 = act(p->p_off[l - 1], h, w, g.dims[l - 1]); d0.C0 = g.dims[l - 1]; }
       const ConvW& c0 = p->enc[2 * l];
-      d0.w = P + c0.w_off; d0.scale = fptr(c0.scale_off); d0.shift = fptr(c0.shift_off);
+      d0.w = P + c0.w_off; d0.scale = bn_scale(c0.scale_off); d0.shift = fptr(c0.shift_off);
       d0.Cout = g.dims[l]; d0.relu = 1;
       d0.out = act(p->a_off[l], h, w, g.dims[l]);
       GSD_TRY(add(d0));
+      if (l == 0 && g.dtype == GSD_DTYPE_BF16 && g.dims[0] == 64 && (g.in_channels == 3 || g.in_channels == 6)) {
+        // the same layer with the input prologue fused into its producer warps (used when no resampling is needed)
+        GSD_TRY(build_first_launch(d0.w, fptr(c0.shift_off), d0.out, ch.nb, h, w, g.in_channels, p->num_sms, &ch.first));
+        ch.has_first = getenv("GSD_NO_BIAS_MMA") ? 0 : 1;      // the fused kernel has no epilogue-constant path
+      }
       ConvDesc d1;
       taps3x3(&d1);
       d1.B = ch.nb; d1.H = h; d1.W = w;
       d1.src0 = d0.out; d1.C0 = g.dims[l];
       const ConvW& c1 = p->enc[2 * l + 1];
-      d1.w = P + c1.w_off; d1.scale = fptr(c1.scale_off); d1.shift = fptr(c1.shift_off);
+      d1.w = P + c1.w_off; d1.scale = bn_scale(c1.scale_off); d1.shift = fptr(c1.shift_off);
       d1.Cout = g.dims[l]; d1.relu = 1;
       d1.out = act(p->s_off[l], h, w, g.dims[l]);
       if (l < p->depth) d1.pooled = act(p->p_off[l], p->Hs[l + 1], p->Ws[l + 1], g.dims[l]);
@@ -400,7 +415,7 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       t.src0 = (i == 0) ? act(p->s_off[p->depth], hs, wsz, g.dims[l + 1]) : act(p->db_off[i - 1], hs, wsz, g.dims[l + 1]);
       t.C0 = g.dims[l + 1];
       const ConvW& u = p->upT[i];
-      t.w = P + u.w_off; t.scale = fptr(u.scale_off); t.shift = fptr(u.shift_off);
+      t.w = P + u.w_off; t.scale = bn_scale(u.scale_off); t.shift = fptr(u.shift_off);     // transposed conv: scale is exactly 1
       t.Cout = g.dims[l]; t.relu = 0;
       t.out = act(p->u_off[i], 2 * hs, 2 * wsz, g.dims[l]);
       GSD_TRY(add(t));
@@ -411,7 +426,7 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       d0.src1 = t.out; d0.C1 = g.dims[l]; d0.H1 = 2 * hs; d0.W1 = 2 * wsz;
       d0.off_y = (h - 2 * hs) / 2; d0.off_x = (w - 2 * wsz) / 2;       // F.pad left/top = diff // 2 (unet.py:46-47)
       const ConvW& c0 = p->dec[2 * i];
-      d0.w = P + c0.w_off; d0.scale = fptr(c0.scale_off); d0.shift = fptr(c0.shift_off);
+      d0.w = P + c0.w_off; d0.scale = bn_scale(c0.scale_off); d0.shift = fptr(c0.shift_off);
       d0.Cout = g.dims[l]; d0.relu = 1;
       d0.out = act(p->da_off[i], h, w, g.dims[l]);
       GSD_TRY(add(d0));
@@ -420,7 +435,7 @@ static int bind(gsd_plan* p, void* ws, const void* packed) {
       d1.B = ch.nb; d1.H = h; d1.W = w;
       d1.src0 = d0.out; d1.C0 = g.dims[l];
       const ConvW& c1 = p->dec[2 * i + 1];
-      d1.w = P + c1.w_off; d1.scale = fptr(c1.scale_off); d1.shift = fptr(c1.shift_off);
+      d1.w = P + c1.w_off; d1.scale = bn_scale(c1.scale_off); d1.shift = fptr(c1.shift_off);
       d1.Cout = g.dims[l]; d1.relu = 1;
       d1.out = act(p->db_off[i], h, w, g.dims[l]);
       if (i == p->depth - 1 && g.dtype == GSD_DTYPE_BF16 && use_halo(d1) && g.dims[0] == 64 && !getenv("GSD_NO_HEAD_FUSION")) {
@@ -459,13 +474,16 @@ static int check_prepost(const gsd_plan* p, const gsd_prepost* pp, const float* 
 
 // one chunk of frames through the whole network on `st`
 static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const float* base, const gsd_prepost* pp,
-                     float* y, void* ws, const void* packed, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
-  auto mark = [&]() -> int {
+                     float* y, void* ws, const void* packed, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr,
+                     std::vector<double>* ev_flops = nullptr) {
+  // profiling only: an event after every launch, with the 2*M*N*K of the launch that just went out (0 = memory-bound pass)
+  auto mark = [&](double flops = 0.0) -> int {
     if (evs) {
       cudaEvent_t e;
       GSD_CUDA(cudaEventCreate(&e));
       GSD_CUDA(cudaEventRecord(e, st));
       evs->push_back(e);
+      if (ev_flops) ev_flops->push_back(flops);
     }
     return 0;
   };
@@ -503,7 +521,7 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const 
         dim3 grid((unsigned)((M + 63) / 64), (unsigned)((s.c.groups * s.c.Cout + 63) / 64));
         conv_f32_kernel<<<grid, 256, 0, st>>>(s.c);
         GSD_CUDA(cudaGetLastError());
-        GSD_TRY(mark());
+        GSD_TRY(mark(s.flops));
       }
     }
     const float* last = reinterpret_cast<const float*>(W + p->db_off[p->depth - 1]) + (size_t)ch.b0 * npix * g.dims[0];
@@ -521,15 +539,26 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const 
     GSD_TRY(mark());
     return 0;
   }
-  __nv_bfloat16* in16 = reinterpret_cast<__nv_bfloat16*>(W + p->in16_off + (size_t)ch.b0 * g.height * g.width * 16 * 2);
-  {
+  // The difference image / finger split / normalisation run inside the first conv's producer warps whenever the raw
+  // frames already have the network's size (G1/G2); with area down-sampling (G3) a separate prologue pass writes the
+  // 16-channel bf16 input first.  GSD_NO_FUSED_PROLOGUE forces the two-pass form (parity tests compare the two).
+  const bool fuse_first = ch.has_first && pre.Hr == pre.H && pre.Wr == pre.W && !getenv("GSD_NO_FUSED_PROLOGUE");
+  p->first_fused = fuse_first ? 1 : 0;
+  if (fuse_first) {
+    FirstLaunch t = ch.first;
+    t.p.pre = pre;
+    GSD_TRY(run_first_launch(t, st));
+    GSD_TRY(mark(t.flops));
+  } else {
+    __nv_bfloat16* in16 = reinterpret_cast<__nv_bfloat16*>(W + p->in16_off + (size_t)ch.b0 * g.height * g.width * 16 * 2);
     const int pg = ew_grid((long)ch.nb * g.height * ((g.width + 255) / 256) * 256, 256, 148 * 32);
     if (pre.Hr == pre.H && pre.Wr == pre.W) prologue_kernel<true><<<pg, 256, 0, st>>>(pre, in16);
     else prologue_kernel<false><<<pg, 256, 0, st>>>(pre, in16);
+    GSD_CUDA(cudaGetLastError());
+    GSD_TRY(mark());
   }
-  GSD_CUDA(cudaGetLastError());
-  GSD_TRY(mark());
-  for (const AnyLaunch& L : ch.convs) {
+  for (size_t li = fuse_first ? 1 : 0; li < ch.convs.size(); ++li) {
+    const AnyLaunch& L = ch.convs[li];
     if (L.halo && L.hl.p.head_w) {
       HaloLaunch t = L.hl;
       t.p.head_y = head_out;
@@ -541,7 +570,7 @@ static int run_chunk(gsd_plan* p, const ChunkLaunches& ch, const void* x, const 
     } else {
       GSD_TRY(run_conv_launch(L.tc, st));
     }
-    GSD_TRY(mark());
+    GSD_TRY(mark(L.flops));
   }
   if (!p->head_fused) {
     const __nv_bfloat16* last = reinterpret_cast<const __nv_bfloat16*>(W + p->db_off[p->depth - 1] + (size_t)ch.b0 * npix * 64 * 2);
@@ -713,19 +742,23 @@ extern "C" int gsd_forward_profiled(gsd_plan* p, const void* x, const float* bas
   GSD_CUDA(cudaSetDevice(p->device));
   GSD_TRY(bind(p, workspace, packed));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nconv = p->g.dtype == GSD_DTYPE_FP32 ? 2 * (p->depth + 1) + 3 * p->depth : (int)p->chunks[0].convs.size();
-  const int per_chunk = nconv + 2;
-  GSD_CHECK(capacity >= per_chunk, "gsd_forward_profiled: capacity %d < %d", capacity, per_chunk);
-  for (int i = 0; i < per_chunk; ++i) { ms_host[i] = 0.f; flops_host[i] = 0.0; }
+  int per_chunk = 0;
   for (const ChunkLaunches& ch : p->chunks) {
     std::vector<cudaEvent_t> evs;
-    GSD_TRY(run_chunk(p, ch, x, base, pp, y, workspace, packed, st, &evs));
+    std::vector<double> fl;
+    GSD_TRY(run_chunk(p, ch, x, base, pp, y, workspace, packed, st, &evs, &fl));
     GSD_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i + 1 < (int)evs.size() && i < per_chunk; ++i) {
+    const int n = (int)evs.size() - 1;          // intervals: one per launch (the last also covers head / resample passes)
+    GSD_CHECK(capacity >= n, "gsd_forward_profiled: capacity %d < %d", capacity, n);
+    if (per_chunk == 0) {
+      per_chunk = n;
+      for (int i = 0; i < n; ++i) { ms_host[i] = 0.f; flops_host[i] = 0.0; }
+    }
+    for (int i = 0; i < n && i < per_chunk; ++i) {
       float ms = 0.f;
       GSD_CUDA(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
       ms_host[i] += ms;
-      if (p->g.dtype == GSD_DTYPE_BF16 && i >= 1 && i - 1 < (int)ch.convs.size()) flops_host[i] += ch.convs[i - 1].flops;
+      flops_host[i] += fl[i + 1];
     }
     for (auto e : evs) cudaEventDestroy(e);
   }

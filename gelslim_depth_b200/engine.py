@@ -67,6 +67,11 @@ class Plan:
         return lib.gsd_plan_forward_launches(self.handle)
 
     @property
+    def first_fused(self) -> bool:
+        """the last forward ran the input prologue inside the first conv (no prologue launch, no 16-channel tensor)"""
+        return bool(lib.gsd_plan_first_fused(self.handle))
+
+    @property
     def conv_flops(self) -> float:
         return lib.gsd_plan_conv_flops(self.handle)
 

@@ -98,6 +98,11 @@ int gsd_plan_set_chunk_ramp(gsd_plan* p, int first_frames, int last_frames);
 /* 2*M*N*K summed over the conv / transposed-conv GEMMs of one gsd_forward (valid after the first
  * forward); the denominator-free numerator of bench.py's tensor roofline. */
 double gsd_plan_conv_flops(const gsd_plan* p);
+/* 1 if the plan's last forward ran get_difference_image / the Left-Right split / normalize_tactile_image
+ * (image_utils.py:6-10, general_dataset.py:71, normalization_utils.py:29-34) inside the first conv's producer warps
+ * (raw frames already at network size), 0 if a separate prologue pass wrote the normalised 16-channel input first
+ * (area down-sampling needed, fp32 mode, or GSD_NO_FUSED_PROLOGUE set). */
+int gsd_plan_first_fused(const gsd_plan* p);
 
 /* Replaces: model.load_state_dict / .to(device) on the reference module (test_depth_estimation.py:61-65).
  * params: fp32 device pointers in nn.Module.parameters() order of the reference UNet

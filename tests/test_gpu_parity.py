@@ -583,3 +583,76 @@ def test_integration_md_ctypes_stub_runs_as_printed():
     y = ns["unet_forward_b200"](net, x.to(dev()))
     torch.cuda.synchronize()
     assert rel_l2(y, oracle.unet_forward(sd, x)) < 2e-2
+
+
+@pytest.mark.parametrize("case", ["f32_diff", "u8_nchw", "u8_nhwc", "pairs_u8", "plain"])
+def test_first_conv_fused_prologue_bit_identical(case, monkeypatch):
+    """north_star bullet 4: get_difference_image (image_utils.py:6-10), the Left/Right split (general_dataset.py:71)
+    and normalize_tactile_image (normalization_utils.py:29-34) run inside the first conv's producer warps
+    (csrc/conv_first.cuh): no prologue launch, no normalised tensor in HBM.  Must equal -- bit for bit -- the two-pass
+    form (prologue_kernel + TMA-fed first conv, forced by GSD_NO_FUSED_PROLOGUE) on ragged geometries, and the oracle
+    within the bf16 bound."""
+    from gelslim_depth_b200.engine import make_prepost
+    from gelslim_depth_b200.models.unet import UNet
+    pairs = case == "pairs_u8"
+    cin = 3 if pairs else 6
+    torch.manual_seed(21)
+    net = UNet(cin, 1 if pairs else 2, layer_dimensions=[64, 128, 256])
+    sd = oracle.conditioned_state_dict(net.state_dict(), seed=5)
+    net.load_state_dict(sd)
+    net = net.to(dev()).eval()
+    g = torch.Generator().manual_seed(33)
+    B, H, W = 3, 40, 53                                  # ragged 16 x 8 tiles, still halo-kernel territory (>= 75 % useful rows)
+    raw8 = torch.randint(0, 256, (B, 6, H, W), generator=g, dtype=torch.uint8)
+    base = torch.randint(0, 256, (1 if case != "f32_diff" else B, 6, H, W), generator=g).float()
+    scale, shift = [1 / 255.0, 1 / 200.0, 1 / 255.0], [0.0, 0.25, -0.5]
+    kw = dict(use_diff=case != "plain", base_batch=base.shape[0], in_scale=scale, in_shift=shift, out_scale=-2.1, out_shift=0.3,
+              split_fingers=pairs)
+    if case == "u8_nhwc":
+        x = raw8.permute(0, 2, 3, 1).contiguous().to(dev())
+        pp = make_prepost(cin, (H, W), (H, W), input_u8=2, **kw)
+    elif case in ("u8_nchw", "pairs_u8"):
+        x = raw8.to(dev())
+        pp = make_prepost(cin, (H, W), (H, W), input_u8=1, **kw)
+    else:
+        x = raw8.float().to(dev())
+        pp = make_prepost(cin, (H, W), (H, W), **kw)
+    n_net = 2 * B if pairs else B
+    plan = net.plan_for(n_net, H, W, dev())
+    packed = net.packed_weights(plan)
+    based = base.to(dev()) if case != "plain" else None
+
+    def run():
+        y = torch.empty(n_net, net.n_classes, H, W, device=dev())
+        plan.forward(x, based, pp, y, packed)
+        torch.cuda.synchronize()
+        return y
+
+    y_fused = run()
+    assert plan.first_fused
+    n_fused = plan.launches
+    monkeypatch.setenv("GSD_NO_FUSED_PROLOGUE", "1")
+    y_two_pass = run()
+    assert not plan.first_fused and plan.launches == n_fused + 1         # the prologue pass is the only extra launch
+    monkeypatch.delenv("GSD_NO_FUSED_PROLOGUE")
+    assert torch.equal(y_fused, y_two_pass)
+    # oracle: the reference's own order of operations on the CPU
+    xin = raw8.float()
+    if case != "plain":
+        xin = oracle.get_difference_image(xin, base)
+    if pairs:
+        xin = oracle.split_fingers(xin)
+    sc = torch.tensor([scale[min(c, 2)] for c in range(cin)]).view(1, cin, 1, 1)
+    sh = torch.tensor([shift[min(c, 2)] for c in range(cin)]).view(1, cin, 1, 1)
+    ref = oracle.unet_forward(sd, xin * sc + sh) * -2.1 + 0.3
+    assert rel_l2(y_fused, ref) < 2e-2
+    # Both forms above add the 64-channel layers' BatchNorm shift with one extra UMMA per tile (csrc/bias_mma.cuh: bf16
+    # hi + lo split of the fp32 constant, exact products, fp32 accumulation).  GSD_NO_BIAS_MMA (read when a plan binds)
+    # restores the epilogue add: same mathematics, different rounding order -- a few outputs move by one bf16 ulp per layer.
+    monkeypatch.setenv("GSD_NO_BIAS_MMA", "1")
+    net._plans.clear()
+    plan = net.plan_for(n_net, H, W, dev())
+    y_epi = run()
+    assert not plan.first_fused                      # the fused kernel has no epilogue-constant path
+    assert rel_l2(y_epi, y_fused) < 2e-2, rel_l2(y_epi, y_fused)      # measured 3e-3 .. 8e-3 (11 layers of one-ulp flips)
+    assert rel_l2(y_epi, ref) < 2e-2
