@@ -51,6 +51,8 @@ SYMBOLS = {
     "gsd_plan_conv_flops": (C.c_double, [C.c_void_p]),
     "gsd_plan_first_fused": (C.c_int, [C.c_void_p]),
     "gsd_pack_weights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "gsd_pack_weights_if_changed": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
     "gsd_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p]),
     "gsd_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,

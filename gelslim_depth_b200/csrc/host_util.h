@@ -93,6 +93,48 @@ inline int encode_bf16_map(CUtensorMap* m, void* base, int rank, const uint64_t*
   return 0;
 }
 
+// Every ABI entry that launches work makes `device` current for the duration of the call and restores the caller's
+// current device on return (a torch process may drive cuda:1 while its current device is 0).
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) {
+    err_ = cudaGetDevice(&prev_);
+    if (err_ == cudaSuccess && prev_ != device) {
+      err_ = cudaSetDevice(device);
+      switched_ = err_ == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched_) cudaSetDevice(prev_);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+  int status() const { return err_ == cudaSuccess ? 0 : fail(-2, "cudaSetDevice failed: %s", cudaGetErrorString(err_)); }
+
+ private:
+  int prev_ = 0;
+  bool switched_ = false;
+  cudaError_t err_ = cudaSuccess;
+};
+
+#define GSD_DEVICE(dev)                  \
+  ::gsd::DeviceGuard _gsd_guard(dev);    \
+  GSD_TRY(_gsd_guard.status())
+
+// device that owns a pointer (ops that take no device argument launch where their first tensor lives)
+inline int device_of(const void* ptr, int* device) {
+  cudaPointerAttributes a;
+  GSD_CUDA(cudaPointerGetAttributes(&a, ptr));
+  GSD_CHECK(a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged, "expected a device pointer");
+  *device = a.device;
+  return 0;
+}
+// launch on the device that owns `ptr`, restoring the caller's current device afterwards
+#define GSD_DEVICE_OF(ptr)               \
+  int _gsd_dev = 0;                      \
+  GSD_TRY(::gsd::device_of(ptr, &_gsd_dev)); \
+  GSD_DEVICE(_gsd_dev)
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace gsd

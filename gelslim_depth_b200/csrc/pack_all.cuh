@@ -1,0 +1,138 @@
+// gsd_pack_weights as ONE kernel launch (+ one fingerprint launch for the "only if the parameters changed" form).
+//
+// Why the fingerprint: the module's parameters are ordinary torch tensors that the caller may rewrite in ways the host
+// cannot see -- torch_ema 0.3's copy_to / restore (train_unet.py:389,428,480) and the reference's weight init
+// (train_unet.py:248-250) write through `param.data`, which bypasses the tensor version counter, and the library's own
+// training kernels update parameters and BatchNorm running statistics through raw pointers.  The eval-mode forward
+// therefore keys its packed-operand cache on the CONTENT: params_fingerprint_kernel folds every parameter / buffer word
+// into a 64-bit position-dependent sum on the device, the block that finishes last compares it with the fingerprint of
+// the packed copy and raises `changed`; pack_all_kernel, launched right behind it on the same stream, returns
+// immediately when nothing changed.  No host synchronisation, capture-safe, 124 MB of reads (~25 us) per check.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gsd {
+
+constexpr int kPackMaxItems = 28;      // 2*(depth+1) + 3*depth + head weight + head bias for depth <= 5 ... checked on the host
+constexpr int kFpMaxTensors = 112;     // parameters + BatchNorm buffers of the deepest supported net ... checked on the host
+
+struct PackAllItem {
+  const float* w;        // Conv2d (O,I,3,3) / ConvTranspose2d (I,O,2,2) weight, or the tensor to copy (kind 4)
+  const float* a;        // kind 0/1: BatchNorm gamma;  kind 2/3: transposed-conv bias
+  const float* beta;     // kind 0/1
+  const float* mean;
+  const float* var;
+  void* out_w;
+  float* scale;
+  float* shift;
+  int kind;              // 0 conv+BN bf16 (scale folded into the operand), 1 conv+BN fp32, 2 convT bf16, 3 convT fp32, 4 plain fp32 copy
+  int O, I, Ipad, taps;
+  long long nw;          // weight elements written
+  long long start;       // running sum of (nw + constants) of the preceding items
+};
+
+struct PackAllParams {
+  PackAllItem it[kPackMaxItems];
+  int n;
+  long long total;
+  float eps;
+};
+
+// gate (or null): device uint64[4] = {fingerprint of the packed copy, changed flag, accumulator, block ticket}
+__global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ PackAllParams p, const unsigned long long* __restrict__ gate) {
+  if (gate && gate[1] == 0ull) return;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < p.total; idx += (long long)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < p.n && idx >= p.it[k + 1].start) ++k;
+    const PackAllItem& q = p.it[k];
+    long long e = idx - q.start;
+    if (e < q.nw) {
+      switch (q.kind) {
+        case 0: {      // bf16 [O][taps][Ipad], zero for i >= I, BatchNorm scale folded in (identical expression to the constant below)
+          const int i = (int)(e % q.Ipad);
+          const int t = (int)((e / q.Ipad) % q.taps);
+          const int o = (int)(e / ((long long)q.Ipad * q.taps));
+          const float sc = q.a[o] * rsqrtf(q.var[o] + p.eps);
+          static_cast<__nv_bfloat16*>(q.out_w)[e] = __float2bfloat16_rn(i < q.I ? q.w[((long long)o * q.I + i) * q.taps + t] * sc : 0.f);
+          break;
+        }
+        case 1: {      // fp32 [taps][I][O]
+          const int o = (int)(e % q.O);
+          const int i = (int)((e / q.O) % q.I);
+          const int t = (int)(e / ((long long)q.O * q.I));
+          static_cast<float*>(q.out_w)[e] = q.w[((long long)o * q.I + i) * q.taps + t];
+          break;
+        }
+        case 2: {      // bf16 [(dy*2+dx)*O + o][I]
+          const int i = (int)(e % q.I);
+          const int o = (int)((e / q.I) % q.O);
+          const int g = (int)(e / ((long long)q.I * q.O));
+          static_cast<__nv_bfloat16*>(q.out_w)[e] = __float2bfloat16_rn(q.w[((long long)i * q.O + o) * 4 + g]);
+          break;
+        }
+        case 3: {      // fp32 [I][4*O], n = (dy*2+dx)*O + o
+          const int n = (int)(e % (4 * q.O));
+          const int i = (int)(e / (4 * q.O));
+          const int g = n / q.O, o = n - g * q.O;
+          static_cast<float*>(q.out_w)[e] = q.w[((long long)i * q.O + o) * 4 + g];
+          break;
+        }
+        default: static_cast<float*>(q.out_w)[e] = q.w[e]; break;
+      }
+    } else {
+      e -= q.nw;       // per-channel epilogue constants
+      if (q.kind <= 1) {               // eval-mode BatchNorm folded to y = x*scale + shift (unet.py:12; eps 1e-5)
+        const float s = q.a[e] * rsqrtf(q.var[e] + p.eps);
+        q.scale[e] = s;
+        q.shift[e] = q.beta[e] - q.mean[e] * s;
+      } else {                         // transposed conv: scale 1, shift = bias[o] for each of the 4 (dy,dx) groups
+        q.scale[e] = 1.f;
+        q.shift[e] = q.a[e % q.O];
+      }
+    }
+  }
+}
+
+struct FingerprintParams {
+  const uint32_t* ptr[kFpMaxTensors];
+  long long start[kFpMaxTensors + 1];      // in 32-bit words
+  int n;
+};
+
+__global__ void __launch_bounds__(256) params_fingerprint_kernel(const __grid_constant__ FingerprintParams p, unsigned long long* __restrict__ state) {
+  __shared__ long long s_start[kFpMaxTensors + 1];
+  __shared__ unsigned long long s_part[8];
+  for (int i = threadIdx.x; i <= p.n; i += blockDim.x) s_start[i] = p.start[i];
+  __syncthreads();
+  const long long total = s_start[p.n];
+  unsigned long long acc = 0;
+  int k = 0;
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    while (w >= s_start[k + 1]) ++k;       // w only grows
+    const unsigned long long bits = __ldg(p.ptr[k] + (w - s_start[k]));
+    acc += (bits + 0x9E3779B97F4A7C15ull) * (((unsigned long long)w * 0xBF58476D1CE4E5B9ull) | 1ull);   // position-dependent odd weight
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long b = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) b += s_part[i];
+    atomicAdd(state + 2, b);
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(state + 3, 1ull);
+    if (ticket == gridDim.x - 1) {         // last block: compare with the fingerprint of the packed copy, re-arm
+      __threadfence();
+      const unsigned long long now = atomicAdd(state + 2, 0ull) | 1ull;     // never 0 (0 = "nothing packed yet")
+      state[1] = (now != state[0]) ? 1ull : 0ull;
+      state[0] = now;
+      state[2] = 0ull;
+      state[3] = 0ull;
+    }
+  }
+}
+
+}  // namespace gsd

@@ -8,6 +8,7 @@
 #include "conv_host.h"
 #include "elementwise.cuh"
 #include "host_util.h"
+#include "pack_all.cuh"
 
 using namespace gsd;
 
@@ -254,54 +255,112 @@ extern "C" int gsd_debug_chunk_schedule(int batch, int chunk, int first, int las
 extern "C" double gsd_plan_conv_flops(const gsd_plan* p) { return p ? p->conv_flops : 0; }
 extern "C" int gsd_plan_first_fused(const gsd_plan* p) { return p ? p->first_fused : 0; }
 
+// One launch for every layer (pack_all.cuh); gate != null: only if the device-side fingerprint says the parameters changed.
+static int pack_weights_impl(gsd_plan* p, const void* const* params, const void* const* bn, void* packed,
+                             const unsigned long long* gate, cudaStream_t st) {
+  char* base = static_cast<char*>(packed);
+  const bool f32 = p->g.dtype == GSD_DTYPE_FP32;
+  PackAllParams P;
+  memset(&P, 0, sizeof P);
+  P.eps = 1e-5f;
+  int pi = 0, bi = 0, n = 0;
+  long long cur = 0;
+  auto F = [](const void* q) { return static_cast<const float*>(q); };
+  auto push = [&](PackAllItem it, long long consts) -> int {
+    GSD_CHECK(n < kPackMaxItems, "gsd_pack_weights: more than %d layers", kPackMaxItems);
+    it.start = cur;
+    cur += it.nw + consts;
+    P.it[n++] = it;
+    return 0;
+  };
+  auto conv_bn = [&](const ConvW& c) -> int {
+    PackAllItem it = {};
+    it.w = F(params[pi++]); it.a = F(params[pi++]); it.beta = F(params[pi++]);
+    it.mean = F(bn[bi++]); it.var = F(bn[bi++]);
+    it.out_w = base + c.w_off;
+    it.scale = reinterpret_cast<float*>(base + c.scale_off); it.shift = reinterpret_cast<float*>(base + c.shift_off);
+    it.kind = f32 ? 1 : 0;       // bf16: the BatchNorm scale gamma / sqrt(var + eps) is folded into the operand, only the shift is left
+    it.O = c.cout; it.I = c.cin; it.Ipad = c.cin_pad; it.taps = c.taps;
+    it.nw = (long long)c.cout * c.taps * c.cin_pad;
+    return push(it, c.cout);
+  };
+  for (size_t i = 0; i < p->enc.size(); ++i) GSD_TRY(conv_bn(p->enc[i]));
+  for (int i = 0; i < p->depth; ++i) {
+    const ConvW& u = p->upT[i];
+    PackAllItem it = {};
+    it.w = F(params[pi++]); it.a = F(params[pi++]);
+    it.out_w = base + u.w_off;
+    it.scale = reinterpret_cast<float*>(base + u.scale_off); it.shift = reinterpret_cast<float*>(base + u.shift_off);
+    it.kind = f32 ? 3 : 2; it.O = u.cout; it.I = u.cin; it.Ipad = u.cin; it.taps = 1;
+    it.nw = 4LL * u.cout * u.cin;
+    GSD_TRY(push(it, 4LL * u.cout));
+    GSD_TRY(conv_bn(p->dec[2 * i]));
+    GSD_TRY(conv_bn(p->dec[2 * i + 1]));
+  }
+  for (int h = 0; h < 2; ++h) {      // OutConv weight (n_classes x dims[0]) and bias: plain copies
+    PackAllItem it = {};
+    it.w = F(params[pi++]);
+    it.out_w = base + (h == 0 ? p->head_w_off : p->head_b_off);
+    it.kind = 4;
+    it.nw = h == 0 ? (long long)p->g.n_classes * p->g.dims[0] : p->g.n_classes;
+    GSD_TRY(push(it, 0));
+  }
+  P.n = n;
+  P.total = cur;
+  GSD_CHECK(pi == gsd_plan_num_params(p) && bi == gsd_plan_num_bn_buffers(p), "gsd_pack_weights: internal count mismatch");
+  pack_all_kernel<<<148 * 8, 256, 0, st>>>(P, gate);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int gsd_pack_weights(gsd_plan* p, const void* const* params, const void* const* bn, void* packed,
                                 void* stream) {
   GSD_CHECK(p && params && bn && packed, "gsd_pack_weights: null argument");
+  GSD_DEVICE(p->device);
+  return pack_weights_impl(p, params, bn, packed, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gsd_pack_weights_if_changed(gsd_plan* p, const void* const* params, const void* const* bn, void* packed,
+                                           unsigned long long* state, void* stream) {
+  GSD_CHECK(p && params && bn && packed && state, "gsd_pack_weights_if_changed: null argument");
+  GSD_DEVICE(p->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GSD_CUDA(cudaSetDevice(p->device));
-  char* base = static_cast<char*>(packed);
-  int pi = 0, bi = 0;
-  auto F = [](const void* q) { return static_cast<const float*>(q); };
-  auto pack_conv_bn = [&](const ConvW& c) -> int {
-    const float* w = F(params[pi++]);
-    const float* gamma = F(params[pi++]);
-    const float* beta = F(params[pi++]);
-    const float* mean = F(bn[bi++]);
-    const float* var = F(bn[bi++]);
-    const long total = (long)c.cout * c.taps * c.cin_pad;
-    if (p->g.dtype == GSD_DTYPE_FP32)
-      pack_conv_weight_f32_kernel<<<ew_grid(total), 256, 0, st>>>(w, c.cout, c.cin, c.taps, reinterpret_cast<float*>(base + c.w_off));
-    else   // bf16: the BatchNorm scale gamma / sqrt(var + eps) is folded into the operand, only the shift is left for the conv
-      pack_conv_weight_bn_kernel<<<ew_grid(total), 256, 0, st>>>(w, gamma, var, 1e-5f, c.cout, c.cin, c.taps, c.cin_pad,
-                                                                  reinterpret_cast<__nv_bfloat16*>(base + c.w_off));
-    fold_bn_kernel<<<(c.cout + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, c.cout, 1e-5f,
-                                                         reinterpret_cast<float*>(base + c.scale_off),
-                                                         reinterpret_cast<float*>(base + c.shift_off));
-    GSD_CUDA(cudaGetLastError());
-    return 0;
+  FingerprintParams fp;
+  memset(&fp, 0, sizeof fp);
+  const int np = gsd_plan_num_params(p), nb = gsd_plan_num_bn_buffers(p);
+  GSD_CHECK(np + nb <= kFpMaxTensors, "gsd_pack_weights_if_changed: more than %d tensors", kFpMaxTensors);
+  // element counts in nn.Module.parameters() order, then (running_mean, running_var) per BatchNorm in module order
+  long long cur = 0;
+  int k = 0;
+  auto add = [&](const void* ptr, long long words) {
+    fp.ptr[k] = static_cast<const uint32_t*>(ptr);
+    fp.start[k++] = cur;
+    cur += words;
   };
-  for (size_t i = 0; i < p->enc.size(); ++i) GSD_TRY(pack_conv_bn(p->enc[i]));
+  int pi = 0, bi = 0;
+  std::vector<int> bn_channels;
+  auto conv_bn = [&](const ConvW& c) {
+    add(params[pi++], (long long)c.cout * c.cin * c.taps);
+    add(params[pi++], c.cout);
+    add(params[pi++], c.cout);
+    bn_channels.push_back(c.cout);
+  };
+  for (size_t i = 0; i < p->enc.size(); ++i) conv_bn(p->enc[i]);
   for (int i = 0; i < p->depth; ++i) {
-    const ConvW& u = p->upT[i];
-    const float* w = F(params[pi++]);
-    const float* b = F(params[pi++]);
-    if (p->g.dtype == GSD_DTYPE_FP32)
-      pack_convt_weight_f32_kernel<<<ew_grid(4L * u.cout * u.cin), 256, 0, st>>>(w, u.cin, u.cout, reinterpret_cast<float*>(base + u.w_off));
-    else
-      pack_convt_weight_kernel<<<ew_grid(4L * u.cout * u.cin), 256, 0, st>>>(w, u.cin, u.cout,
-                                                                             reinterpret_cast<__nv_bfloat16*>(base + u.w_off));
-    convt_bias_kernel<<<(4 * u.cout + 127) / 128, 128, 0, st>>>(b, u.cout, reinterpret_cast<float*>(base + u.scale_off),
-                                                                reinterpret_cast<float*>(base + u.shift_off));
-    GSD_CUDA(cudaGetLastError());
-    GSD_TRY(pack_conv_bn(p->dec[2 * i]));
-    GSD_TRY(pack_conv_bn(p->dec[2 * i + 1]));
+    add(params[pi++], 4LL * p->upT[i].cout * p->upT[i].cin);
+    add(params[pi++], p->upT[i].cout);
+    conv_bn(p->dec[2 * i]);
+    conv_bn(p->dec[2 * i + 1]);
   }
-  const long hw = (long)p->g.n_classes * p->g.dims[0];
-  copy_f32_kernel<<<1, 256, 0, st>>>(F(params[pi++]), hw, reinterpret_cast<float*>(base + p->head_w_off));
-  copy_f32_kernel<<<1, 32, 0, st>>>(F(params[pi++]), p->g.n_classes, reinterpret_cast<float*>(base + p->head_b_off));
+  add(params[pi++], (long long)p->g.n_classes * p->g.dims[0]);
+  add(params[pi++], p->g.n_classes);
+  for (int c : bn_channels) { add(bn[bi++], c); add(bn[bi++], c); }
+  GSD_CHECK(pi == np && bi == nb, "gsd_pack_weights_if_changed: internal count mismatch");
+  fp.start[k] = cur;
+  fp.n = k;
+  params_fingerprint_kernel<<<148 * 4, 256, 0, st>>>(fp, state);
   GSD_CUDA(cudaGetLastError());
-  GSD_CHECK(pi == gsd_plan_num_params(p) && bi == gsd_plan_num_bn_buffers(p), "gsd_pack_weights: internal count mismatch");
-  return 0;
+  return pack_weights_impl(p, params, bn, packed, state, st);
 }
 
 static void taps3x3(ConvDesc* d) {
@@ -594,7 +653,7 @@ extern "C" int gsd_forward(gsd_plan* p, const void* x, const float* base, const 
                            void* workspace, const void* packed, void* stream) {
   GSD_CHECK(p && x && y && workspace && packed, "gsd_forward: null argument");
   GSD_TRY(check_prepost(p, pp, base));
-  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_DEVICE(p->device);
   GSD_TRY(bind(p, workspace, packed));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (const ChunkLaunches& ch : p->chunks) GSD_TRY(run_chunk(p, ch, x, base, pp, y, workspace, packed, st));
@@ -662,7 +721,7 @@ extern "C" int gsd_forward_host(gsd_plan* p, const void* x_host, const float* ba
                                 void* stream) {
   GSD_CHECK(p && x_host && y_host && x_dev && y_dev && workspace && packed, "gsd_forward_host: null argument");
   GSD_TRY(check_prepost(p, pp, base));
-  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_DEVICE(p->device);
   GSD_TRY(bind(p, workspace, packed));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GSD_TRY(enqueue_host(p, x_host, base, pp, y_host, x_dev, y_dev, workspace, packed, st, -1));
@@ -677,7 +736,7 @@ extern "C" int gsd_forward_host_async(gsd_plan* p, const void* x_host, const flo
   GSD_CHECK(p && x_host && y_host && x_dev && y_dev && workspace && packed, "gsd_forward_host_async: null argument");
   GSD_CHECK(slot >= 0 && slot < kHostSlots, "gsd_forward_host_async: slot %d out of range [0, %d)", slot, kHostSlots);
   GSD_TRY(check_prepost(p, pp, base));
-  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_DEVICE(p->device);
   GSD_TRY(bind(p, workspace, packed));
   return enqueue_host(p, x_host, base, pp, y_host, x_dev, y_dev, workspace, packed, static_cast<cudaStream_t>(stream),
                       slot);
@@ -687,7 +746,7 @@ extern "C" int gsd_forward_host_wait(gsd_plan* p, int slot) {
   GSD_CHECK(p, "gsd_forward_host_wait: null plan");
   GSD_CHECK(slot >= 0 && slot < kHostSlots, "gsd_forward_host_wait: slot %d out of range [0, %d)", slot, kHostSlots);
   GSD_CHECK(p->slot_used[slot], "gsd_forward_host_wait: slot %d has no call in flight", slot);
-  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_DEVICE(p->device);
   GSD_CUDA(cudaEventSynchronize(p->ev_slot_out[slot]));
   return 0;
 }
@@ -698,7 +757,7 @@ extern "C" int gsd_op_conv_bf16(const void* src0, int C0, const void* src1, int 
                                 const float* shift, int relu, void* out, void* pooled, int block_n, int device,
                                 void* stream) {
   GSD_CHECK(src0 && w && scale && shift && out && tap_dy && tap_dx, "gsd_op_conv_bf16: null argument");
-  GSD_CUDA(cudaSetDevice(device));
+  GSD_DEVICE(device);
   int sms = 0, major = 0;
   GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
@@ -721,7 +780,7 @@ extern "C" int gsd_op_image_affine(const float* x, const float* base, int base_b
   GSD_CHECK(!split_fingers || B % 2 == 0, "gsd_op_image_affine: split_fingers needs an even output batch (2 x frames)");
   GSD_CHECK(!use_diff || base, "gsd_op_image_affine: use_diff without base");
   GSD_CHECK(B >= 1 && Cc >= 1 && H >= 1 && W >= 1 && Hr >= 1 && Wr >= 1, "gsd_op_image_affine: bad shape");
-  GSD_CUDA(cudaSetDevice(device));
+  GSD_DEVICE(device);
   PreParams p;
   p.x = x; p.base = use_diff ? base : nullptr; p.base_batch = base_batch; p.use_diff = use_diff;
   p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W; p.split_fingers = split_fingers ? 1 : 0; p.input_u8 = 0;
@@ -739,7 +798,7 @@ extern "C" int gsd_forward_profiled(gsd_plan* p, const void* x, const float* bas
                                     double* flops_host, int capacity, int* n_out) {
   GSD_CHECK(p && x && y && workspace && packed && ms_host && flops_host && n_out, "gsd_forward_profiled: null argument");
   GSD_TRY(check_prepost(p, pp, base));
-  GSD_CUDA(cudaSetDevice(p->device));
+  GSD_DEVICE(p->device);
   GSD_TRY(bind(p, workspace, packed));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int per_chunk = 0;
@@ -772,7 +831,7 @@ extern "C" int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* sr
                                         const float* shift, int relu, void* out, void* pooled, int block_n,
                                         int base_off_mode, int device, void* stream) {
   GSD_CHECK(src0 && w && scale && shift && out, "gsd_op_conv3x3_halo_bf16: null argument");
-  GSD_CUDA(cudaSetDevice(device));
+  GSD_DEVICE(device);
   int sms = 0, major = 0;
   GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
@@ -793,7 +852,7 @@ extern "C" int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* sr
 extern "C" int gsd_op_wgrad3x3_bf16(const void* x0, int C0, const void* x1, int C1, int H1, int W1, int off_y, int off_x,
                                     const void* dz, int Cout, int B, int H, int W, float* dw, int device, void* stream) {
   GSD_CHECK(x0 && dz && dw, "gsd_op_wgrad3x3_bf16: null argument");
-  GSD_CUDA(cudaSetDevice(device));
+  GSD_DEVICE(device);
   int sms = 0, major = 0;
   GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
@@ -807,6 +866,7 @@ extern "C" int gsd_op_gaussian_blur(const float* x, int planes, int H, int W, in
   GSD_CHECK(x && out && planes >= 1 && H >= 1 && W >= 1, "gsd_op_gaussian_blur: bad argument");
   GSD_CHECK(kernel_size >= 1 && kernel_size <= 31 && (kernel_size & 1), "gsd_op_gaussian_blur: kernel_size must be odd and <= 31");
   GSD_CHECK(kernel_size / 2 < H && kernel_size / 2 < W, "gsd_op_gaussian_blur: reflect padding needs kernel_size/2 < H, W");
+  GSD_DEVICE_OF(x);
   BlurParams p;
   memset(&p, 0, sizeof p);
   p.k = kernel_size; p.planes = planes; p.H = H; p.W = W;
@@ -823,4 +883,4 @@ extern "C" int gsd_op_gaussian_blur(const float* x, int planes, int H, int W, in
   return 0;
 }
 
-#include "train_abi.h"
+#include "train_plan.h"

@@ -5,7 +5,6 @@
 using namespace gsd;
 
 static int check_dev(int device, const char* who) {
-  GSD_CUDA(cudaSetDevice(device));
   int major = 0;
   GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
   GSD_CHECK(major == 10, "%s: device %d is not sm_100 (no fallback)", who, device);
@@ -24,6 +23,7 @@ extern "C" int gsd_op_conv_auto_bf16(const void* src0, int C0, const void* src1,
                                      const float* scale, const float* shift, int relu, void* out, void* pooled,
                                      float* stats, int device, void* stream) {
   GSD_CHECK(src0 && w && out, "gsd_op_conv_auto_bf16: null argument");     // scale / shift may be NULL (= 1 / 0)
+  GSD_DEVICE(device);
   GSD_TRY(check_dev(device, "gsd_op_conv_auto_bf16"));
   ConvDesc d;
   d.src0 = src0; d.C0 = C0; d.src1 = src1; d.C1 = src1 ? C1 : 0; d.H1 = H1; d.W1 = W1; d.off_y = off_y; d.off_x = off_x;
@@ -81,6 +81,7 @@ extern "C" int gsd_op_convt_dgrad_bf16(const void* du, int Cs, int Hf, int Wf, i
                                        int B, int H, int W, const float* scale, const float* shift, void* out, int device,
                                        void* stream) {
   GSD_CHECK(du && w && out, "gsd_op_convt_dgrad_bf16: null argument");        // scale / shift may be NULL (= 1 / 0)
+  GSD_DEVICE(device);
   GSD_TRY(check_dev(device, "gsd_op_convt_dgrad_bf16"));
   ConvDesc d;
   d.src0 = du; d.C0 = 2 * Cs; d.B = B; d.H = H; d.W = W; d.w = w; d.Cout = Cin; d.groups = 1; d.ntaps = 2;
@@ -94,6 +95,7 @@ extern "C" int gsd_op_convt_dgrad_bf16(const void* du, int Cs, int Hf, int Wf, i
 extern "C" int gsd_op_convt_wgrad_bf16(const void* in, int Cin, const void* du, int Cout, int Hf, int Wf, int off_y, int off_x,
                                        int B, int H, int W, float* dw, int device, void* stream) {
   GSD_CHECK(in && du && dw, "gsd_op_convt_wgrad_bf16: null argument");
+  GSD_DEVICE(device);
   GSD_TRY(check_dev(device, "gsd_op_convt_wgrad_bf16"));
   WgradPwLaunch L;
   GSD_TRY(build_wgrad_pw_launch(in, Cin, du, Cout, Hf, Wf, off_y, off_x, B, H, W, dw, num_sms_of(device), &L));
@@ -105,6 +107,7 @@ extern "C" int gsd_op_prologue_bf16(const float* x, const float* base, int base_
                                     int Wr, int H, int W, const float* scale8_host, const float* shift8_host, void* out16,
                                     void* stream) {
   GSD_CHECK(x && out16 && scale8_host && shift8_host && Cc <= 8, "gsd_op_prologue_bf16: bad argument");
+  GSD_DEVICE_OF(x);
   PreParams p;
   p.x = x; p.base = use_diff ? base : nullptr; p.base_batch = base_batch; p.use_diff = use_diff;
   p.B = B; p.C = Cc; p.Hr = Hr; p.Wr = Wr; p.H = H; p.W = W; p.split_fingers = 0; p.input_u8 = 0;
@@ -118,6 +121,7 @@ extern "C" int gsd_op_prologue_bf16(const float* x, const float* base, int base_
 
 extern "C" int gsd_op_negate_f32(const float* in, int n, float* out, void* stream) {
   GSD_CHECK(in && out && n > 0, "gsd_op_negate_f32: bad argument");
+  GSD_DEVICE_OF(in);
   negate_f32_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out);
   GSD_CUDA(cudaGetLastError());
   return 0;
@@ -127,6 +131,7 @@ extern "C" int gsd_op_bn_finalize(const float* stats, double count, const float*
                                   float* running_var, float momentum, float eps, int C, const float* neg_center, float* scale,
                                   float* shift, float* mean, float* rstd, long long* num_batches_tracked, void* stream) {
   GSD_CHECK(stats && gamma && beta && scale && shift && mean && rstd && C > 0, "gsd_op_bn_finalize: bad argument");
+  GSD_DEVICE_OF(stats);
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, (float)count, gamma, beta, running_mean,
                                                                                     running_var, momentum, eps, C, neg_center, scale, shift,
                                                                                     mean, rstd, num_batches_tracked);
@@ -137,6 +142,7 @@ extern "C" int gsd_op_bn_finalize(const float* stats, double count, const float*
 extern "C" int gsd_op_bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H, int W, int C, void* a,
                                     void* pooled, void* stream) {
   GSD_CHECK(z && scale && shift && a && C % 8 == 0, "gsd_op_bn_relu_apply: bad argument");
+  GSD_DEVICE_OF(z);
   const int C8 = C / 8;
   GSD_CHECK((C8 & (C8 - 1)) == 0 && C8 <= 256, "gsd_op_bn_relu_apply: C/8 must be a power of two <= 256");
   int c8_shift = 0;
@@ -153,6 +159,7 @@ extern "C" int gsd_op_bn_relu_apply(const void* z, const float* scale, const flo
 // loss (1 float, accumulated: caller zeroes) and dy = 2 (y - t) / n   (train_unet.py:51-52,370)
 extern "C" int gsd_op_mse(const float* y, const float* t, long long n, float* loss, float* dy, void* stream) {
   GSD_CHECK(y && t && loss && dy && n > 0, "gsd_op_mse: bad argument");
+  GSD_DEVICE_OF(y);
   mse_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, t, (long)n, loss, dy);
   GSD_CUDA(cudaGetLastError());
   return 0;
@@ -160,6 +167,7 @@ extern "C" int gsd_op_mse(const float* y, const float* t, long long n, float* lo
 
 extern "C" int gsd_op_head_fwd(const void* a, const float* w, const float* bias, int ncls, int B, int H, int W, float* y, void* stream) {
   GSD_CHECK(a && w && bias && y && ncls >= 1 && ncls <= 4, "gsd_op_head_fwd: bad argument");
+  GSD_DEVICE_OF(a);
   const long npix = (long)H * W;
   head_kernel<64><<<ew_grid(npix * B), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), w, bias, ncls, 1.f,
                                                                                    0.f, npix, B, y);
@@ -171,6 +179,7 @@ extern "C" int gsd_op_head_fwd(const void* a, const float* w, const float* bias,
 extern "C" int gsd_op_bn_relu_head_fwd(const void* z, const float* scale, const float* shift, const float* w, const float* bias,
                                        int ncls, int B, int H, int W, float* y, void* stream) {
   GSD_CHECK(z && scale && shift && w && bias && y && ncls >= 1 && ncls <= 4, "gsd_op_bn_relu_head_fwd: bad argument");
+  GSD_DEVICE_OF(z);
   const long npix = (long)H * W;
   head_kernel<64><<<ew_grid(npix * B), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(z), w, bias, ncls, 1.f,
                                                                                    0.f, npix, B, y, scale, shift);
@@ -182,11 +191,11 @@ extern "C" int gsd_op_bn_relu_head_fwd(const void* z, const float* scale, const 
 template <int NCLS>
 static int launch_head_bn_bwd(const __nv_bfloat16* z, const float* dy, const float* w, const float* scale, const float* shift,
                               const float* mean, const float* rstd, const float* gamma, float count, unsigned npix, unsigned total,
-                              float* sums, float* dw, float* db, __nv_bfloat16* dz, cudaStream_t st) {
+                              float* sums, float* dw, float* db, __nv_bfloat16* dz, cudaStream_t st, float* sums2 = nullptr) {
   long blocks = ((long)total * 8 + 255) / 256;
   const int grid = (int)(blocks < 148 * 2 ? blocks : 148 * 2);
-  head_bn_bwd_kernel<NCLS, false><<<grid, 256, 0, st>>>(z, dy, w, scale, shift, mean, rstd, gamma, count, npix, total, sums, dw, db, dz);
-  head_bn_bwd_kernel<NCLS, true><<<grid, 256, 0, st>>>(z, dy, w, scale, shift, mean, rstd, gamma, count, npix, total, sums, dw, db, dz);
+  head_bn_bwd_kernel<NCLS, false><<<grid, 256, 0, st>>>(z, dy, w, scale, shift, mean, rstd, gamma, count, npix, total, sums, dw, db, dz, sums2);
+  head_bn_bwd_kernel<NCLS, true><<<grid, 256, 0, st>>>(z, dy, w, scale, shift, mean, rstd, gamma, count, npix, total, sums, dw, db, dz, sums2);
   GSD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -195,6 +204,7 @@ extern "C" int gsd_op_head_bn_bwd(const void* z, const float* dy, const float* w
                                   int W, float* sums, float* dw, float* db, void* dz, void* stream) {
   GSD_CHECK(z && dy && w && scale && shift && mean && rstd && gamma && sums && dw && db && dz && ncls >= 1 && ncls <= 4,
             "gsd_op_head_bn_bwd: bad argument");
+  GSD_DEVICE_OF(z);
   const long npix = (long)H * W;
   GSD_CHECK(npix * B < (1L << 31), "gsd_op_head_bn_bwd: more than 2^31 pixels");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -212,6 +222,7 @@ extern "C" int gsd_op_head_bn_bwd(const void* z, const float* dy, const float* w
 extern "C" int gsd_op_head_bwd(const void* a, const float* dy, const float* w, int ncls, int B, int H, int W, void* da, float* dw,
                                float* db, void* stream) {
   GSD_CHECK(a && dy && w && da && dw && db && ncls >= 1 && ncls <= 4, "gsd_op_head_bwd: bad argument");
+  GSD_DEVICE_OF(a);
   const long npix = (long)H * W;
   GSD_CHECK(npix * B < (1L << 31), "gsd_op_head_bwd: more than 2^31 pixels");
   long blocks = (npix * B * 8 + 255) / 256;
@@ -253,6 +264,7 @@ static int reduce_grid(int C, long npix, int* grid, int* block) {
 extern "C" int gsd_op_bn_bwd_reduce(const void* da, const float* scale, const float* shift, const void* z, const float* mean,
                                     const float* rstd, long long npix, int C, float* sums, void* stream) {
   GSD_CHECK(da && sums && C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0, "gsd_op_bn_bwd_reduce: C/8 must be a power of two");
+  GSD_DEVICE_OF(da);
   int grid, block;
   reduce_grid(C, (long)npix, &grid, &block);
   bn_bwd_reduce_kernel<<<grid, block, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
@@ -265,6 +277,7 @@ extern "C" int gsd_op_bn_bwd_apply(const void* da, const float* scale, const flo
                                    const float* rstd, const float* gamma, const float* sums, double count, long long npix, int C,
                                    void* dz, void* stream) {
   GSD_CHECK(da && scale && shift && z && mean && rstd && gamma && sums && dz && C % 8 == 0, "gsd_op_bn_bwd_apply: bad argument");
+  GSD_DEVICE_OF(da);
   GSD_CHECK(((C / 8) & (C / 8 - 1)) == 0, "gsd_op_bn_bwd_apply: C/8 must be a power of two");
   int grid, block;
   reduce_grid(C, (long)npix, &grid, &block);
@@ -278,6 +291,7 @@ extern "C" int gsd_op_bn_bwd_apply(const void* da, const float* scale, const flo
 extern "C" int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* dskip, int B, int H, int W, int C, void* dfull,
                                   void* stream) {
   GSD_CHECK(a && dpool && dfull && C % 8 == 0, "gsd_op_maxpool_bwd: bad argument");
+  GSD_DEVICE_OF(a);
   const int C8 = C / 8;
   GSD_CHECK((C8 & (C8 - 1)) == 0 && C8 <= 256, "gsd_op_maxpool_bwd: C/8 must be a power of two <= 256");
   int c8_shift = 0;
@@ -295,6 +309,7 @@ extern "C" int gsd_op_maxpool_bwd(const void* a, const void* dpool, const void* 
 // mode 2: ConvTranspose2d (I,O,2,2) -> forward operand [(g)*O+o][I];  3: -> its dgrad operand [I][(g, o)]
 extern "C" int gsd_op_pack_weight(int mode, const float* w, int O, int I, int Ipad, void* out, void* stream) {
   GSD_CHECK(w && out, "gsd_op_pack_weight: null argument");
+  GSD_DEVICE_OF(w);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   switch (mode) {
@@ -310,6 +325,7 @@ extern "C" int gsd_op_pack_weight(int mode, const float* w, int O, int I, int Ip
 
 extern "C" int gsd_op_unpack_wgrad(float* dwk, int O, int I, int Ipad, float* grad, int clear, void* stream) {
   GSD_CHECK(dwk && grad, "gsd_op_unpack_wgrad: null argument");
+  GSD_DEVICE_OF(dwk);
   unpack_wgrad_kernel<<<ew_grid((long)O * I * 9), 256, 0, static_cast<cudaStream_t>(stream)>>>(dwk, O, I, Ipad, grad, clear);
   GSD_CUDA(cudaGetLastError());
   return 0;
@@ -319,6 +335,7 @@ extern "C" long long gsd_pack_item_units(int mode, int O, int I, int Ipad) { ret
 
 extern "C" int gsd_op_pack_weights_batched(const gsd_pack_item* items_dev, int n_items, long long total_units, void* stream) {
   GSD_CHECK(items_dev && n_items > 0 && n_items <= 64 && total_units > 0, "gsd_op_pack_weights_batched: need 1..64 items");
+  GSD_DEVICE_OF(items_dev);
   static_assert(sizeof(gsd_pack_item) == sizeof(PackItemDev), "gsd_pack_item layout");
   const int grid = (int)(total_units < 148 * 8 ? total_units : 148 * 8);
   pack_weights_batched_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const PackItemDev*>(items_dev),
@@ -335,6 +352,7 @@ extern "C" int gsd_op_adam_ema_dev(float* p, const float* g, float* m, float* v,
                                    float beta2, float eps, float weight_decay, float ema_decay, long long* counter, float grad_scale,
                                    void* stream) {
   GSD_CHECK(p && g && m && v && counter && n > 0, "gsd_op_adam_ema_dev: bad argument");
+  GSD_DEVICE_OF(p);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   adam_ema_kernel<<<ew_grid((long)n / 4 + 1), 256, 0, st>>>(p, g, m, v, shadow, (long)n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, 0.f,
                                                             grad_scale, counter, ema_decay);
@@ -347,6 +365,7 @@ extern "C" int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, flo
                                float beta2, float eps, float weight_decay, long long step, float ema_decay, long long ema_updates,
                                float grad_scale, void* stream) {
   GSD_CHECK(p && g && m && v && n > 0 && step >= 1, "gsd_op_adam_ema: bad argument");
+  GSD_DEVICE_OF(p);
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   double d = ema_decay;

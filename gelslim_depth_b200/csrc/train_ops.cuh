@@ -222,7 +222,10 @@ __global__ void __launch_bounds__(256, 2) head_bn_bwd_kernel(const __nv_bfloat16
                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                              float count, unsigned npix_per_img, unsigned total,
                                                              float* __restrict__ sums, float* __restrict__ dw,
-                                                             float* __restrict__ db, __nv_bfloat16* __restrict__ dz) {
+                                                             float* __restrict__ db, __nv_bfloat16* __restrict__ dz,
+                                                             float* __restrict__ sums2 = nullptr) {
+  // sums2 (or null = sums + 64): where sum g*zhat (= dgamma) lives; separate pointers let the two reductions land straight in
+  // the BatchNorm bias / weight gradient tensors
   const int c8 = threadIdx.x & 7;
   const unsigned p0 = (blockIdx.x * 256u + threadIdx.x) >> 3, pstep = (gridDim.x * 256u) >> 3;
   float wr[NCLS][8], sc[8], sh[8], mu[8], rs[8];
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(256, 2) head_bn_bwd_kernel(const __nv_bfloat16
     const int c = c8 * 8 + j;
     sc[j] = scale[c]; sh[j] = shift[c]; mu[j] = mean[c]; rs[j] = rstd[c];
     s1[j] = 0.f; s2[j] = 0.f;
-    if (APPLY) { const float inv = 1.f / count; k1[j] = gamma[c] * rstd[c]; k2[j] = sums[c] * inv; k3[j] = sums[64 + c] * inv; }
+    if (APPLY) { const float inv = 1.f / count; k1[j] = gamma[c] * rstd[c]; k2[j] = sums[c] * inv; k3[j] = (sums2 ? sums2[c] : sums[64 + c]) * inv; }
 #pragma unroll
     for (int k = 0; k < NCLS; ++k) { wr[k][j] = w[k * 64 + c]; acc[k][j] = 0.f; }
   }
@@ -302,7 +305,8 @@ __global__ void __launch_bounds__(256, 2) head_bn_bwd_kernel(const __nv_bfloat16
   __syncthreads();
   for (int i = threadIdx.x; i < NCLS * 64; i += 256) atomicAdd(dw + i, red[i]);
   if ((int)threadIdx.x < NCLS) atomicAdd(db + threadIdx.x, red[256 + threadIdx.x]);
-  if (threadIdx.x < 128) atomicAdd(sums + threadIdx.x, red[260 + threadIdx.x]);
+  if (threadIdx.x < 128)
+    atomicAdd((sums2 && threadIdx.x >= 64) ? sums2 + (threadIdx.x - 64) : sums + threadIdx.x, red[260 + threadIdx.x]);
 }
 
 // BatchNorm+ReLU backward, reduction pass: sums[c] = sum g, sums[C+c] = sum g*zhat, g = da*(a>0), zhat=(z-mean)*rstd.
@@ -312,7 +316,9 @@ __global__ void __launch_bounds__(256, 2) head_bn_bwd_kernel(const __nv_bfloat16
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, const __nv_bfloat16* __restrict__ z,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd, long npix,
-                                                            int C, long da_pix_stride, float* __restrict__ sums) {
+                                                            int C, long da_pix_stride, float* __restrict__ sums,
+                                                            float* __restrict__ sums2 = nullptr) {
+  // sums2 (or null = sums + C): destination of sum g*zhat
   // thread -> fixed 8-channel chunk; pixels strided.  blockDim.x * gridDim.x must be a multiple of C/8 (host).
   const int C8 = C / 8;
   const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
-    if (smem[i] != 0.f) atomicAdd(sums + i, smem[i]);
+    if (smem[i] != 0.f) atomicAdd((sums2 && i >= C) ? sums2 + (i - C) : sums + i, smem[i]);
 }
 
 // BatchNorm+ReLU backward, apply pass: dz = gamma*rstd*(g - sum_g/n - zhat*sum_gz/n).
@@ -377,7 +383,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ sums, float count, long npix, int C,
-                                                           long da_pix_stride, __nv_bfloat16* __restrict__ dz) {
+                                                           long da_pix_stride, __nv_bfloat16* __restrict__ dz,
+                                                           const float* __restrict__ sums2 = nullptr) {
   const int C8 = C / 8;
   const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const int c8 = (int)(tid % C8);
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     sc[j] = scale[c]; sh[j] = shift[c]; mu[j] = mean[c]; rs[j] = rstd[c];
     k1[j] = gamma[c] * rstd[c];
     k2[j] = sums[c] * inv;
-    k3[j] = sums[C + c] * inv;
+    k3[j] = (sums2 ? sums2[c] : sums[C + c]) * inv;
   }
   for (long px0 = p0; px0 < npix; px0 += 4 * pstep) {
     uint4 ug[4], uz[4];

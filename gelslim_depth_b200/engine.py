@@ -75,7 +75,9 @@ class Plan:
     def conv_flops(self) -> float:
         return lib.gsd_plan_conv_flops(self.handle)
 
-    def pack(self, params, bn_buffers, packed: torch.Tensor):
+    def pack(self, params, bn_buffers, packed: torch.Tensor, state: Optional[torch.Tensor] = None):
+        """gsd_pack_weights; with `state` (4 x int64 device tensor, zeroed when `packed` is new) the re-pack happens only if
+        the device-side content fingerprint of the parameters changed (gsd_pack_weights_if_changed)."""
         n_p, n_b = lib.gsd_plan_num_params(self.handle), lib.gsd_plan_num_bn_buffers(self.handle)
         if len(params) != n_p or len(bn_buffers) != n_b:
             raise ValueError(f"expected {n_p} params / {n_b} BN buffers, got {len(params)} / {len(bn_buffers)}")
@@ -84,7 +86,11 @@ class Plan:
                 raise ValueError("parameters must be contiguous fp32 tensors on the plan's device")
         pa = (C.c_void_p * n_p)(*[t.data_ptr() for t in params])
         ba = (C.c_void_p * n_b)(*[t.data_ptr() for t in bn_buffers])
-        check(lib.gsd_pack_weights(self.handle, pa, ba, _ptr(packed), _stream(self.device)), "gsd_pack_weights")
+        if state is None:
+            check(lib.gsd_pack_weights(self.handle, pa, ba, _ptr(packed), _stream(self.device)), "gsd_pack_weights")
+        else:
+            check(lib.gsd_pack_weights_if_changed(self.handle, pa, ba, _ptr(packed), _ptr(state), _stream(self.device)),
+                  "gsd_pack_weights_if_changed")
 
     def forward(self, x, base, pp, y, packed):
         check(lib.gsd_forward(self.handle, _ptr(x), _ptr(base), C.byref(pp), _ptr(y), _ptr(self.workspace),

@@ -68,7 +68,8 @@ class UNet(nn.Module):
 
         self._plans = PlanCache(capacity=4)
         self._packed = None          # torch.uint8 arena of GEMM operands + folded BN
-        self._packed_key = None
+        self._pack_state = None      # device int64[4]: content fingerprint of the parameters `_packed` was built from
+        self._frozen = False
         self.precision = "bf16"      # "bf16": tcgen05 tensor-core path; "fp32": FFMA parity path (set_precision)
 
     def set_precision(self, precision: str) -> "UNet":
@@ -79,7 +80,7 @@ class UNet(nn.Module):
         if precision != self.precision:
             self.precision = precision
             self._plans.clear()
-            self._packed, self._packed_key = None, None
+            self._packed, self._pack_state = None, None
         return self
 
     # ------------------------------------------------------------------ validation
@@ -110,26 +111,34 @@ class UNet(nn.Module):
                 out += [m.running_mean, m.running_var]
         return out
 
-    def _weights_key(self):
-        ts = list(self.parameters()) + self._bn_buffers()
-        return tuple((t.data_ptr(), t._version) for t in ts)
-
     def packed_weights(self, plan: Plan) -> torch.Tensor:
-        """bf16 K-major GEMM operands + folded eval-mode BatchNorm; re-packed whenever any parameter or
-        running statistic changed (optimizer.step, ema.average_parameters(), load_state_dict, .to())."""
-        key = self._weights_key() + (self.precision,)
-        if self._packed is None or self._packed_key != key or self._packed.device != plan.device \
-                or self._packed.numel() != plan.packed_bytes:
-            if self._packed is None or self._packed.device != plan.device or self._packed.numel() != plan.packed_bytes:
-                self._packed = torch.empty(plan.packed_bytes, dtype=torch.uint8, device=plan.device)
-            plan.pack([p.detach() for p in self.parameters()], self._bn_buffers(), self._packed)
-            self._packed_key = key
+        """bf16 K-major GEMM operands + folded eval-mode BatchNorm of the CURRENT parameters.
+
+        The cache is keyed on the parameters' content, not on torch's version counters: every call launches a device-side
+        fingerprint of all parameters / running statistics and a gated re-pack that returns immediately when nothing
+        changed (gsd_pack_weights_if_changed: two launches, ~25 us, no host sync).  So optimizer.step, load_state_dict
+        and .to() are covered, and so are the writes torch cannot see: torch_ema's copy_to / restore and the reference's
+        weight init go through `param.data` (train_unet.py:248-250,389,428,480), the library's training kernels through raw
+        pointers.  `frozen_weights()` skips the check for serving loops whose weights never change."""
+        fresh = (self._packed is None or self._packed.device != plan.device or self._packed.numel() != plan.packed_bytes)
+        if fresh:
+            self._packed = torch.empty(plan.packed_bytes, dtype=torch.uint8, device=plan.device)
+            self._pack_state = torch.zeros(4, dtype=torch.int64, device=plan.device)
+        if fresh or not self._frozen:
+            plan.pack([p.detach() for p in self.parameters()], self._bn_buffers(), self._packed, self._pack_state)
         return self._packed
 
     def invalidate_packed_weights(self):
-        """Force a re-pack on the next forward.  Needed by code that updates parameters through raw pointers
-        (FusedTrainer's arena kernel), which torch's version counters cannot see."""
-        self._packed_key = None
+        """Force a re-pack on the next forward (the content fingerprint makes this unnecessary; kept for callers that
+        want the re-pack to happen regardless)."""
+        if self._pack_state is not None:
+            self._pack_state.zero_()
+
+    def frozen_weights(self, frozen: bool = True) -> "UNet":
+        """Serving mode: the caller promises not to touch the parameters; eval forwards skip the fingerprint check.
+        Unfreezing (or any call to invalidate_packed_weights) restores the checked behaviour."""
+        self._frozen = bool(frozen)
+        return self
 
     def plan_for(self, batch: int, height: int, width: int, device: torch.device) -> Plan:
         key = (batch, height, width, device, self.precision)
@@ -139,7 +148,7 @@ class UNet(nn.Module):
 
     def _apply(self, fn, *a, **k):          # .to()/.cuda()/.float(): drop device-specific caches
         self._plans.clear()
-        self._packed, self._packed_key = None, None
+        self._packed, self._pack_state = None, None
         return super()._apply(fn, *a, **k)
 
     # ------------------------------------------------------------------ forward

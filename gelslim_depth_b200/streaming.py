@@ -16,6 +16,8 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
+from . import _lib
+from .engine import Plan
 from .models.unet import UNet
 from .processing_utils.complete_prediction import _prepost_from_config
 
@@ -54,9 +56,15 @@ class DepthStream:
         u8 = layout != "chw_f32"
         shape = (1, H, W, self.frame_channels) if layout == "hwc_u8" else (1, self.frame_channels, H, W)
         dt = torch.uint8 if u8 else torch.float32
-        self.plan = model.plan_for(self.net_batch, self.net_hw[0], self.net_hw[1], self.device)
-        self.packed = model.packed_weights(self.plan)
+        # A private plan (workspace) and a private packed-weight buffer: the captured graphs replay on `self.stream`
+        # while eager model.run() calls of the same geometry may be in flight on the caller's stream -- sharing the
+        # model's PlanCache entry or its packed buffer would make the two race on one workspace.
+        dtype = _lib.DTYPE_FP32 if model.precision == "fp32" else _lib.DTYPE_BF16
+        self.plan = Plan(self.net_batch, model.n_channels, self.net_hw[0], self.net_hw[1], model.n_classes,
+                         model.layer_dimensions, self.device, dtype=dtype)
+        self.packed = torch.empty(self.plan.packed_bytes, dtype=torch.uint8, device=self.device)
         self.stream = torch.cuda.Stream(self.device)
+        self.refresh_weights()
         self._slots: List[dict] = []
         for _ in range(max(1, int(slots))):
             s = {"x_host": torch.empty(shape, dtype=dt).pin_memory(), "x_dev": torch.empty(shape, dtype=dt, device=self.device),
@@ -94,13 +102,12 @@ class DepthStream:
         s["y_host"].copy_(s["y_dev"], non_blocking=True)
 
     def refresh_weights(self):
-        """Call after the model's parameters changed (load_state_dict, EMA swap): re-packs into the same buffer the
-        captured graphs read."""
+        """Call after the model's parameters changed (load_state_dict, EMA swap): re-packs, on the stream the captured
+        graphs replay on, into the buffer they read."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))      # the caller's parameter writes come first
+        with torch.cuda.stream(self.stream):
+            self.plan.pack([p.detach() for p in self.model.parameters()], self.model._bn_buffers(), self.packed)
         self.stream.synchronize()
-        packed = self.model.packed_weights(self.plan)
-        if packed.data_ptr() != self.packed.data_ptr():
-            self.packed.copy_(packed)
-        torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ streaming API
     def push(self, frame) -> int:

@@ -398,31 +398,63 @@ class _ArenaEnv(StepEnv):
         return t
 
 
-class _ArenaSink(GradSink):
-    """Gradients are written straight into the flat arena; a bucket (contiguous range, >= bucket_bytes, formed in
-    backward = reverse-parameter order) is all-reduced on a side stream as soon as its last gradient has been launched,
-    so NCCL traffic overlaps the remaining dgrad / wgrad kernels."""
+class BucketReducer:
+    """Host logic of the overlapped gradient all-reduce: counts down the parameters of each bucket as their gradient
+    kernels are LAUNCHED (backward order) and, when a bucket is complete, hands its contiguous arena range to `launch`.
+    `launch(lo, hi)` is the only device-specific part: on the GPU it orders the communication stream after BOTH compute
+    streams and enqueues the NCCL all-reduce; the world_size-2 gloo test (tests/test_ddp_cpu.py) passes a plain
+    `dist.all_reduce`.  One instance per step."""
 
-    def __init__(self, trainer):
+    def __init__(self, buckets, bucket_of, launch):
+        self.buckets, self.bucket_of, self.launch = buckets, bucket_of, launch
+        self.pending = [len(b["params"]) for b in buckets]
+        self.fired = []
+
+    def done(self, key):
+        bi = self.bucket_of[key]
+        self.pending[bi] -= 1
+        if self.pending[bi] < 0:
+            raise RuntimeError("gradient reported twice for one parameter")
+        if self.pending[bi] == 0:
+            b = self.buckets[bi]
+            self.fired.append(bi)
+            self.launch(b["lo"], b["hi"])
+
+    def all_fired(self) -> bool:
+        return all(n == 0 for n in self.pending)
+
+
+class _ArenaSink(GradSink):
+    """Gradients are written straight into the flat arena; a bucket (contiguous range formed in backward =
+    reverse-parameter order) is all-reduced on the communication stream as soon as its last gradient kernel has been
+    launched, so NCCL traffic overlaps the remaining dgrad / wgrad kernels."""
+
+    def __init__(self, trainer, reduce=True):
         super().__init__()
         self.t = trainer
-        self.pending = [len(b["params"]) for b in trainer.buckets]
+        self.reducer = BucketReducer(trainer.buckets, trainer.bucket_of, self._launch) if (trainer.world > 1 and reduce) else None
 
     def dest(self, p):
         off, k = self.t.index[p]
         return self.t.flat_g[off:off + k].view(p.shape)
 
-    def done(self, p):
+    def _launch(self, lo, hi):
+        # A bucket mixes gradients written on the main stream (BatchNorm, bias) and on the weight-gradient side stream:
+        # the all-reduce must wait for BOTH, whichever stream happened to launch the bucket's last kernel.
         t = self.t
-        bi = t.bucket_of[p]
-        self.pending[bi] -= 1
-        if self.pending[bi] == 0 and t.world > 1:
-            b = t.buckets[bi]
+        streams = {id(s): s for s in (t.main_stream_for_step, torch.cuda.current_stream())}
+        if t.env.side_stream is not None and t.env._forked:      # forked this step (inside the graph capture, if any)
+            streams[id(t.env.side_stream)] = t.env.side_stream
+        for st in streams.values():
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            with torch.cuda.stream(t.comm_stream):
-                t.comm_stream.wait_event(ev)
-                torch.distributed.all_reduce(t.flat_g[b["lo"]:b["hi"]], group=t.pg)
+            ev.record(st)
+            t.comm_stream.wait_event(ev)
+        with torch.cuda.stream(t.comm_stream):
+            torch.distributed.all_reduce(t.flat_g[lo:hi], group=t.pg)
+
+    def done(self, p):
+        if self.reducer is not None:
+            self.reducer.done(p)
 
 
 class FusedTrainer:
@@ -432,7 +464,8 @@ class FusedTrainer:
     (per-replica BatchNorm statistics, like stock DistributedDataParallel)."""
 
     def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, ema_decay=0.995, process_group=None,
-                 bucket_bytes=25 << 20, distributed=None, use_graph=False, overlap_wgrad=True):
+                 bucket_bytes=25 << 20, distributed=None, use_graph=False, overlap_wgrad=True, first_bucket_bytes=4 << 20,
+                 tail_bucket_bytes=2 << 20):
         self.net = net
         self.lr, self.betas, self.eps, self.wd, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         params = list(net.parameters())
@@ -452,7 +485,6 @@ class FusedTrainer:
             self.views.append((off, k))
             self.index[p] = (off, k)
             off += k
-        self.shadow = self.flat_p.clone()                         # torch_ema: shadow = [p.clone()]
         self.counter = torch.zeros(2, dtype=torch.int64, device=dev)   # (Adam steps, EMA updates) so far, advanced on device
         self.use_graph, self._graph, self._warm = use_graph, None, 0
         self.pg = process_group
@@ -460,7 +492,15 @@ class FusedTrainer:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.world = torch.distributed.get_world_size(process_group) if distributed else 1
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
-        self.buckets, self.bucket_of = plan_buckets([(p, *self.index[p]) for p in params], bucket_bytes)
+        self.main_stream_for_step = torch.cuda.current_stream(dev)
+        if self.world > 1:
+            # stock DistributedDataParallel broadcasts rank 0's parameters and buffers at construction: replicas built
+            # from different RNG states / checkpoints must start from ONE model, or they average gradients of different
+            # networks for ever after
+            broadcast_module_state(net, self.flat_p, process_group)
+        self.shadow = self.flat_p.clone()                         # torch_ema: shadow = [p.clone()] (after the broadcast)
+        self.buckets, self.bucket_of = plan_buckets([(p, *self.index[p]) for p in params], bucket_bytes,
+                                                    first_bucket_bytes=first_bucket_bytes, tail_bucket_bytes=tail_bucket_bytes)
         self.pw = PackedTrainWeights(net)                          # after aliasing: the table holds arena pointers
         # overlap_wgrad: weight-gradient GEMMs (tensor-bound) run on a side stream concurrently with the next unit's
         # BatchNorm-backward passes (HBM-bound)
@@ -513,8 +553,30 @@ class FusedTrainer:
         self.net.invalidate_packed_weights()
         return self._loss.clone()
 
+    def backward_only(self, x, target, reduce=True) -> torch.Tensor:
+        """forward + loss + backward WITHOUT the optimizer update; returns a copy of the flat gradient arena (summed over
+        ranks when `reduce`, this rank's own gradient otherwise).  Verification aid for the data-parallel path
+        (bench.py / tests: reduced gradient == mean of per-rank gradients); BatchNorm running statistics do advance."""
+        net, pw, env = self.net, self.pw, self.env
+        self.main_stream_for_step = torch.cuda.current_stream()
+        pw.repack()
+        env.begin_step()
+        y, ctx = train_forward(net, x, pw, env=env)
+        _, dy = ops.mse(y, target.contiguous().float(), loss=env.zeros(1, y.device))
+        train_backward(net, ctx, dy, pw, grads=_ArenaSink(self, reduce=reduce), env=env)
+        if self.world > 1 and reduce:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        net.invalidate_packed_weights()
+        return self.flat_g.clone()
+
+    def param_checksum(self) -> torch.Tensor:
+        """(sum p, sum p^2, sum shadow) in fp64 -- replicas in sync hold bit-identical values"""
+        p, sh = self.flat_p.double(), self.shadow.double()
+        return torch.stack([p.sum(), (p * p).sum(), sh.sum()])
+
     def _step_impl(self, x, target) -> torch.Tensor:
         net, pw, env = self.net, self.pw, self.env
+        self.main_stream_for_step = torch.cuda.current_stream()
         pw.repack()                                                # every layer's bf16 operands: one launch
         env.begin_step()                                           # one memset + one negate for all layers
         y, ctx = train_forward(net, x, pw, env=env)
@@ -530,22 +592,65 @@ class FusedTrainer:
         return loss
 
 
-def plan_buckets(entries, bucket_bytes):
+def plan_buckets(entries, bucket_bytes, first_bucket_bytes=None, tail_bucket_bytes=None):
     """entries: [(key, offset, numel)] in parameter (= arena) order.  Gradients appear in REVERSE order during backward,
-    so buckets are contiguous arena ranges grown from the end.  -> ([{lo, hi, params}], {key: bucket index})"""
+    so buckets are contiguous arena ranges grown from the end.  -> ([{lo, hi, params}], {key: bucket index})
+
+    first_bucket_bytes: size at which the FIRST bucket closes (small: the first all-reduce starts right after the head /
+    last decoder block instead of half-way through backward).  tail_bucket_bytes: the parameters whose gradients arrive
+    LAST (the start of the arena: inc.*, down.0.*) form their own bucket of at most about this size, so the all-reduce
+    that cannot overlap anything is short."""
+    rev = list(reversed(entries))
+    n_tail = 0
+    if tail_bucket_bytes:
+        acc = 0
+        for key, off, k in entries:                      # arena order == reverse arrival order
+            if acc + 4 * k > tail_bucket_bytes and n_tail > 0:
+                break
+            acc += 4 * k
+            n_tail += 1
+            if acc >= tail_bucket_bytes:
+                break
+        if n_tail >= len(entries):
+            n_tail = 0
+    body, tail = (rev[:len(rev) - n_tail], rev[len(rev) - n_tail:]) if n_tail else (rev, [])
     buckets, bucket_of = [], {}
     cur = None
-    for key, off, k in reversed(entries):
+    for key, off, k in body:
         if cur is None:
             cur = {"lo": off, "hi": off + k, "params": []}
         cur["lo"] = off
         cur["params"].append(key)
-        if (cur["hi"] - cur["lo"]) * 4 >= bucket_bytes:
+        limit = first_bucket_bytes if (first_bucket_bytes and not buckets) else bucket_bytes
+        if (cur["hi"] - cur["lo"]) * 4 >= limit:
             buckets.append(cur)
             cur = None
     if cur is not None:
         buckets.append(cur)
+    if tail:
+        buckets.append({"lo": tail[-1][1], "hi": tail[0][1] + tail[0][2], "params": [key for key, _, _ in tail]})
     for i, b in enumerate(buckets):
         for key in b["params"]:
             bucket_of[key] = i
     return buckets, bucket_of
+
+
+def broadcast_module_state(net, flat_p, process_group=None, src=0):
+    """rank `src`'s parameters (one flat arena) and BatchNorm buffers -> every rank (DistributedDataParallel's
+    construction-time broadcast, torch/nn/parallel/distributed.py `_sync_module_states`)."""
+    dist = torch.distributed
+    dist.broadcast(flat_p, src, group=process_group)
+    bufs = [b for b in net.buffers()]
+    if not bufs:
+        return
+    fl = [b for b in bufs if b.is_floating_point()]
+    it = [b for b in bufs if not b.is_floating_point()]
+    for group in (fl, it):
+        if not group:
+            continue
+        flat = torch.cat([b.detach().reshape(-1) for b in group])
+        dist.broadcast(flat, src, group=process_group)
+        off = 0
+        for b in group:
+            b.data.copy_(flat[off:off + b.numel()].view_as(b))
+            off += b.numel()

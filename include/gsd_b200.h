@@ -113,6 +113,15 @@ int gsd_plan_first_fused(const gsd_plan* p);
 int gsd_pack_weights(gsd_plan* p, const void* const* params, const void* const* bn_buffers,
                      void* packed, void* stream);
 
+/* The same, but only if the parameters / BatchNorm buffers CHANGED since `packed` was last written -- decided on the
+ * device from a 64-bit content fingerprint, so writes the host cannot see are caught too: torch_ema 0.3's copy_to /
+ * restore and the reference's weight init write through `param.data` (train_unet.py:248-250,389,428,480), which bypasses
+ * torch's tensor version counters, and the training kernels of this library update parameters through raw pointers.
+ * state: 4 x uint64 in device memory, zero-initialised by the caller whenever `packed` is (re)allocated; two launches
+ * (fingerprint, gated pack), asynchronous on `stream`, no host synchronisation. */
+int gsd_pack_weights_if_changed(gsd_plan* p, const void* const* params, const void* const* bn_buffers, void* packed,
+                                unsigned long long* state, void* stream);
+
 /* Replaces: UNet.forward (unet.py:79-88) and, with a non-trivial gsd_prepost, the whole of
  * predict_depth_from_RGB (complete_prediction.py:4-10).
  * x:    fp32 (or uint8, see gsd_prepost.input_u8) NCHW (batch, in_channels, raw_height, raw_width)
@@ -277,6 +286,69 @@ int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, float* shadow,
 int gsd_op_adam_ema_dev(float* p, const float* g, float* m, float* v, float* shadow, long long n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, float ema_decay, long long* counter, float grad_scale,
                         void* stream);
+
+/* --- training plan: the loop body of train_utils/train_unet.py:346-377 sequenced by the library --------------------------
+ *     optimizer.zero_grad(); output = unet(x=input); loss = MSE_loss(output, target); loss.backward();
+ *     optimizer.step(); ema.update()
+ * One gsd_train_plan per (geometry with mode = GSD_MODE_TRAIN, device).  All memory is the caller's: the workspace
+ * (gsd_train_plan_workspace_bytes: saved activations, gradient temporaries, bf16 operands, per-layer constants), the fp32
+ * parameters / gradients / BatchNorm buffers (pointers in nn.Module.parameters() order, see gsd_pack_weights) and the
+ * optimizer arenas.  Every call below only enqueues library kernels and memset / copy nodes on `stream` (plus a plan-owned
+ * side stream that is forked from and joined back into it with events): no allocation, no host synchronisation, CUDA-graph
+ * capturable.  gsd_train_plan_bind is the one exception (uploads small tables, synchronises). */
+typedef struct gsd_train_plan gsd_train_plan;
+/* Fires on the HOST while the step is being enqueued: bucket >= 0 -- the last gradient kernel of gradient bucket `bucket`
+ * (flat-arena elements [lo, hi), see gsd_train_plan_set_buckets) has just been enqueued on main_stream / side_stream
+ * (NULL if not in use): order the communication stream after both and enqueue the all-reduce of that range (replaces the
+ * reducer hooks of torch DistributedDataParallel around train_unet.py:374).  bucket == -1 (gsd_train_step only): backward
+ * is fully enqueued, the optimizer kernel comes next: make main_stream wait for the communication stream. */
+typedef void (*gsd_bucket_cb)(void* user, int bucket, long long lo, long long hi, void* main_stream, void* side_stream);
+typedef struct gsd_adam {
+  float lr, beta1, beta2, eps, weight_decay;  /* torch.optim.Adam(lr=1e-3, weight_decay=1e-6), train_unet.py:306 */
+  float ema_decay;                            /* torch_ema ExponentialMovingAverage(decay=0.995), train_unet.py:309 */
+  float grad_scale;                           /* multiplies the gradient first: 1 / world_size after a sum all-reduce */
+} gsd_adam;
+typedef struct gsd_optimizer_state {
+  float* params;        /* flat fp32 arena the bound parameter pointers alias, n elements */
+  const float* grads;   /* flat arena the bound gradient pointers alias */
+  float* m;             /* Adam first / second moments */
+  float* v;
+  float* ema;           /* EMA shadow, or NULL */
+  long long n;
+  long long* counter;   /* device int64[2]: Adam steps / EMA updates done so far (advanced on the device) */
+  gsd_adam hp;
+} gsd_optimizer_state;
+/* Replaces: UNet(...).train() + the shape specialisation of the first step (train_unet.py:235,344). */
+int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g, int device);
+void gsd_train_plan_destroy(gsd_train_plan* p);
+size_t gsd_train_plan_workspace_bytes(const gsd_train_plan* p);
+int gsd_train_plan_num_params(const gsd_train_plan* p);
+int gsd_train_plan_num_bn(const gsd_train_plan* p);
+/* element count of every parameter in parameters() order (to lay out flat arenas); returns the number of parameters */
+int gsd_train_plan_param_numel(const gsd_train_plan* p, long long* out, int capacity);
+/* kernel launches one gsd_train_step enqueues */
+int gsd_train_plan_launches(const gsd_train_plan* p);
+/* params / grads: fp32 device pointers in parameters() order; bn_buffers: (running_mean, running_var) per BatchNorm in
+ * module order; num_batches_tracked: int64 device pointers per BatchNorm, or NULL.  Re-bind whenever a pointer changes. */
+int gsd_train_plan_bind(gsd_train_plan* p, const void* const* params, void* const* grads, void* const* bn_buffers,
+                        long long* const* num_batches_tracked, void* workspace);
+/* Gradient buckets for the data-parallel all-reduce: bucket_of_param[i] in [0, n_buckets), bucket b covers flat-arena
+ * elements [lo[b], hi[b]).  n_buckets == 0 disables the callback. */
+int gsd_train_plan_set_buckets(gsd_train_plan* p, int n_buckets, const int* bucket_of_param, const long long* lo,
+                               const long long* hi);
+/* Replaces: `output = unet(x=input)` in .train() mode (train_unet.py:347; UNet.forward unet.py:79-88 with batch-statistics
+ * BatchNorm: running statistics updated in place with momentum 0.1 / unbiased variance, num_batches_tracked += 1). */
+int gsd_train_forward(gsd_train_plan* p, const float* x, float* y, void* stream);
+/* Replaces: `loss.backward()` (train_unet.py:374) given dy = d loss / d output (fp32 NCHW): dgrad / wgrad as tcgen05
+ * GEMMs, BatchNorm / ReLU / max-pool / transposed-conv backward; every parameter gradient lands at its bound pointer. */
+int gsd_backward(gsd_train_plan* p, const float* dy, void* stream, gsd_bucket_cb cb, void* user);
+/* Replaces: `optimizer.step(); ema.update()` (train_unet.py:375-376) over flat arenas. */
+int gsd_adam_ema_step(float* param_arena, const float* grad_arena, float* m, float* v, float* ema, long long n,
+                      const gsd_adam* hp, long long* counter, void* stream);
+/* Replaces: the whole loop body (train_unet.py:346-377).  loss: device float, overwritten with MSE_loss(output, target)
+ * (train_unet.py:51-52); opt == NULL stops after backward (gradients only). */
+int gsd_train_step(gsd_train_plan* p, const float* x, const float* target, float* loss, const gsd_optimizer_state* opt,
+                   void* stream, gsd_bucket_cb cb, void* user);
 
 /* Stand-alone processing helper: fp32 NCHW -> fp32 NCHW,
  *   out[:, c] = scale8[min(c,7)] * area_resample(use_diff ? (x - base + 255)/2 : x) + shift8[min(c,7)]

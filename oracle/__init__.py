@@ -11,7 +11,7 @@ container by ``tests/golden/make_golden.py`` (which imports ``/root/reference``)
 as small fixtures under ``tests/golden/``; ``tests/test_oracle_golden.py`` replays them.
 """
 from .unet_oracle import (unet_forward, unet_forward_with_taps, conditioned_state_dict,
-                          trainer_init_state_dict, state_dict_digest)
+                          trainer_init_state_dict, random_init_state_dict, state_dict_digest)
 from .processing_oracle import (get_difference_image, area_resample, normalize_tactile_image,
                                 denormalize_depth_image, normalize_depth_image,
                                 predict_depth_from_RGB, split_fingers, blur_depth_images,

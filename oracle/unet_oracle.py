@@ -138,6 +138,34 @@ def conditioned_state_dict(sd: Dict[str, torch.Tensor], seed: int = 0) -> Dict[s
     return out
 
 
+def random_init_state_dict(n_channels: int, n_classes: int, dims=(64, 128, 256, 512, 1024), seed: int = 0) -> Dict[str, torch.Tensor]:
+    """The state_dict `torch.manual_seed(seed); UNet(n_channels, n_classes, dims)` yields (unet.py:60-77), built from
+    plain torch.nn layers created in the reference's construction order (DoubleConv: conv, BN, conv, BN; Down: the same
+    behind a MaxPool; Up: ConvTranspose2d then DoubleConv; OutConv last), so the default-init RNG stream and the key
+    order are the reference's.  Lets the CPU baseline draw its weights without importing the product package."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def double(prefix, cin, cout):
+        for ci, bi, (a, b) in ((0, 1, (cin, cout)), (3, 4, (cout, cout))):
+            conv, bn = nn.Conv2d(a, b, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(b)
+            sd[f"{prefix}.double_conv.{ci}.weight"] = conv.weight.detach()
+            for k, v in bn.state_dict().items():
+                sd[f"{prefix}.double_conv.{bi}.{k}"] = v.detach()
+
+    double("inc", n_channels, dims[0])
+    for i, (lo, hi) in enumerate(zip(dims[:-1], dims[1:])):
+        double(f"down.{i}.maxpool_conv.1", lo, hi)
+    for i, (hi, lo) in enumerate(zip(dims[:0:-1], dims[-2::-1])):
+        up = nn.ConvTranspose2d(hi, hi // 2, kernel_size=2, stride=2)
+        sd[f"up.{i}.up.weight"], sd[f"up.{i}.up.bias"] = up.weight.detach(), up.bias.detach()
+        double(f"up.{i}.conv", hi, lo)
+    outc = nn.Conv2d(dims[0], n_classes, kernel_size=1)
+    sd["outc.conv.weight"], sd["outc.conv.bias"] = outc.weight.detach(), outc.bias.detach()
+    return sd
+
+
 def trainer_init_state_dict(sd: Dict[str, torch.Tensor], seed: int = 0) -> Dict[str, torch.Tensor]:
     """train_unet.py:248-250: every parameter whose name contains 'weight' (conv, convT, outc
     AND BatchNorm gamma) is re-drawn N(0, 0.01^2); biases and buffers keep their values."""

@@ -1,5 +1,6 @@
-"""world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: gradient bucketing / all-reduce / 1/world scaling
-used by FusedTrainer, and the frame sharding of batch-sharded inference."""
+"""world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: the bucket planner, the BucketReducer that FusedTrainer's
+gradient sink drives during backward (the same class, with gloo's all_reduce as the launcher), the 1/world gradient scale,
+the construction-time broadcast of rank 0's model, and the frame sharding of batch-sharded inference."""
 import os
 import sys
 
@@ -10,19 +11,57 @@ import torch.multiprocessing as mp
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
+def _unet_entries():
+    """(name, offset, numel) of UNet(6,2)'s 64 parameters in arena order, without instantiating 31 M floats"""
+    dims = [64, 128, 256, 512, 1024]
+    sizes = []
+
+    def double(a, b):
+        sizes.extend([b * a * 9, b, b, b * b * 9, b, b])
+
+    double(6, dims[0])
+    for lo, hi in zip(dims[:-1], dims[1:]):
+        double(lo, hi)
+    for hi, lo in zip(dims[:0:-1], dims[-2::-1]):
+        sizes.extend([hi * (hi // 2) * 4, hi // 2])
+        double(hi, lo)
+    sizes.extend([2 * 64, 2])
+    entries, off = [], 0
+    for i, k in enumerate(sizes):
+        entries.append((i, off, k))
+        off += k
+    return entries, off
+
+
+def test_bucket_plan_of_the_full_unet():
+    sys.path.insert(0, ROOT)
+    from gelslim_depth_b200.train.engine import plan_buckets
+    entries, total = _unet_entries()
+    assert len(entries) == 64 and total > 31_000_000
+    buckets, bucket_of = plan_buckets(entries, 25 << 20, first_bucket_bytes=4 << 20, tail_bucket_bytes=2 << 20)
+    # contiguous cover of the arena, formed from its END (backward order); every parameter in exactly one bucket
+    assert sorted(k for b in buckets for k in b["params"]) == list(range(64))
+    assert buckets[0]["hi"] == total and buckets[-1]["lo"] == 0
+    for a, b in zip(buckets[:-1], buckets[1:]):
+        assert b["hi"] == a["lo"]
+    mb = [(b["hi"] - b["lo"]) * 4 / 2 ** 20 for b in buckets]
+    assert mb[0] <= 8, mb          # the first all-reduce starts after the head + last decoder blocks
+    assert mb[-1] <= 2.5, mb       # the all-reduce that nothing can hide (inc.*, down.0.*) is short
+    assert 63 in buckets[0]["params"] and 0 in buckets[-1]["params"]
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from gelslim_depth_b200.train.engine import plan_buckets
+    from gelslim_depth_b200.train.engine import BucketReducer, broadcast_module_state, plan_buckets
     sizes = [1728, 64, 64, 36864, 64, 64, 73728, 128, 128, 147456, 2097152, 512, 128, 2]     # mini parameter list
     entries, off = [], 0
     for i, k in enumerate(sizes):
         entries.append((i, off, k))
         off += k
-    buckets, bucket_of = plan_buckets(entries, bucket_bytes=1 << 20)
-    # every parameter in exactly one bucket, buckets contiguous, formed from the END of the arena (backward order)
+    buckets, bucket_of = plan_buckets(entries, bucket_bytes=1 << 20, first_bucket_bytes=1 << 10, tail_bucket_bytes=1 << 13)
     assert sorted(k for b in buckets for k in b["params"]) == list(range(len(sizes)))
     assert buckets[0]["hi"] == off and buckets[-1]["lo"] == 0
     for a, b in zip(buckets[:-1], buckets[1:]):
@@ -30,17 +69,42 @@ def _worker(rank, world, port, q):
     g = torch.Generator().manual_seed(100 + rank)
     flat = torch.randn(off, generator=g)
     mine = flat.clone()
-    pending = [len(b["params"]) for b in buckets]
-    for i in reversed(range(len(sizes))):               # gradients become ready in reverse parameter order
-        bi = bucket_of[i]
-        pending[bi] -= 1
-        if pending[bi] == 0:
-            dist.all_reduce(flat[buckets[bi]["lo"]:buckets[bi]["hi"]])
+    # the reducer FusedTrainer uses, with gloo's all_reduce as the launcher; gradients become ready in reverse order
+    launches = []
+
+    def launch(lo, hi):
+        launches.append((lo, hi))
+        dist.all_reduce(flat[lo:hi])
+
+    red = BucketReducer(buckets, bucket_of, launch)
+    for i in reversed(range(len(sizes))):
+        red.done(i)
+    assert red.all_fired() and red.fired == list(range(len(buckets)))      # buckets fire in arena-END-first order
+    assert launches[0][1] == off and launches[-1][0] == 0
     flat *= 1.0 / world                                   # grad_scale of gsd_op_adam_ema
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine)
     want = sum(gathered) / world
     ok = torch.allclose(flat, want, rtol=1e-6, atol=1e-6)
+    try:
+        red.done(0)
+        ok = False                                        # a second report for one parameter must raise
+    except RuntimeError:
+        pass
+    # construction-time broadcast (DistributedDataParallel semantics): replicas built from different seeds end up
+    # with rank 0's parameters AND BatchNorm buffers (float and int64)
+    torch.manual_seed(1234 + rank)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8))
+    with torch.no_grad():
+        net[1].running_mean.normal_()
+        net[1].num_batches_tracked.fill_(7 + rank)
+    flat_p = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    broadcast_module_state(net, flat_p)
+    state = torch.cat([flat_p, net[1].running_mean, net[1].running_var, net[1].num_batches_tracked.float().reshape(1)])
+    lo_, hi_ = state.clone(), state.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    ok = ok and torch.equal(lo_, hi_) and int(net[1].num_batches_tracked) == 7
     # batch-sharded inference: frames [rank*B, (rank+1)*B) per rank, throughput adds up (bench.py weak scaling)
     frames = torch.tensor([64.0 * 5])
     dist.all_reduce(frames)
@@ -48,7 +112,7 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_and_sharding_gloo():
+def test_bucketed_allreduce_broadcast_and_sharding_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000

@@ -180,6 +180,28 @@ def test_unet_forward_vs_oracle_odd_geometry():
         net.outc.conv.bias.add_(1.0)
     y2 = net(x=x.to(dev()))
     assert torch.allclose(y2, y + 1.0, atol=1e-5)
+    # ... and the writes torch's version counters do NOT see: torch_ema 0.3's copy_to / restore and the reference's weight
+    # init go through `param.data` (train_unet.py:248-250,389,428,480); the packed-operand cache is keyed on a device-side
+    # content fingerprint, so the next eval forward still runs the new weights, and an unchanged model does not re-pack
+    assert int(net._pack_state[1]) == 1                      # the add_ above was seen as a change ...
+    y2b = net(x=x.to(dev()))
+    assert int(net._pack_state[1]) == 0 and torch.equal(y2b, y2)      # ... and nothing changed since
+    v0 = net.outc.conv.bias._version
+    net.outc.conv.bias.data.copy_(net.outc.conv.bias.data - 1.0)
+    assert net.outc.conv.bias._version == v0                 # invisible to the host
+    y3 = net(x=x.to(dev()))
+    assert int(net._pack_state[1]) == 1 and torch.allclose(y3, y, atol=1e-5)
+    bn = net.inc.double_conv[1]
+    bn.running_mean.data.add_(0.25)                          # raw write to a BatchNorm buffer (what the training kernels do)
+    sd2 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    y4 = net(x=x.to(dev()))
+    assert rel_l2(y4, oracle.unet_forward(sd2, x)) < 2e-2 and not torch.allclose(y4, y, atol=1e-3)
+    # serving mode: the caller promises frozen weights, the check is skipped (documented contract)
+    net.frozen_weights(True)
+    bn.running_mean.data.sub_(0.25)
+    assert torch.equal(net(x=x.to(dev())), y4)
+    net.frozen_weights(False)
+    assert torch.allclose(net(x=x.to(dev())), y, atol=1e-5)
 
 
 def shipped_cfg(size, tactile_spelling=False):
