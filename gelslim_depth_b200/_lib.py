@@ -34,6 +34,20 @@ class PrePost(C.Structure):
                 ("split_fingers", C.c_int32), ("input_u8", C.c_int32)]
 
 
+class Adam(C.Structure):               # gsd_adam
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("ema_decay", C.c_float), ("grad_scale", C.c_float)]
+
+
+class OptimizerState(C.Structure):     # gsd_optimizer_state
+    _fields_ = [("params", C.c_void_p), ("grads", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("ema", C.c_void_p),
+                ("n", C.c_longlong), ("counter", C.c_void_p), ("hp", Adam)]
+
+
+# gsd_bucket_cb(user, bucket, lo, hi, main_stream, side_stream)
+BUCKET_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p)
+NULL_CB = C.cast(None, BUCKET_CB)      # "no callback"
+
 # name -> (restype, argtypes): every symbol include/gsd_b200.h declares
 SYMBOLS = {
     "gsd_abi_version": (C.c_int, []),
@@ -95,6 +109,23 @@ SYMBOLS = {
     "gsd_op_pack_weights_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "gsd_pack_item_units": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gsd_op_adam_ema": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_longlong, C.c_float, C.c_longlong, C.c_float, C.c_void_p]),
+    "gsd_train_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Geometry), C.c_int]),
+    "gsd_debug_train_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Geometry)]),
+    "gsd_train_plan_destroy": (None, [C.c_void_p]),
+    "gsd_train_plan_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "gsd_train_plan_num_params": (C.c_int, [C.c_void_p]),
+    "gsd_train_plan_num_bn": (C.c_int, [C.c_void_p]),
+    "gsd_train_plan_param_numel": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]),
+    "gsd_train_plan_launches": (C.c_int, [C.c_void_p]),
+    "gsd_train_plan_bind": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_void_p), C.c_void_p]),
+    "gsd_train_plan_set_buckets": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "gsd_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsd_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, BUCKET_CB, C.c_void_p]),
+    "gsd_adam_ema_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(Adam), C.c_void_p,
+                                    C.c_void_p]),
+    "gsd_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OptimizerState), C.c_void_p, BUCKET_CB,
+                                 C.c_void_p]),
     "gsd_op_image_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p]),

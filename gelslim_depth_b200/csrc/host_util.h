@@ -98,6 +98,7 @@ inline int encode_bf16_map(CUtensorMap* m, void* base, int rank, const uint64_t*
 class DeviceGuard {
  public:
   explicit DeviceGuard(int device) {
+    if (device < 0) return;          // host-only call (dry-run plans of the CPU tests)
     err_ = cudaGetDevice(&prev_);
     if (err_ == cudaSuccess && prev_ != device) {
       err_ = cudaSetDevice(device);

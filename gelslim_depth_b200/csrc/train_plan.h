@@ -64,6 +64,11 @@ __global__ void __launch_bounds__(256) zero_frame_kernel(__nv_bfloat16* __restri
 
 }  // namespace
 
+static bool& dry_create_mode() {
+  static thread_local bool on = false;
+  return on;
+}
+
 struct gsd_train_plan {
   gsd_geometry g{};
   int device = 0, num_sms = 148, depth = 0;
@@ -95,11 +100,18 @@ struct gsd_train_plan {
   size_t ev_next = 0;
   bool forked = false;
   int overlap = 1;
+  bool dry = false;      // gsd_debug_train_plan_create: walk the step's structure (gradient order, bucket callbacks) without a GPU
   // per-call
   gsd_bucket_cb cb = nullptr;
   void* cb_user = nullptr;
   cudaStream_t main = nullptr;
 };
+
+// every launch of the backward pass goes through this: the dry-run plan of the CPU tests enqueues nothing
+#define TP_RUN(p, expr)            \
+  do {                             \
+    if (!(p)->dry) GSD_TRY(expr);  \
+  } while (0)
 
 namespace {
 
@@ -122,6 +134,7 @@ cudaEvent_t next_event(gsd_train_plan* p) {
 // far on the main stream
 int side_begin(gsd_train_plan* p, cudaStream_t* st) {
   if (!p->overlap) { *st = p->main; return 0; }
+  if (p->dry) { p->forked = true; *st = p->side; return 0; }
   cudaEvent_t e = next_event(p);
   GSD_CUDA(cudaEventRecord(e, p->main));
   GSD_CUDA(cudaStreamWaitEvent(p->side, e, 0));
@@ -131,6 +144,7 @@ int side_begin(gsd_train_plan* p, cudaStream_t* st) {
 }
 int side_join(gsd_train_plan* p) {
   if (!p->forked) return 0;
+  if (p->dry) { p->forked = false; return 0; }
   cudaEvent_t e = next_event(p);
   GSD_CUDA(cudaEventRecord(e, p->side));
   GSD_CUDA(cudaStreamWaitEvent(p->main, e, 0));
@@ -190,13 +204,13 @@ int unit_backward(gsd_train_plan* p, TrainUnit& u, const void* da, const float* 
     __nv_bfloat16* dzb = wsp<__nv_bfloat16>(p, u.dz);
     float* dw = p->grads[pw], *db = p->grads[pb];
     switch (p->g.n_classes) {
-      case 1: GSD_TRY(launch_head_bn_bwd<1>(zb, dy, w_head, scale, shift, mean, rstd, p->params[u.p_g], (float)npix, np, tot, dbeta, dw, db, dzb, st, dgamma)); break;
-      case 2: GSD_TRY(launch_head_bn_bwd<2>(zb, dy, w_head, scale, shift, mean, rstd, p->params[u.p_g], (float)npix, np, tot, dbeta, dw, db, dzb, st, dgamma)); break;
-      case 3: GSD_TRY(launch_head_bn_bwd<3>(zb, dy, w_head, scale, shift, mean, rstd, p->params[u.p_g], (float)npix, np, tot, dbeta, dw, db, dzb, st, dgamma)); break;
-      default: GSD_TRY(launch_head_bn_bwd<4>(zb, dy, w_head, scale, shift, mean, rstd, p->params[u.p_g], (float)npix, np, tot, dbeta, dw, db, dzb, st, dgamma)); break;
+      case 1: TP_RUN(p, launch_head_bn_bwd<1>(zb, dy, w_head, scale, shift, mean, rstd, p->params[u.p_g], (float)npix, np, tot, dbeta, dw, db, dzb, st, dgamma)); break;
+      case 2: TP_RUN(p, launch_head_bn_bwd<2>(zb, dy, w_head, scale, shift, mean, rstd, p->params[u.p_g], (float)npix, np, tot, dbeta, dw, db, dzb, st, dgamma)); break;
+      case 3: TP_RUN(p, launch_head_bn_bwd<3>(zb, dy, w_head, scale, shift, mean, rstd, p->params[u.p_g], (float)npix, np, tot, dbeta, dw, db, dzb, st, dgamma)); break;
+      default: TP_RUN(p, launch_head_bn_bwd<4>(zb, dy, w_head, scale, shift, mean, rstd, p->params[u.p_g], (float)npix, np, tot, dbeta, dw, db, dzb, st, dgamma)); break;
     }
   } else {
-    GSD_TRY(bn_bwd_launch(da, scale, shift, p->ws + u.z, mean, rstd, p->params[u.p_g], (double)npix, npix, u.Cout, dbeta, dgamma,
+    TP_RUN(p, bn_bwd_launch(da, scale, shift, p->ws + u.z, mean, rstd, p->params[u.p_g], (double)npix, npix, u.Cout, dbeta, dgamma,
                           p->ws + u.dz, st));
   }
   grad_done(p, u.p_b);
@@ -207,21 +221,21 @@ int unit_backward(gsd_train_plan* p, TrainUnit& u, const void* da, const float* 
     const char* wd = p->ws + u.w_dgrad;                        // [ci][9][co] bf16
     if (u.C1) {
       const size_t rows = (size_t)u.C0 * 9 * u.Cout * 2;       // bytes of the skip half
-      GSD_TRY(gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd, u.C0, 9, 1, nullptr, nullptr, 0,
+      TP_RUN(p, gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd, u.C0, 9, 1, nullptr, nullptr, 0,
                                     p->ws + u.din0, nullptr, nullptr, p->device, st));
-      GSD_TRY(gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd + rows, u.C1, 9, 1, nullptr, nullptr, 0,
+      TP_RUN(p, gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd + rows, u.C1, 9, 1, nullptr, nullptr, 0,
                                     p->ws + u.din1, nullptr, nullptr, p->device, st));
     } else {
-      GSD_TRY(gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd, u.C0, 9, 1, nullptr, nullptr, 0,
+      TP_RUN(p, gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd, u.C0, 9, 1, nullptr, nullptr, 0,
                                     p->ws + u.din0, nullptr, nullptr, p->device, st));
     }
   }
   cudaStream_t sw;
   GSD_TRY(side_begin(p, &sw));
   float* dwk = wsp<float>(p, u.dwk);
-  GSD_TRY(gsd_op_wgrad3x3_bf16(p->ws + u.src0, u.C0, u.C1 ? p->ws + u.src1 : nullptr, u.C1, u.H1, u.W1, u.off_y, u.off_x, p->ws + u.dz, u.Cout,
+  TP_RUN(p, gsd_op_wgrad3x3_bf16(p->ws + u.src0, u.C0, u.C1 ? p->ws + u.src1 : nullptr, u.C1, u.H1, u.W1, u.off_y, u.off_x, p->ws + u.dz, u.Cout,
                                B, u.H, u.W, dwk, p->device, sw));
-  GSD_TRY(gsd_op_unpack_wgrad(dwk, u.Cout, u.first ? u.cin_real : u.C0 + u.C1, u.C0 + u.C1, p->grads[u.p_w], 1, sw));
+  TP_RUN(p, gsd_op_unpack_wgrad(dwk, u.Cout, u.first ? u.cin_real : u.C0 + u.C1, u.C0 + u.C1, p->grads[u.p_w], 1, sw));
   grad_done(p, u.p_w);
   return 0;
 }
@@ -239,16 +253,21 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
   GSD_CHECK(g->dims[0] == 64, "gsd_train_plan_create: layer_dimensions[0] must be 64");
   for (int i = 0; i + 1 < g->n_dims; ++i)
     GSD_CHECK(g->dims[i + 1] == 2 * g->dims[i], "gsd_train_plan_create: layer_dimensions must double at every level (unet.py:48)");
-  int ndev = 0;
-  GSD_CUDA(cudaGetDeviceCount(&ndev));
-  GSD_CHECK(device >= 0 && device < ndev, "gsd_train_plan_create: device %d out of range (%d devices)", device, ndev);
-  int major = 0, sms = 0;
-  GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
-  GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  GSD_CHECK(major == 10, "gsd_train_plan_create: device %d is sm_%d0; this library contains sm_100a code only (no fallback)", device, major);
-  GSD_DEVICE(device);
+  const bool dry = dry_create_mode();
+  int sms = 148;
+  if (!dry) {
+    int ndev = 0, major = 0;
+    GSD_CUDA(cudaGetDeviceCount(&ndev));
+    GSD_CHECK(device >= 0 && device < ndev, "gsd_train_plan_create: device %d out of range (%d devices)", device, ndev);
+    GSD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    GSD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    GSD_CHECK(major == 10, "gsd_train_plan_create: device %d is sm_%d0; this library contains sm_100a code only (no fallback)", device, major);
+  }
+  DeviceGuard guard(dry ? -1 : device);
+  GSD_TRY(guard.status());
 
   gsd_train_plan* p = new gsd_train_plan();
+  p->dry = dry;
   p->g = *g;
   p->device = device;
   p->num_sms = sms;
@@ -358,12 +377,28 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
     p->dec[2 * i].src1 = p->ups[i].u;
     p->dec[2 * i + 1].src0 = p->dec[2 * i].a;
   }
-  GSD_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
-  p->events.resize(192);
-  for (auto& e : p->events) GSD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (!dry) {
+    GSD_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    p->events.resize(192);
+    for (auto& e : p->events) GSD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   if (getenv("GSD_NO_WGRAD_OVERLAP")) p->overlap = 0;
+  if (dry) {               // nothing is ever dereferenced, but the tables are indexed
+    p->params.assign(p->n_params, nullptr);
+    p->grads.assign(p->n_params, nullptr);
+    p->bnbuf.assign(2 * p->n_bn, nullptr);
+  }
   *out = p;
   return 0;
+}
+
+// The same plan without a GPU: layout and step structure only.  gsd_backward on it enqueues nothing but reports gradients
+// and buckets in the real order (tests/test_ddp_cpu.py drives the data-parallel host logic with it).
+extern "C" int gsd_debug_train_plan_create(gsd_train_plan** out, const gsd_geometry* g) {
+  dry_create_mode() = true;
+  const int rc = gsd_train_plan_create(out, g, 0);
+  dry_create_mode() = false;
+  return rc;
 }
 
 extern "C" void gsd_train_plan_destroy(gsd_train_plan* p) {
@@ -513,16 +548,19 @@ extern "C" int gsd_train_forward(gsd_train_plan* p, const float* x, float* y, vo
 // the last gradient kernel of that bucket was enqueued: (user, bucket, lo, hi, main stream, side stream or NULL).
 extern "C" int gsd_backward(gsd_train_plan* p, const float* dy, void* stream, gsd_bucket_cb cb, void* user) {
   GSD_CHECK(p && dy, "gsd_backward: null argument");
-  GSD_CHECK(p->bound, "gsd_backward: call gsd_train_plan_bind first");
-  GSD_DEVICE(p->device);
+  GSD_CHECK(p->bound || p->dry, "gsd_backward: call gsd_train_plan_bind first");
+  DeviceGuard guard(p->dry ? -1 : p->device);
+  GSD_TRY(guard.status());
   p->main = static_cast<cudaStream_t>(stream);
   p->cb = cb; p->cb_user = user;
   p->pending = p->bucket_size;
   p->forked = false;
   cudaStream_t st = p->main;
   const int B = p->g.batch, depth = p->depth;
-  prep_kernel<<<p->n_prep_bwd, 256, 0, st>>>(wsp<PrepItem>(p, p->prep_bwd));
-  GSD_CUDA(cudaGetLastError());
+  if (!p->dry) {
+    prep_kernel<<<p->n_prep_bwd, 256, 0, st>>>(wsp<PrepItem>(p, p->prep_bwd));
+    GSD_CUDA(cudaGetLastError());
+  }
   const void* da = nullptr;
   // ---- decoder, last block first
   for (int i = depth - 1; i >= 0; --i) {
@@ -534,20 +572,20 @@ extern "C" int gsd_backward(gsd_train_plan* p, const float* dy, void* stream, gs
     GSD_TRY(unit_backward(p, u1, p->ws + u2.din0, nullptr, true));
     TrainUp& t = p->ups[i];
     // transposed conv: only the (2hs x 2ws) window of u1.din1 at (off_y, off_x) is its output gradient, the rest is F.pad
-    if (u1.H != 2 * t.hs || u1.W != 2 * t.ws) {
+    if (!p->dry && (u1.H != 2 * t.hs || u1.W != 2 * t.ws)) {
       const long border = (long)B * ((long)u1.H * u1.W - 4L * t.hs * t.ws) * (t.Cout / 8);
       zero_frame_kernel<<<ew_grid(border), 256, 0, st>>>(wsp<__nv_bfloat16>(p, u1.din1), B, u1.H, u1.W, t.Cout / 8, u1.off_y, u1.off_x, 2 * t.hs,
                                                          2 * t.ws);
       GSD_CUDA(cudaGetLastError());
     }
-    GSD_TRY(gsd_op_convt_dgrad_bf16(p->ws + u1.din1, t.Cout, u1.H, u1.W, u1.off_y, u1.off_x, p->ws + t.w_dgrad, t.Cin, B, t.hs, t.ws, nullptr, nullptr,
+    TP_RUN(p, gsd_op_convt_dgrad_bf16(p->ws + u1.din1, t.Cout, u1.H, u1.W, u1.off_y, u1.off_x, p->ws + t.w_dgrad, t.Cin, B, t.hs, t.ws, nullptr, nullptr,
                                     p->ws + t.din, p->device, st));
     cudaStream_t sw;
     GSD_TRY(side_begin(p, &sw));
-    GSD_TRY(gsd_op_bn_bwd_reduce(p->ws + u1.din1, nullptr, nullptr, nullptr, nullptr, nullptr, (long long)B * u1.H * u1.W, t.Cout, p->grads[t.p_b], sw));
+    TP_RUN(p, gsd_op_bn_bwd_reduce(p->ws + u1.din1, nullptr, nullptr, nullptr, nullptr, nullptr, (long long)B * u1.H * u1.W, t.Cout, p->grads[t.p_b], sw));
     grad_done(p, t.p_b);
-    GSD_CUDA(cudaMemsetAsync(p->grads[t.p_w], 0, (size_t)4 * t.Cin * t.Cout * 4, sw));
-    GSD_TRY(gsd_op_convt_wgrad_bf16(p->ws + t.src, t.Cin, p->ws + u1.din1, t.Cout, u1.H, u1.W, u1.off_y, u1.off_x, B, t.hs, t.ws, p->grads[t.p_w],
+    if (!p->dry) GSD_CUDA(cudaMemsetAsync(p->grads[t.p_w], 0, (size_t)4 * t.Cin * t.Cout * 4, sw));
+    TP_RUN(p, gsd_op_convt_wgrad_bf16(p->ws + t.src, t.Cin, p->ws + u1.din1, t.Cout, u1.H, u1.W, u1.off_y, u1.off_x, B, t.hs, t.ws, p->grads[t.p_w],
                                     p->device, sw));
     grad_done(p, t.p_w);
     da = p->ws + t.din;
@@ -558,7 +596,7 @@ extern "C" int gsd_backward(gsd_train_plan* p, const float* dy, void* stream, gs
     TrainUnit& u2 = p->enc[2 * l + 1];
     if (l < depth) {
       // dpool from level l+1 + the skip-connection gradient of decoder block depth-1-l
-      GSD_TRY(gsd_op_maxpool_bwd(p->ws + u2.a, p->ws + p->enc[2 * l + 2].din0, p->ws + p->dec[2 * (depth - 1 - l)].din0, B, u2.H, u2.W, u2.Cout,
+      TP_RUN(p, gsd_op_maxpool_bwd(p->ws + u2.a, p->ws + p->enc[2 * l + 2].din0, p->ws + p->dec[2 * (depth - 1 - l)].din0, B, u2.H, u2.W, u2.Cout,
                                  p->ws + p->dfull[l], st));
       da = p->ws + p->dfull[l];
     }

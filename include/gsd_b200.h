@@ -350,6 +350,10 @@ int gsd_adam_ema_step(float* param_arena, const float* grad_arena, float* m, flo
 int gsd_train_step(gsd_train_plan* p, const float* x, const float* target, float* loss, const gsd_optimizer_state* opt,
                    void* stream, gsd_bucket_cb cb, void* user);
 
+/* Host-logic tests: the same plan without a GPU.  gsd_backward on it enqueues nothing but walks the real step structure,
+ * i.e. reports complete gradient buckets through the callback in the real order (tests/test_ddp_cpu.py). */
+int gsd_debug_train_plan_create(gsd_train_plan** out, const gsd_geometry* g);
+
 /* Stand-alone processing helper: fp32 NCHW -> fp32 NCHW,
  *   out[:, c] = scale8[min(c,7)] * area_resample(use_diff ? (x - base + 255)/2 : x) + shift8[min(c,7)]
  * Replaces (when called outside the fused forward): get_difference_image (image_utils.py:6-10),

@@ -1,6 +1,7 @@
-"""world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: the bucket planner, the BucketReducer that FusedTrainer's
-gradient sink drives during backward (the same class, with gloo's all_reduce as the launcher), the 1/world gradient scale,
-the construction-time broadcast of rank 0's model, and the frame sharding of batch-sharded inference."""
+"""world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: the bucket planner; the library's own backward driven as
+a DRY RUN (gsd_debug_train_plan_create: the real step structure, nothing enqueued), whose gsd_bucket_cb callbacks feed the
+BucketReducer FusedTrainer uses (here with gloo's all_reduce as the launcher); the 1/world gradient scale; the
+construction-time broadcast of rank 0's model; and the frame sharding of batch-sharded inference."""
 import os
 import sys
 
@@ -55,42 +56,60 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+    from gelslim_depth_b200 import _lib
+    from gelslim_depth_b200._lib import lib
     from gelslim_depth_b200.train.engine import BucketReducer, broadcast_module_state, plan_buckets
-    sizes = [1728, 64, 64, 36864, 64, 64, 73728, 128, 128, 147456, 2097152, 512, 128, 2]     # mini parameter list
+    # a small U-Net geometry: the library lays out its 28 parameters and walks its real backward structure (dry run)
+    g = _lib.Geometry()
+    g.batch, g.in_channels, g.height, g.width, g.n_classes, g.n_dims = 2, 3, 24, 29, 1, 3
+    for i, d in enumerate((64, 128, 256)):
+        g.dims[i] = d
+    g.dtype, g.mode = _lib.DTYPE_BF16, _lib.MODE_TRAIN
+    h = C.c_void_p()
+    assert lib.gsd_debug_train_plan_create(C.byref(h), C.byref(g)) == 0, lib.gsd_last_error()
+    n = lib.gsd_train_plan_num_params(h)
+    numel = (C.c_longlong * n)()
+    assert lib.gsd_train_plan_param_numel(h, numel, n) == n == 6 * 3 + 8 * 2 + 2
     entries, off = [], 0
-    for i, k in enumerate(sizes):
-        entries.append((i, off, k))
-        off += k
-    buckets, bucket_of = plan_buckets(entries, bucket_bytes=1 << 20, first_bucket_bytes=1 << 10, tail_bucket_bytes=1 << 13)
-    assert sorted(k for b in buckets for k in b["params"]) == list(range(len(sizes)))
+    for i, k in enumerate(numel):
+        entries.append((i, off, int(k)))
+        off += int(k)
+    buckets, bucket_of = plan_buckets(entries, bucket_bytes=1 << 20, first_bucket_bytes=1 << 16, tail_bucket_bytes=1 << 16)
+    assert len(buckets) >= 3 and sorted(k for b in buckets for k in b["params"]) == list(range(n))
     assert buckets[0]["hi"] == off and buckets[-1]["lo"] == 0
     for a, b in zip(buckets[:-1], buckets[1:]):
         assert b["hi"] == a["lo"]
-    g = torch.Generator().manual_seed(100 + rank)
-    flat = torch.randn(off, generator=g)
+    nb = len(buckets)
+    assert lib.gsd_train_plan_set_buckets(h, nb, (C.c_int * n)(*[bucket_of[i] for i in range(n)]),
+                                          (C.c_longlong * nb)(*[b["lo"] for b in buckets]),
+                                          (C.c_longlong * nb)(*[b["hi"] for b in buckets])) == 0
+    gen = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(off, generator=gen)            # this rank's "gradient arena"
     mine = flat.clone()
-    # the reducer FusedTrainer uses, with gloo's all_reduce as the launcher; gradients become ready in reverse order
     launches = []
 
     def launch(lo, hi):
         launches.append((lo, hi))
         dist.all_reduce(flat[lo:hi])
 
-    red = BucketReducer(buckets, bucket_of, launch)
-    for i in reversed(range(len(sizes))):
-        red.done(i)
-    assert red.all_fired() and red.fired == list(range(len(buckets)))      # buckets fire in arena-END-first order
-    assert launches[0][1] == off and launches[-1][0] == 0
-    flat *= 1.0 / world                                   # grad_scale of gsd_op_adam_ema
+    red = BucketReducer(nb, launch)
+    red.begin_step()
+    cb = _lib.BUCKET_CB(lambda user, bucket, lo, hi, main, side: red.on_bucket(bucket, lo, hi))
+    assert lib.gsd_backward(h, C.c_void_p(16), None, cb, None) == 0, lib.gsd_last_error()      # dry run: only the callbacks happen
+    ok = red.all_fired() and red.fired == list(range(nb))            # buckets complete in arena-END-first order
+    ok = ok and launches[0][1] == off and launches[-1][0] == 0
+    flat *= 1.0 / world                                   # grad_scale of gsd_adam_ema_step
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine)
     want = sum(gathered) / world
-    ok = torch.allclose(flat, want, rtol=1e-6, atol=1e-6)
+    ok = ok and torch.allclose(flat, want, rtol=1e-6, atol=1e-6)
     try:
-        red.done(0)
-        ok = False                                        # a second report for one parameter must raise
+        red.on_bucket(0, 0, 1)
+        ok = False                                        # a second report of one bucket in a step must raise
     except RuntimeError:
         pass
+    lib.gsd_train_plan_destroy(h)
     # construction-time broadcast (DistributedDataParallel semantics): replicas built from different seeds end up
     # with rank 0's parameters AND BatchNorm buffers (float and int64)
     torch.manual_seed(1234 + rank)

@@ -323,14 +323,71 @@ def test_fused_trainer_cuda_graph_matches_eager():
     assert curves[1][-1] < curves[1][0]
 
 
+def _blocks(net):
+    enc = [net.inc.double_conv] + [d.maxpool_conv[1].double_conv for d in net.down]
+    dec = [(u.up, u.conv.double_conv) for u in net.up]
+    return enc, dec
+
+
+class _PackedTrainWeights:
+    """test driver of gsd_op_pack_weights_batched: the same item table csrc/train_plan.h builds (forward + dgrad operands of
+    every layer, one launch), with the operands exposed per layer"""
+
+    def __init__(self, net):
+        from gelslim_depth_b200._lib import PackItem, lib
+        from gelslim_depth_b200.train import ops
+        enc, dec = _blocks(net)
+        self.fwd, self.dgrad = {}, {}
+        items = []          # (mode, param, O, I, Ipad, key, wants dgrad operand)
+        for bi, seq in enumerate(enc):
+            for ci in (0, 3):
+                w = seq[ci].weight
+                O, I = w.shape[:2]
+                first = bi == 0 and ci == 0
+                items.append((0, w, O, I, 16 if first else I, id(seq[ci]), not first))
+        for up, seq in dec:
+            I, O = up.weight.shape[:2]
+            items.append((2, up.weight, O, I, I, id(up), False))
+            items.append((3, up.weight, O, I, I, id(up), False))
+            for ci in (0, 3):
+                cw = seq[ci].weight
+                items.append((0, cw, cw.shape[0], cw.shape[1], cw.shape[1], id(seq[ci]), True))
+        device = items[0][1].device
+        al = lambda n: (n + 7) // 8 * 8                                  # every operand 16-byte aligned
+        elems = sum(al(ops.pack_out_elems(m, O, I, ip)) + (al(ops.pack_out_elems(1, O, I)) if dg else 0)
+                    for (m, _, O, I, ip, _, dg) in items)
+        self.arena = torch.empty(elems, dtype=torch.bfloat16, device=device)
+        table = (PackItem * len(items))()
+        cur, units = 0, 0
+        for k, (mode, w, O, I, ipad, key, dg) in enumerate(items):
+            n = ops.pack_out_elems(mode, O, I, ipad)
+            out = self.arena[cur:cur + n]
+            cur += al(n)
+            (self.dgrad if mode == 3 else self.fwd)[key] = out
+            table[k].w, table[k].out, table[k].out_dgrad = w.data_ptr(), out.data_ptr(), None
+            if dg:
+                n2 = ops.pack_out_elems(1, O, I)
+                self.dgrad[key] = self.arena[cur:cur + n2]
+                table[k].out_dgrad = self.dgrad[key].data_ptr()
+                cur += al(n2)
+            table[k].mode, table[k].O, table[k].I, table[k].Ipad, table[k].start = mode, O, I, ipad, units
+            units += lib.gsd_pack_item_units(mode, O, I, ipad)
+        self.n_items, self.total = len(items), units
+        self.table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(device)
+        self.repack()
+
+    def repack(self):
+        from gelslim_depth_b200.train import ops
+        ops.pack_weights_batched(self.table, self.n_items, self.total, self.arena.device)
+
+
 def test_batched_weight_pack_matches_per_layer_pack():
     """gsd_op_pack_weights_batched (one launch, tiled, forward + dgrad operands from one staged tile) is bit-identical
     to the per-layer gsd_op_pack_weight modes 0-3 for every layer, including the 6->16 channel padding of inc.0."""
     from gelslim_depth_b200.train import ops
-    from gelslim_depth_b200.train.engine import PackedTrainWeights, _blocks
     net, _ = make_net(6, 2, 11, dims=(64, 128, 256))
     net = net.to(dev()).train()
-    pw = PackedTrainWeights(net)
+    pw = _PackedTrainWeights(net)
     enc, dec = _blocks(net)
     n = 0
     for bi, seq in enumerate(enc):
@@ -394,3 +451,101 @@ def test_fused_last_unit_matches_unfused_ops(ncls):
     assert torch.allclose(sums, sums_ref, rtol=1e-5, atol=1e-4)
     diff = (dz.float() - dz_ref.float()).abs()
     assert float((diff > 2 ** -7 * dz_ref.float().abs() + 1e-6).float().mean()) == 0.0   # at most one bf16 ulp (sums order)
+
+
+def test_train_step_through_the_c_abi_only():
+    """gsd_train_plan_create / bind / gsd_train_step called through ctypes alone -- torch tensors are nothing but
+    the memory here (flat arenas the caller owns).  Three steps of train_unet.py:346-377 against oracle.TrainOracle, the
+    gradients of step 1 against the oracle's, and gsd_train_forward / gsd_backward / gsd_adam_ema_step called separately
+    against the one-call form."""
+    import ctypes as C
+    from gelslim_depth_b200 import _lib
+    from gelslim_depth_b200._lib import lib
+    cin, ncls, dims, B, H, W = 3, 1, (64, 128, 256), 2, 40, 53
+    net, sd = make_net(cin, ncls, 21, dims=dims)
+    names = [k for k, _ in net.named_parameters()]
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(B, cin, H, W, generator=g)
+    tgt = -0.9 * torch.rand(B, ncls, H, W, generator=g)
+    tr = oracle.TrainOracle(sd)
+    _, grads_ref, _, _ = tr.loss_and_grads(x, tgt)
+    ref_losses = [tr.step(x, tgt) for _ in range(3)]
+
+    geo = _lib.Geometry()
+    geo.batch, geo.in_channels, geo.height, geo.width, geo.n_classes, geo.n_dims = B, cin, H, W, ncls, len(dims)
+    for i, d in enumerate(dims):
+        geo.dims[i] = d
+    geo.dtype, geo.mode = _lib.DTYPE_BF16, _lib.MODE_TRAIN
+
+    def build():
+        """plan + caller-owned memory, initialised from the state_dict"""
+        h = C.c_void_p()
+        assert lib.gsd_train_plan_create(C.byref(h), C.byref(geo), 0) == 0, lib.gsd_last_error()
+        n = lib.gsd_train_plan_num_params(h)
+        numel = (C.c_longlong * n)()
+        assert lib.gsd_train_plan_param_numel(h, numel, n) == n == len(names)
+        total = sum(numel)
+        mem = {k: torch.zeros(total, device=dev()) for k in ("p", "g", "m", "v")}
+        offs, off = [], 0
+        for k, cnt in zip(names, numel):
+            assert sd[k].numel() == cnt, k
+            mem["p"][off:off + cnt].copy_(sd[k].flatten())
+            offs.append(off)
+            off += cnt
+        mem["ema"] = mem["p"].clone()
+        bn_keys = [k[:-len(".running_mean")] for k in sd if k.endswith(".running_mean")]
+        bn = [sd[k + s].clone().to(dev()) for k in bn_keys for s in (".running_mean", ".running_var")]
+        nbt = [torch.zeros((), dtype=torch.int64, device=dev()) for _ in bn_keys]
+        assert lib.gsd_train_plan_num_bn(h) == len(bn_keys)
+        ws = torch.empty(lib.gsd_train_plan_workspace_bytes(h), dtype=torch.uint8, device=dev())
+        vp = lambda ts: (C.c_void_p * len(ts))(*ts)
+        assert lib.gsd_train_plan_bind(h, vp([mem["p"].data_ptr() + 4 * o for o in offs]), vp([mem["g"].data_ptr() + 4 * o for o in offs]),
+                                       vp([t.data_ptr() for t in bn]), vp([t.data_ptr() for t in nbt]), C.c_void_p(ws.data_ptr())) == 0, \
+            lib.gsd_last_error()
+        counter = torch.zeros(2, dtype=torch.int64, device=dev())
+        opt = _lib.OptimizerState()
+        opt.params, opt.grads, opt.m, opt.v, opt.ema = (mem[k].data_ptr() for k in ("p", "g", "m", "v", "ema"))
+        opt.n, opt.counter = total, counter.data_ptr()
+        opt.hp.lr, opt.hp.beta1, opt.hp.beta2, opt.hp.eps, opt.hp.weight_decay, opt.hp.ema_decay, opt.hp.grad_scale = \
+            1e-3, 0.9, 0.999, 1e-8, 1e-6, 0.995, 1.0
+        return h, mem, offs, numel, bn, nbt, ws, counter, opt
+
+    xd, td = x.to(dev()), tgt.to(dev())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # ---- the one-call form
+    h, mem, offs, numel, bn, nbt, ws, counter, opt = build()
+    loss = torch.zeros(1, device=dev())
+    losses = []
+    for step in range(3):
+        assert lib.gsd_train_step(h, xd.data_ptr(), td.data_ptr(), loss.data_ptr(), C.byref(opt), st, _lib.NULL_CB, None) == 0, lib.gsd_last_error()
+        losses.append(float(loss))
+        if step == 0:
+            g1 = mem["g"].clone()
+    torch.cuda.synchronize()
+    assert abs(losses[0] - ref_losses[0]) < 2e-2 * abs(ref_losses[0]) + 1e-4, (losses, ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 0.1 * abs(b) + 1e-3, (losses, ref_losses)
+    assert counter.tolist() == [3, 3] and all(int(t) == 3 for t in nbt)
+    for k, o, cnt in zip(names, offs, numel):                 # where the backward path is short the gradient matches fp32 pointwise
+        if k.startswith("outc"):
+            assert rel_l2(g1[o:o + cnt], grads_ref[k].flatten()) < 1e-2, k
+    flat_ref = torch.cat([grads_ref[k].flatten() for k in names]).double()
+    assert float(torch.nn.functional.cosine_similarity(g1.double().cpu(), flat_ref, dim=0)) > 0.9
+    assert lib.gsd_train_plan_launches(h) > 100
+    # ---- forward / loss / backward / optimizer as separate calls: the same first step
+    h2, mem2, _, _, bn2, nbt2, ws2, counter2, opt2 = build()
+    y = torch.empty(B, ncls, H, W, device=dev())
+    dy = torch.empty_like(y)
+    loss2 = torch.zeros(1, device=dev())
+    assert lib.gsd_train_forward(h2, xd.data_ptr(), y.data_ptr(), st) == 0, lib.gsd_last_error()
+    assert lib.gsd_op_mse(y.data_ptr(), td.data_ptr(), y.numel(), loss2.data_ptr(), dy.data_ptr(), st) == 0
+    assert lib.gsd_backward(h2, dy.data_ptr(), st, _lib.NULL_CB, None) == 0, lib.gsd_last_error()
+    g2 = mem2["g"].clone()
+    assert lib.gsd_adam_ema_step(opt2.params, opt2.grads, opt2.m, opt2.v, opt2.ema, opt2.n, C.byref(opt2.hp), opt2.counter, st) == 0
+    torch.cuda.synchronize()
+    assert abs(float(loss2) - losses[0]) < 1e-3 * abs(losses[0])          # BatchNorm statistics use fp32 atomics: not bit-reproducible
+    assert rel_l2(g2, g1) < 5e-2 and counter2.tolist() == [1, 1]
+    y_ref = oracle.unet_forward(sd, x, training=True)
+    assert rel_l2(y, y_ref) < 4e-2
+    lib.gsd_train_plan_destroy(h)
+    lib.gsd_train_plan_destroy(h2)
