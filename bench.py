@@ -255,6 +255,10 @@ def bench_train(torch, dist, dev, rank, world, batch, steps):
         dist.all_gather(parts, g_loc)
         mean = torch.stack(parts).mean(0)
         grad_err = float((g_red - mean).abs().max() / (mean.abs().max() + 1e-30))   # backward uses fp32 atomics: not bit-reproducible
+    buckets_mb = [round((b["hi"] - b["lo"]) * 4 / 2 ** 20, 1) for b in ft.buckets]
+    train_launches = ft.plan.launches
+    ft.close()                  # the captured graph holds NCCL nodes: free it while the process group is alive
+    del ft
     sps = world * batch * steps / (ms / 1e3)
     sustained, burst = measured_peaks()[:2]
     tf = sps / world * 599.41 / 1e3
@@ -262,7 +266,7 @@ def bench_train(torch, dist, dev, rank, world, batch, steps):
             "batch_per_gpu": batch, "steps": steps, "gflop_per_sample": 599.41, "tflops_per_gpu": tf,
             "tensor_frac_sustained": tf / sustained, "tensor_frac_burst": tf / burst,
             "ddp_in_sync": in_sync, "ddp_reduced_grad_rel_err": grad_err,
-            "ddp_buckets_mb": [round((b["hi"] - b["lo"]) * 4 / 2 ** 20, 1) for b in ft.buckets],
+            "ddp_buckets_mb": buckets_mb, "launches_per_step": train_launches,
             "losses": [round(float(v), 6) for v in torch.cat(losses).cpu()], "clocks": clocks,
             "what": "fwd (train-mode BN) + MSE + bwd (dgrad/wgrad on tcgen05) + bucketed NCCL all-reduce + fused Adam/EMA, "
                     "whole step replayed as one CUDA graph"}
@@ -308,6 +312,22 @@ def run_reference(args):
 
 
 _REAL_STDOUT = None
+
+
+def shutdown(dist, world):
+    """leave the process group; a teardown that blocks (peer already gone, captured collectives ...) must never hang the
+    bench: the line is out, a watchdog ends the process"""
+    if world <= 1:
+        return
+    import gc
+    gc.collect()
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    try:
+        dist.destroy_process_group()
+    finally:
+        t.cancel()
 
 
 def emit(line: dict):
@@ -548,8 +568,7 @@ def main():
         net.eval()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(dist, world)
         return
     x_dev = raw.to(dev)
     y_dev = torch.empty(B, NCLS, H, W, device=dev)
@@ -646,8 +665,7 @@ def main():
                         "latency_b1_p50_ms": latency.get("p50_ms"), "latency_b1_p99_ms": latency.get("p99_ms"),
                         "g3_pairs_per_s": g3.get("value"), "cpu_frames_per_s": cpu["value"] if cpu else None}}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(dist, world)
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -235,7 +236,15 @@ class FusedTrainer:
         self._loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.reducer = BucketReducer(len(self.buckets), self._allreduce_range) if self.world > 1 else None
         self._cb_streams = (None, None)
-        self._cb = _lib.BUCKET_CB(self._on_bucket)                # keep the ctypes thunk alive as long as the trainer
+        # the ctypes thunk lives as long as the trainer but must not keep it alive (a cycle would park the captured CUDA
+        # graph -- with its NCCL nodes -- until interpreter shutdown, after the process group is gone)
+        ref = weakref.ref(self)
+
+        def _thunk(user, bucket, lo, hi, main_stream, side_stream):
+            me = ref()
+            if me is not None:
+                me._on_bucket(user, bucket, lo, hi, main_stream, side_stream)
+        self._cb = _lib.BUCKET_CB(_thunk)
         self._opt = _lib.OptimizerState()
         o = self._opt
         o.params, o.grads, o.m, o.v, o.ema = (self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
@@ -281,6 +290,11 @@ class FusedTrainer:
             self.plan.set_buckets(self.buckets if self.world > 1 else [], index_of)
         self.plan.bind([p.detach() for p in self.net.parameters()], self.grad_views, _bn_modules(self.net))
         return self.plan
+
+    def close(self):
+        """release the captured graph, the plan and its workspace now (before a process group is destroyed)"""
+        self._graph = None
+        self.plan = None
 
     def average_parameters(self):
         """`with trainer.average_parameters():` == torch_ema's context manager (train_unet.py:389,428,480): the EMA
