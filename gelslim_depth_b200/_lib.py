@@ -74,6 +74,9 @@ SYMBOLS = {
     "gsd_forward_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "gsd_forward_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "gsd_debug_num_activations": (C.c_int, [C.c_void_p]),
+    "gsd_debug_activation_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gsd_debug_read_activation": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsd_debug_plan_conv3x3": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int)]),
     "gsd_debug_chunk_schedule": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int), C.c_int]),
     "gsd_forward_profiled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrePost), C.c_void_p, C.c_void_p,

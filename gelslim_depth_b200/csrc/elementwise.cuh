@@ -351,6 +351,19 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, long n, float* __
     dst[idx] = src[idx];
 }
 
+// debugging taps: (B,H,W,C) activation -> fp32 (B,C,H,W)
+template <class T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ in, int B, int C, int H, int W, float* __restrict__ out) {
+  const long total = (long)B * C * H * W;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    const int c = (int)((idx / ((long)W * H)) % C);
+    const long b = idx / ((long)W * H * C);
+    out[idx] = (float)in[((b * H + y) * W + x) * C + c];
+  }
+}
+
 inline int ew_grid(long total, int threads = 256, int cap = 148 * 16) {
   long g = (total + threads - 1) / threads;
   if (g < 1) g = 1;

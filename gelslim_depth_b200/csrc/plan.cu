@@ -825,6 +825,56 @@ extern "C" int gsd_forward_profiled(gsd_plan* p, const void* x, const float* bas
   return 0;
 }
 
+// ---------------------------------------------------------------- per-layer taps (parity tests)
+// index: 0 .. 2(depth+1)-1 = the encoder's conv -> BN -> ReLU units in network order (inc.0, inc.3, down.0.0, ...);
+// then per decoder block: transposed conv (up.i.up), up.i.conv.0, up.i.conv.3.
+static int tap_lookup(const gsd_plan* p, int index, size_t* off, int* C, int* H, int* W) {
+  const int n_enc = 2 * (p->depth + 1);
+  GSD_CHECK(index >= 0 && index < n_enc + 3 * p->depth, "activation index %d out of range [0, %d)", index, n_enc + 3 * p->depth);
+  if (index < n_enc) {
+    const int l = index / 2;
+    *off = (index & 1) ? p->s_off[l] : p->a_off[l];
+    *C = p->g.dims[l]; *H = p->Hs[l]; *W = p->Ws[l];
+    return 0;
+  }
+  const int i = (index - n_enc) / 3, k = (index - n_enc) % 3, l = p->depth - 1 - i;
+  *C = p->g.dims[l];
+  if (k == 0) { *off = p->u_off[i]; *H = 2 * p->Hs[l + 1]; *W = 2 * p->Ws[l + 1]; }
+  else { *off = k == 1 ? p->da_off[i] : p->db_off[i]; *H = p->Hs[l]; *W = p->Ws[l]; }
+  return 0;
+}
+
+extern "C" int gsd_debug_num_activations(const gsd_plan* p) { return p ? 2 * (p->depth + 1) + 3 * p->depth : 0; }
+
+extern "C" int gsd_debug_activation_shape(const gsd_plan* p, int index, int* C, int* H, int* W) {
+  GSD_CHECK(p && C && H && W, "gsd_debug_activation_shape: null argument");
+  size_t off;
+  return tap_lookup(p, index, &off, C, H, W);
+}
+
+// NHWC (bf16 or fp32, the plan's dtype) activation of layer `index` left in `workspace` by the last gsd_forward ->
+// fp32 NCHW (batch, C, H, W).  The last decoder unit only exists when the 1x1 head is not fused into it
+// (GSD_NO_HEAD_FUSION); plans that run in several chunks are not supported.
+extern "C" int gsd_debug_read_activation(const gsd_plan* p, int index, const void* workspace, float* dst, void* stream) {
+  GSD_CHECK(p && workspace && dst, "gsd_debug_read_activation: null argument");
+  GSD_CHECK(p->chunks.size() == 1, "gsd_debug_read_activation: run one forward with a single chunk first");
+  size_t off;
+  int C, H, W;
+  GSD_TRY(tap_lookup(p, index, &off, &C, &H, &W));
+  GSD_CHECK(!(p->head_fused && index == gsd_debug_num_activations(p) - 1),
+            "gsd_debug_read_activation: the last unit's output is never stored when the 1x1 head is fused into it");
+  GSD_DEVICE(p->device);
+  const long total = (long)p->g.batch * C * H * W;
+  const char* src = static_cast<const char*>(workspace) + off;
+  if (p->g.dtype == GSD_DTYPE_FP32)
+    nhwc_to_nchw_kernel<float><<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float*>(src), p->g.batch, C, H, W, dst);
+  else
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+                                                                                                   p->g.batch, C, H, W, dst);
+  GSD_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // conv3x3 (pad 1) through the halo kernel (conv_halo.cuh); same tensor conventions as gsd_op_conv_bf16.
 extern "C" int gsd_op_conv3x3_halo_bf16(const void* src0, int C0, const void* src1, int C1, int H1, int W1, int off_y,
                                         int off_x, int B, int H, int W, const void* w, int Cout, const float* scale,

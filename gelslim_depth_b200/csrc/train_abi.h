@@ -344,6 +344,14 @@ extern "C" int gsd_op_pack_weights_batched(const gsd_pack_item* items_dev, int n
   return 0;
 }
 
+// 1 - beta the way torch.optim.Adam evaluates it: the caller's beta is a double-precision Python float (0.999) that reached us
+// as its nearest float; round it back to the shortest decimal (7 significant digits) before subtracting in double
+static float one_minus(float beta) {
+  char buf[32];
+  snprintf(buf, sizeof buf, "%.7g", (double)beta);
+  return (float)(1.0 - atof(buf));
+}
+
 // Adam (coupled L2) + EMA over a flat fp32 arena of n elements; step is 1-based; shadow may be NULL (no EMA).
 // grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
 // Graph-replayable variant: `counter` = 2 device int64 (Adam steps and EMA updates done so far); the kernel derives
@@ -355,7 +363,7 @@ extern "C" int gsd_op_adam_ema_dev(float* p, const float* g, float* m, float* v,
   GSD_DEVICE_OF(p);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   adam_ema_kernel<<<ew_grid((long)n / 4 + 1), 256, 0, st>>>(p, g, m, v, shadow, (long)n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, 0.f,
-                                                            grad_scale, counter, ema_decay);
+                                                            grad_scale, counter, ema_decay, one_minus(beta1), one_minus(beta2));
   adam_tick_kernel<<<1, 1, 0, st>>>(counter);
   GSD_CUDA(cudaGetLastError());
   return 0;
@@ -373,7 +381,7 @@ extern "C" int gsd_op_adam_ema(float* p, const float* g, float* m, float* v, flo
   if (warm < d) d = warm;
   adam_ema_kernel<<<ew_grid((long)n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, shadow, (long)n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), (float)(1.0 - d), grad_scale, nullptr,
-      ema_decay);
+      ema_decay, one_minus(beta1), one_minus(beta2));
   GSD_CUDA(cudaGetLastError());
   return 0;
 }

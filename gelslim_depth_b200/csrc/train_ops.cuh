@@ -626,7 +626,9 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, co
                                                        float* __restrict__ v, float* __restrict__ shadow, long n, float lr,
                                                        float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                                                        float ema_one_minus_d, float grad_scale, const long long* __restrict__ counter,
-                                                       float ema_decay) {
+                                                       float ema_decay, float one_minus_b1, float one_minus_b2) {
+  // one_minus_b1/2 = float(1 - beta) evaluated in double on the host, as torch.optim.Adam does (`value=1 - beta2` is a Python
+  // float): 1.f - 0.999f would be 1.3e-5 off
   if (counter) {
     const double t = (double)(counter[0] + 1), nu = (double)(counter[1] + 1);
     bc1 = (float)(1.0 - pow((double)b1, t));
@@ -644,8 +646,8 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, co
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float gr = G[j] * grad_scale + wd * P[j];
-      M[j] = b1 * M[j] + (1.f - b1) * gr;
-      V[j] = b2 * V[j] + (1.f - b2) * gr * gr;
+      M[j] = b1 * M[j] + one_minus_b1 * gr;
+      V[j] = b2 * V[j] + one_minus_b2 * gr * gr;
       P[j] -= (lr / bc1) * M[j] / (sqrtf(V[j]) / bc2_sqrt + eps);
       S[j] -= ema_one_minus_d * (S[j] - P[j]);
     }
@@ -656,8 +658,8 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, co
   }
   for (long i = n4 * 4 + blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float gr = g[i] * grad_scale + wd * p[i];
-    m[i] = b1 * m[i] + (1.f - b1) * gr;
-    v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = b1 * m[i] + one_minus_b1 * gr;
+    v[i] = b2 * v[i] + one_minus_b2 * gr * gr;
     p[i] -= (lr / bc1) * m[i] / (sqrtf(v[i]) / bc2_sqrt + eps);
     if (shadow) shadow[i] -= ema_one_minus_d * (shadow[i] - p[i]);
   }

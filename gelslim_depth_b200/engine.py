@@ -107,6 +107,31 @@ class Plan:
               "gsd_forward_profiled")
         return [(ms[i], fl[i]) for i in range(n.value)]
 
+    def activations(self):
+        """per-layer taps of the last forward (parity tests): {reference hook name: fp32 NCHW tensor}.  Names follow
+        forward hooks on the reference module (unet.py:7-57): '<prefix>.double_conv.2' / '.5' = post-ReLU outputs,
+        'up.i.up' = transposed-conv output."""
+        depth = self.geometry.n_dims - 1
+        names = []
+        for l in range(depth + 1):
+            prefix = "inc" if l == 0 else f"down.{l - 1}.maxpool_conv.1"
+            names += [f"{prefix}.double_conv.2", f"{prefix}.double_conv.5"]
+        for i in range(depth):
+            names += [f"up.{i}.up", f"up.{i}.conv.double_conv.2", f"up.{i}.conv.double_conv.5"]
+        n = lib.gsd_debug_num_activations(self.handle)
+        assert n == len(names)
+        out = {}
+        for idx, name in enumerate(names):
+            c, h, w = C.c_int(), C.c_int(), C.c_int()
+            check(lib.gsd_debug_activation_shape(self.handle, idx, C.byref(c), C.byref(h), C.byref(w)), "gsd_debug_activation_shape")
+            t = torch.empty(self.geometry.batch, c.value, h.value, w.value, dtype=torch.float32, device=self.device)
+            rc = lib.gsd_debug_read_activation(self.handle, idx, _ptr(self.workspace), _ptr(t), _stream(self.device))
+            if rc != 0 and idx == n - 1:
+                continue                     # fused 1x1 head: the last unit's output is never stored
+            check(rc, "gsd_debug_read_activation")
+            out[name] = t
+        return out
+
     def forward_host(self, x_host, base, pp, y_host, x_dev, y_dev, packed):
         check(lib.gsd_forward_host(self.handle, _ptr(x_host), _ptr(base), C.byref(pp), _ptr(y_host), _ptr(x_dev),
                                    _ptr(y_dev), _ptr(self.workspace), _ptr(packed), _stream(self.device)),

@@ -170,6 +170,17 @@ int gsd_debug_plan_conv3x3(int B, int H, int W, int C0, int C1, int Cout, int nu
  * number of chunks written to out[capacity] (negative = error). */
 int gsd_debug_chunk_schedule(int batch, int chunk, int first, int last, int* out, int capacity);
 
+/* --- per-layer taps (parity tests localise an error to a layer: the oracle records the same tensors, oracle/unet_oracle.py
+ * unet_forward_with_taps, as forward hooks on unet.py:7-57 would) -------------------------------------------------------- */
+/* activations a plan keeps after gsd_forward: index 0 .. 2*n_dims-1 = encoder conv->BN->ReLU units in network order
+ * (inc.double_conv.2, inc.double_conv.5, down.0...double_conv.2, ...), then per decoder block: up.i.up output,
+ * up.i.conv.double_conv.2, up.i.conv.double_conv.5. */
+int gsd_debug_num_activations(const gsd_plan* p);
+int gsd_debug_activation_shape(const gsd_plan* p, int index, int* C, int* H, int* W);
+/* -> dst fp32 NCHW (batch, C, H, W) from the workspace of the last (single-chunk) gsd_forward.  The very last unit is only
+ * stored when the 1x1 head is not fused into it (environment GSD_NO_HEAD_FUSION at bind time). */
+int gsd_debug_read_activation(const gsd_plan* p, int index, const void* workspace, float* dst, void* stream);
+
 /* --- single operators (used by the parity tests; the plan is built from exactly these) ---------- */
 /* conv KxK (taps given explicitly) as implicit GEMM on tcgen05, NHWC bf16.
  *   src0:(B,H,W,C0) [+ src1:(B,H1,W1,C1) placed at offset (off_y, off_x), zero elsewhere -> virtual

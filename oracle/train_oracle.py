@@ -62,6 +62,11 @@ class TrainOracle:
             self.sd[prefix + ".running_mean"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean)
             self.sd[prefix + ".running_var"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var_unbiased)
             self.sd[prefix + ".num_batches_tracked"] += 1
+        self.apply_update(grads)
+        return float(loss)
+
+    def apply_update(self, grads):
+        """optimizer.step(); ema.update() (train_unet.py:375-376) for given gradients {key: tensor}"""
         # Adam, coupled L2 (train_unet.py:306,375)
         self.t += 1
         b1, b2 = self.betas
@@ -78,4 +83,3 @@ class TrainOracle:
         d = min(self.ema_decay, (1 + self.ema_updates) / (10 + self.ema_updates))
         for k in self.keys:
             self.shadow[k].sub_((1 - d) * (self.shadow[k] - self.sd[k]))
-        return float(loss)

@@ -59,12 +59,13 @@ def test_full_size_pipeline_vs_oracle_and_batch_invariance(net_and_frames):
     # (2) determinism: the same launch twice is bit-identical
     y16b = predict_depth_from_frames(raw8.float().to(dev()), base.to(dev()), net, (H, W), cfg)
     assert torch.equal(y16, y16b)
-    # (3) a frame's depth map does not depend on what else is in the batch (eval mode; other tile configurations at
-    #     small batch may re-order nothing inside a dot product: same K order => bit-identical here)
+    # (3) a frame's depth map does not depend on what else is in the batch (eval mode): the launch rules pick other
+    #     kernels / tile shapes / CTA pairing at batch 1 and 4 than at 16, but every variant accumulates a dot product in
+    #     the same K order (channel block, tap), so the result is BIT-identical
     y1 = predict_depth_from_frames(raw8[11:12].float().to(dev()), base.to(dev()), net, (H, W), cfg)
-    assert torch.allclose(y1[0], y16[11], rtol=0, atol=2e-2 * float(y16[11].abs().max())), float((y1[0] - y16[11]).abs().max())
+    assert torch.equal(y1[0], y16[11]), float((y1[0] - y16[11]).abs().max())
     y4 = predict_depth_from_frames(raw8[8:12].float().to(dev()), base.to(dev()), net, (H, W), cfg)
-    assert torch.allclose(y4[3], y16[11], rtol=0, atol=2e-2 * float(y16[11].abs().max()))
+    assert torch.equal(y4[3], y16[11]), float((y4[3] - y16[11]).abs().max())
     # (4) uint8 camera bytes == float frames, bit for bit
     y8 = predict_depth_from_frames(raw8.to(dev()), base.to(dev()), net, (H, W), cfg)
     assert torch.equal(y8, y16)
