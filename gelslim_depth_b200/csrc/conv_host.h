@@ -475,7 +475,7 @@ inline int build_first_launch(const void* w, const float* bias, void* out, int B
   p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
   const long items = (long)p.tiles_x * p.tiles_y * B;
   GSD_CHECK(items < (1L << 24) && p.tiles_x < 4096 && p.tiles_y < 4096, "first conv: too many tiles for the 24-bit tile index");
-  GSD_CHECK((long)B * H * W < (1L << 31) / 64, "first conv: output too large for 32-bit pixel arithmetic");
+  GSD_CHECK((long)B * H * W < (1L << 31), "first conv: output too large for 32-bit pixel arithmetic");
   {
     uint64_t dims[2] = {9ull * 16, 64};
     uint64_t str[1] = {9ull * 16 * 2};
