@@ -211,7 +211,11 @@ def bench_train(torch, dist, dev, rank, world, batch, steps):
             if "weight" in name:
                 torch.nn.init.normal_(p, mean=0, std=0.01)          # train_unet.py:248-250
     net = net.to(dev).train()
-    ft = FusedTrainer(net, use_graph=True)
+    kw = {}
+    if os.environ.get("GSD_DDP_BUCKET_MB"):            # tuning experiments only: "bucket,first,tail" in MB
+        b, f, t = (float(v) for v in os.environ["GSD_DDP_BUCKET_MB"].split(","))
+        kw = dict(bucket_bytes=int(b * 2 ** 20), first_bucket_bytes=int(f * 2 ** 20) or None, tail_bucket_bytes=int(t * 2 ** 20) or None)
+    ft = FusedTrainer(net, use_graph=True, **kw)
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.rand(batch, CIN, H, W, generator=g).to(dev)
     t = (-0.9 * torch.rand(batch, NCLS, H, W, generator=g)).to(dev)
