@@ -39,8 +39,8 @@ def measured_peaks():
 
 def traffic_from_profile():
     """dram__bytes_read.sum + dram__bytes_write.sum of the 22 conv launches of one batch-64 forward, from the committed
-    `ncu --set full` capture (profiles/r1_traffic.json); bytes per step, like `achieved` is FLOPs per step."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    `ncu --set full` capture (profiles/r2_traffic.json); bytes per step, like `achieved` is FLOPs per step."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
