@@ -38,6 +38,8 @@ struct HaloParams {
   const float* bias;     // [Cout] or null: additive constant applied by one extra UMMA per tile (bias_mma.cuh) instead of
                          //   the epilogue; needs Cout == BN (a single N tile); scale / shift are then normally null
   __nv_bfloat16* out;    // (B, H, W, Cout) or null (head-only)
+  __nv_bfloat16* out2;   // split output (dgrad of the decoder's concat conv, unet.py:48): channels >= split_c go to the dense
+  int split_c;           //   tensor out2 (B, H, W, Cout - split_c), channels < split_c to out (B, H, W, split_c); null: one tensor
   __nv_bfloat16* pooled; // (B, H/2, W/2, Cout) or null
   // fused OutConv 1x1 + bias + depth de-normalisation (unet.py:54, normalization_utils.py:129); Cout == BN == 64
   const float* head_w;   // [ncls][64] or null
@@ -73,7 +75,9 @@ struct HaloGeom {
 // CTA2: thread-block cluster of two CTAs sharing every tcgen05.mma (cta_group::2, M = 256): each CTA stages and reads
 // only HALF of the weight rows, so the smem operand traffic per UMMA drops from 32 + N/4 to 32 + N/8 wavefronts and the
 // weight TMA traffic halves.  The pair walks pairs of M groups (same N tile); only the leader issues MMAs.
-template <int BN, int MT, bool WRES, int BKB, int NEPI, bool CTA2 = false>
+// SPLIT: two dense output tensors (HaloParams::out2 / split_c) -- a separate instantiation so that the pointer bookkeeping
+// costs the single-output kernels nothing
+template <int BN, int MT, bool WRES, int BKB, int NEPI, bool CTA2 = false, bool SPLIT = false>
 __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr int kHaloThreads = 64 + 32 * NEPI;
   using G = HaloGeom<BKB>;
@@ -317,18 +321,32 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
         const int img_row0 = (int)b * p.H;              // 32-bit pixel arithmetic, one 64-bit multiply per pointer
         px.prow = p.pooled ? p.pooled + (size_t)(((int)b * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout + nt * BN + (hx ? 16 : 0) + (hy ? 8 : 0)
                            : nullptr;
+        const int row_c = SPLIT ? p.split_c : p.Cout;        // channels per pixel of `out`
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = 8 * i + (lane >> 2);
           const int yy = ty * 16 + 4 * q + (r >> 3), xx = tx * 8 + (r & 7);
-          px.rp[i] = (p.out && yy < p.H && xx < p.W) ? p.out + (size_t)((img_row0 + yy) * p.W + xx) * p.Cout + nt * BN : nullptr;
+          px.rp[i] = (p.out && yy < p.H && xx < p.W) ? p.out + (size_t)((img_row0 + yy) * p.W + xx) * row_c + nt * BN : nullptr;
         }
         const uint32_t t_row = tmem_base + (buf * MT + j) * BN + ((uint32_t)(q * 32) << 16);
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32)
+        {
+          if constexpr (SPLIT) {   // this 32-column unit belongs to `out` (channels < split_c) or to `out2`
+            const bool second = (int)(nt * BN) + c0 >= p.split_c;       // warp-uniform
+            __nv_bfloat16* const tbase = second ? p.out2 - p.split_c : p.out;     // "- split_c": "+ c0" then lands on the right channel
+            const int pitch = second ? p.Cout - p.split_c : p.split_c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + (lane >> 2);
+              const int yy = ty * 16 + 4 * q + (r >> 3), xx = tx * 8 + (r & 7);
+              px.rp[i] = (yy < p.H && xx < p.W) ? tbase + (size_t)((img_row0 + yy) * p.W + xx) * pitch + nt * BN : nullptr;
+            }
+          }
           epilogue_32cols(t_row, c0, p.scale ? g_scale + nt * BN : nullptr, p.shift ? g_shift + nt * BN : nullptr, p.relu, px, s_epi + ew * kEpiStageBytesPerWarp, lane, hacc,
                           p.head_w ? g_head : nullptr, p.head_ncls);
+        }
         if (p.head_w && valid) {
           const size_t plane = (size_t)p.H * p.W;
           float* yo = p.head_y + (size_t)b * p.head_ncls * plane + (size_t)y * p.W + x;

@@ -32,6 +32,7 @@ struct ConvDesc {
   float head_scale = 1.f, head_shift = 0.f; int head_ncls = 0;
   float* stats = nullptr;      // [2][groups*Cout] fp32, accumulated (caller zeroes): sum / sum of squares of the raw output
   const float* bias = nullptr; // halo kernel, Cout == 64: additive constant applied by the tensor core (bias_mma.cuh)
+  void* out2 = nullptr; int split_c = 0;   // halo kernel: channels >= split_c go to the dense tensor out2 (see HaloParams)
   // transposed-conv INPUT gradient: src0 is a dense (B, Hf, Wf, Cs) tensor holding the gradient of the (2H x 2W)
   // up-sampled map at offset (s2d_off_y, s2d_off_x); C0 must be 2*Cs, ntaps 2 (gy), the output domain is H x W.
   int s2d = 0, s2d_Hf = 0, s2d_Wf = 0, s2d_off_y = 0, s2d_off_x = 0;
@@ -303,6 +304,9 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   p.head_scale = d.head_scale; p.head_shift = d.head_shift; p.head_ncls = d.head_ncls;
   p.stats = d.stats;
   p.bias = d.bias;
+  p.out2 = static_cast<__nv_bfloat16*>(d.out2); p.split_c = d.out2 ? d.split_c : 0;
+  GSD_CHECK(!d.out2 || (d.out && !d.pooled && !d.head_w && d.split_c > 0 && d.split_c < d.Cout && d.split_c % 32 == 0 && (d.Cout - d.split_c) % 8 == 0),
+            "halo conv: split output needs 0 < split_c < Cout, split_c a multiple of 32, no pooling / head");
   GSD_CHECK(!d.bias || d.Cout == 64, "halo conv: the tensor-core bias needs Cout == 64 (one N tile)");
   GSD_CHECK(!d.head_w || (d.Cout == 64 && d.head_ncls >= 1 && d.head_ncls <= 4 && d.head_y && d.head_b),
             "halo conv: fused 1x1 head needs Cout == 64 and 1..4 classes");
@@ -423,6 +427,19 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
 
 template <int BN, int MT, bool WRES, int BKB, int NEPI>
 inline int launch_halo_cfg(const HaloLaunch& L, cudaStream_t st) {
+  if constexpr (BKB == 128 && !WRES && BN >= 128) {        // split output (dgrad of the concat convs): N >= 128, streamed weights
+    if (L.p.out2) {
+      if (L.cta2) {
+        static SmemAttrCache attr_cache_s2;
+        GSD_TRY(attr_cache_s2.ensure(conv_halo_kernel<BN, MT, WRES, BKB, NEPI, true, true>, L.smem));
+        return launch_maybe_pdl(conv_halo_kernel<BN, MT, WRES, BKB, NEPI, true, true>, L.p, L.grid, 64 + 32 * NEPI, L.smem, st, L.pdl, 2);
+      }
+      static SmemAttrCache attr_cache_s;
+      GSD_TRY(attr_cache_s.ensure(conv_halo_kernel<BN, MT, WRES, BKB, NEPI, false, true>, L.smem));
+      return launch_maybe_pdl(conv_halo_kernel<BN, MT, WRES, BKB, NEPI, false, true>, L.p, L.grid, 64 + 32 * NEPI, L.smem, st, L.pdl);
+    }
+  }
+  GSD_CHECK(!L.p.out2, "halo conv: split output is built for N >= 128 with streamed weights only");
   if constexpr (BKB == 128) {
     if (L.cta2) {
       static SmemAttrCache attr_cache2;

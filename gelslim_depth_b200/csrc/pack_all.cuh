@@ -106,13 +106,20 @@ __global__ void __launch_bounds__(256) params_fingerprint_kernel(const __grid_co
   __shared__ unsigned long long s_part[8];
   for (int i = threadIdx.x; i <= p.n; i += blockDim.x) s_start[i] = p.start[i];
   __syncthreads();
-  const long long total = s_start[p.n];
   unsigned long long acc = 0;
-  int k = 0;
-  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
-    while (w >= s_start[k + 1]) ++k;       // w only grows
-    const unsigned long long bits = __ldg(p.ptr[k] + (w - s_start[k]));
-    acc += (bits + 0x9E3779B97F4A7C15ull) * (((unsigned long long)w * 0xBF58476D1CE4E5B9ull) | 1ull);   // position-dependent odd weight
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
+  auto mix = [](unsigned long long bits, long long w) {      // position-dependent odd weight: permutations change the sum
+    return (bits + 0x9E3779B97F4A7C15ull) * (((unsigned long long)w * 0xBF58476D1CE4E5B9ull) | 1ull);
+  };
+  for (int k = 0; k < p.n; ++k) {                            // tensor-major: no per-word table search, coalesced loads
+    const uint32_t* __restrict__ src = p.ptr[k];
+    const long long base = s_start[k], n = s_start[k + 1] - base;
+    long long w = gtid;
+    for (; w + 3 * gsize < n; w += 4 * gsize) {              // four independent loads in flight per thread
+      const uint32_t b0 = __ldg(src + w), b1 = __ldg(src + w + gsize), b2 = __ldg(src + w + 2 * gsize), b3 = __ldg(src + w + 3 * gsize);
+      acc += mix(b0, base + w) + mix(b1, base + w + gsize) + mix(b2, base + w + 2 * gsize) + mix(b3, base + w + 3 * gsize);
+    }
+    for (; w < n; w += gsize) acc += mix(__ldg(src + w), base + w);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

@@ -358,7 +358,7 @@ extern "C" int gsd_pack_weights_if_changed(gsd_plan* p, const void* const* param
   GSD_CHECK(pi == np && bi == nb, "gsd_pack_weights_if_changed: internal count mismatch");
   fp.start[k] = cur;
   fp.n = k;
-  params_fingerprint_kernel<<<148 * 4, 256, 0, st>>>(fp, state);
+  params_fingerprint_kernel<<<148 * 8, 256, 0, st>>>(fp, state);
   GSD_CUDA(cudaGetLastError());
   return pack_weights_impl(p, params, bn, packed, state, st);
 }

@@ -20,6 +20,7 @@ struct TrainUnit {          // conv3x3 -> BatchNorm2d -> ReLU (unet.py:11-13 / 1
   int H = 0, W = 0, C0 = 0, C1 = 0, Cout = 0, cin_real = 0;
   int H1 = 0, W1 = 0, off_y = 0, off_x = 0;
   bool first = false, pool = false, apply = true;
+  bool one_dgrad = false;      // concat unit: both halves of the input gradient from ONE launch (split-output halo kernel)
   int p_w = 0, p_g = 0, p_b = 0, bn = 0, neg_off = 0;
   size_t z = 0, a = 0, pooled = 0, consts = 0, stats = 0, dz = 0, din0 = 0, din1 = 0, w_fwd = 0, w_dgrad = 0, dwk = 0;
   size_t src0 = 0, src1 = 0;      // workspace offsets of the conv inputs
@@ -220,11 +221,24 @@ int unit_backward(gsd_train_plan* p, TrainUnit& u, const void* da, const float* 
   if (need_dx) {
     const char* wd = p->ws + u.w_dgrad;                        // [ci][9][co] bf16
     if (u.C1) {
-      const size_t rows = (size_t)u.C0 * 9 * u.Cout * 2;       // bytes of the skip half
-      TP_RUN(p, gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd, u.C0, 9, 1, nullptr, nullptr, 0,
-                                    p->ws + u.din0, nullptr, nullptr, p->device, st));
-      TP_RUN(p, gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd + rows, u.C1, 9, 1, nullptr, nullptr, 0,
-                                    p->ws + u.din1, nullptr, nullptr, p->device, st));
+      // the decoder's concat conv: ONE launch with N = C0 + C1 whose epilogue writes the skip half and the up half of the
+      // input gradient to two dense tensors (at the top level two N = 64 launches are bound by the smem operand reads, one
+      // N = 128 launch is not: 24.35 -> 24.31 ms per step); the tap-streaming kernel and small batches keep two launches
+      ConvDesc d;
+      d.src0 = p->ws + u.dz; d.C0 = u.Cout; d.B = B; d.H = u.H; d.W = u.W; d.w = wd; d.Cout = u.C0 + u.C1; d.groups = 1;
+      taps3x3(&d);
+      d.out = p->ws + u.din0; d.out2 = p->ws + u.din1; d.split_c = u.C0;
+      if (u.one_dgrad && !p->dry) {
+        HaloLaunch L;
+        GSD_TRY(build_halo_launch(d, p->num_sms, &L));
+        GSD_TRY(run_halo_launch(L, st));
+      } else if (!u.one_dgrad) {
+        const size_t rows = (size_t)u.C0 * 9 * u.Cout * 2;       // bytes of the skip half
+        TP_RUN(p, gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd, u.C0, 9, 1, nullptr, nullptr, 0,
+                                      p->ws + u.din0, nullptr, nullptr, p->device, st));
+        TP_RUN(p, gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd + rows, u.C1, 9, 1, nullptr, nullptr, 0,
+                                      p->ws + u.din1, nullptr, nullptr, p->device, st));
+      }
     } else {
       TP_RUN(p, gsd_op_conv_auto_bf16(p->ws + u.dz, u.Cout, nullptr, 0, 0, 0, 0, 0, B, u.H, u.W, wd, u.C0, 9, 1, nullptr, nullptr, 0,
                                     p->ws + u.din0, nullptr, nullptr, p->device, st));
@@ -377,6 +391,24 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
     p->dec[2 * i].src1 = p->ups[i].u;
     p->dec[2 * i + 1].src0 = p->dec[2 * i].a;
   }
+  // concat units: one split-output dgrad launch where the launch rules give it N >= 128 with streamed weights (small batches
+  // plan N = 64 work items and the tap-streaming kernel has no split output: those keep two launches)
+  for (int i = 0; i < p->depth; ++i) {
+    TrainUnit& u = p->dec[2 * i];
+    ConvDesc d;
+    void* dummy = reinterpret_cast<void*>(static_cast<uintptr_t>(256));
+    d.src0 = dummy; d.C0 = u.Cout; d.B = (int)B; d.H = u.H; d.W = u.W; d.w = dummy; d.Cout = u.C0 + u.C1; d.groups = 1;
+    taps3x3(&d);
+    d.out = dummy; d.out2 = dummy; d.split_c = u.C0;
+    if (!getenv("GSD_SPLIT_DGRAD2") && prefer_halo(d, sms)) {
+      HaloLaunch L;
+      const bool was = plan_only_mode();
+      plan_only_mode() = true;
+      const int rc = build_halo_launch(d, sms, &L);
+      plan_only_mode() = was;
+      u.one_dgrad = rc == 0 && L.bn >= 128 && !L.wres;
+    }
+  }
   if (!dry) {
     GSD_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
     p->events.resize(192);
@@ -418,7 +450,8 @@ extern "C" int gsd_train_plan_launches(const gsd_train_plan* p) {
   int n = 3 + (3 * U - 1) + D + 1;            // pack, constants, prologue | conv + finalize (+ apply, not the last unit) | transposed convs | head
   n += 1;                                     // MSE
   n += 1 + 2 * U + (U - 1 + D) + 2 * U;       // zero fills | BatchNorm backward (2 passes) | dgrad (concat: 2, first layer: 0) | wgrad + unpack
-  for (int i = 0; i < D; ++i) n += 3 + ((p->dec[2 * i].H != 2 * p->ups[i].hs || p->dec[2 * i].W != 2 * p->ups[i].ws) ? 1 : 0);
+  for (int i = 0; i < D; ++i)
+    n += 3 + ((p->dec[2 * i].H != 2 * p->ups[i].hs || p->dec[2 * i].W != 2 * p->ups[i].ws) ? 1 : 0) - (p->dec[2 * i].one_dgrad ? 1 : 0);
   n += D;                                     // max-pool backward
   return n + 2;                               // Adam + EMA, step counter
 }
