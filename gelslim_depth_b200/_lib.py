@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgsd_b200.so")
+LIB_PATH = os.environ.get("GSD_B200_LIB") or os.path.join(HERE, "libgsd_b200.so")     # override: A/B experiments against an older build
 
 GSD_MAX_DIMS = 8
 DTYPE_BF16, DTYPE_FP32 = 0, 1

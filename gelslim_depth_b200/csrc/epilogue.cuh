@@ -19,6 +19,7 @@ namespace gsd {
 constexpr int kEpiWarps = 8;
 constexpr int kEpiStageBytesPerWarp = 32 * 64;   // 32 pixels x 32 channels bf16
 
+
 struct EpiPixel {
   __nv_bfloat16* prow;    // &pooled[window][channel base + this lane's 8-channel piece] or null
   __nv_bfloat16* rp[4];   // &out[pixel of warp row 8*i + lane/4][tile channel base] (null: outside the image)
@@ -43,34 +44,42 @@ __device__ __forceinline__ void epilogue_32cols(uint32_t t_row, int c0, const fl
   tmem_ld32(t_row + c0, v);
   tmem_ld_wait();
   if (px.s_stats) {
-    // Batch statistics over the 32 pixels of this warp for 32 channels: butterfly transpose-reduce -- at every
-    // step a lane keeps half of its channels and adds the partner's copy of them, so 31 shuffles (not 160) leave
-    // lane l with the warp total of channel bitrev-free index `l` of this unit.
-    float s1[32], s2[32];
+    // Batch statistics (sum, sum of squares of the raw fp32 accumulators) of 32 channels over this warp's 32 pixels, through
+    // the warp's 2 KB staging patch (it is free here: the bf16 transposition below runs after it).  Two halves of 16
+    // channels: every lane writes 16 accumulators of its pixel as a 64-byte row (chunk j at j ^ ((row >> 1) & 3): the
+    // STS.128 of a quarter-warp hit eight different 16-byte bank groups), then lanes 0-15 sum one channel each over the
+    // even rows and lanes 16-31 over the odd rows (one 128-byte wavefront per LDS), and one shuffle joins the two.
+    // 64 smem wavefronts + 4 shuffles per unit and warp.  The 62-shuffle butterfly this replaces cost ~3.5x that on the
+    // one-wavefront-per-clock pipe that also feeds the tensor core's operands (ncu counts shuffles as LSU shared-memory
+    // wavefronts): +30 % on a 64-channel train-mode forward conv.
+    const int ch = lane & 15, odd = lane >> 4;
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float a = px.valid ? __uint_as_float(v[i]) : 0.f;
-      s1[i] = a;
-      s2[i] = a * a;
-    }
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-    for (int step = 0; step < 5; ++step) {
-      const int n = 16 >> step;                 // channels kept after this step
-      const int mask = 16 >> step;              // partner lane
-      const bool upper = (lane & mask) != 0;    // upper lanes keep the upper half of the channel range
-#pragma unroll
-      for (int i = 0; i < n; ++i) {
-        const float send1 = upper ? s1[i] : s1[i + n];
-        const float send2 = upper ? s2[i] : s2[i + n];
-        const float keep1 = upper ? s1[i + n] : s1[i];
-        const float keep2 = upper ? s2[i + n] : s2[i];
-        s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, mask);
-        s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t addr = stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+        const int k = 16 * h + 4 * j;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(px.valid ? v[k] : 0u), "r"(px.valid ? v[k + 1] : 0u),
+                     "r"(px.valid ? v[k + 2] : 0u), "r"(px.valid ? v[k + 3] : 0u) : "memory");
       }
+      __syncwarp();
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int r2 = 0; r2 < 16; ++r2) {
+        const uint32_t addr = stage + (2 * r2 + odd) * 64 + (((ch >> 2) ^ (r2 & 3)) << 4) + ((ch & 3) << 2);
+        float x;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+        a1 += x;
+        a2 = fmaf(x, x, a2);
+      }
+      __syncwarp();
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+      if (odd == h) { s1 = a1; s2 = a2; }        // lane l ends up with channel c0 + l
     }
-    // after the 5 steps lane l holds channel index l (bit k of l selected the upper half at step with mask 16>>k')
-    atomicAdd(px.s_stats + px.stats_ch0 + c0 + lane, s1[0]);
-    atomicAdd(px.s_stats + px.stats_stride + px.stats_ch0 + c0 + lane, s2[0]);
+    atomicAdd(px.s_stats + px.stats_ch0 + c0 + lane, s1);
+    atomicAdd(px.s_stats + px.stats_stride + px.stats_ch0 + c0 + lane, s2);
   }
   // per-channel constants are warp-uniform smem reads: fetch them as 128-bit broadcasts (one smem wavefront per
   // 4 channels) -- the smem data pipe is shared with the tensor core's operand reads and is the scarce resource.
