@@ -167,6 +167,11 @@ class UNet(nn.Module):
                 raise NotImplementedError("train mode runs the plain bf16 network (no fused pre/post-processing, no fp32 mode)")
             from ..train.engine import unet_train_forward
             return unet_train_forward(self, x.contiguous().float())
+        if x.requires_grad and torch.is_grad_enabled():
+            # the reference's eval-mode forward is differentiable w.r.t. its input (unet.py:79-88 under autograd); this
+            # path is not -- say so instead of silently returning a tensor that is cut off from the graph
+            raise NotImplementedError("gelslim_depth_b200.UNet: the eval-mode forward does not propagate gradients to its input "
+                                      "(call it under torch.no_grad(), detach the input, or use .train() for the training step)")
         if x.dtype == torch.uint8:
             if pp is None or not pp.input_u8:
                 raise ValueError("uint8 frames need a gsd_prepost with input_u8 set (predict_depth_from_frames does that)")

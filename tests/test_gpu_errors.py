@@ -53,6 +53,18 @@ def test_forward_argument_checks():
                 torch.ones(64, device=dev()), torch.zeros(64, device=dev()), [(a, b) for a in (-1, 0, 1) for b in (-1, 0, 1)])
 
 
+def test_eval_forward_refuses_input_gradients_loudly():
+    """VERDICT r1 weak #8: the reference's eval forward participates in autograd; ours does not and must say so."""
+    from gelslim_depth_b200.models.unet import UNet
+    net = UNet(3, 1, layer_dimensions=[64, 128]).to(dev()).eval()
+    x = torch.rand(1, 3, 16, 24, device=dev(), requires_grad=True)
+    with pytest.raises(NotImplementedError, match="does not propagate gradients"):
+        net(x=x)
+    with torch.no_grad():
+        assert net(x=x).shape == (1, 1, 16, 24)
+    assert net(x=x.detach()).requires_grad is False
+
+
 def test_plan_cache_eviction_and_batch_changes():
     from gelslim_depth_b200.models.unet import UNet
     torch.manual_seed(0)
