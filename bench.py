@@ -295,16 +295,28 @@ def run_reference(args):
     t0 = time.perf_counter()
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    step = _cpu_step_fn(torch, args.cpu_batch)
+    cpu_batch, probe = args.cpu_batch, None
+    if cpu_batch <= 0:
+        # the CPU path's best operating point on this box: single frames or batches of 8 (oneDNN is usually FASTER per frame
+        # on single frames here: 5.5 vs 4.4 frames/s on 16 threads), probed with one warm + one timed pass each
+        probe = {}
+        for b in (1, 8):
+            fn = _cpu_step_fn(torch, b)
+            fn()
+            t = time.perf_counter()
+            fn()
+            probe[b] = b / (time.perf_counter() - t)
+        cpu_batch = max(probe, key=probe.get)
+    step = _cpu_step_fn(torch, cpu_batch)
     for _ in range(args.warmup):
         step()
     t1 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t1
-    fps = args.steps * args.cpu_batch / dt
-    sample = (f"each step = {args.cpu_batch} 6x320x427 frame pairs (bounded sample of the batch-64 workload), fp32, "
-              f"{threads} host threads")
+    fps = args.steps * cpu_batch / dt
+    sample = (f"each step = {cpu_batch} 6x320x427 frame pair(s) (bounded sample of the batch-64 workload), fp32, "
+              f"{threads} host threads" + (f"; batch chosen by a probe: {({k: round(v, 2) for k, v in probe.items()})} frames/s" if probe else ""))
     line = {"impl": "reference", "metric": "unet_frames_per_s_6x320x427", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -423,7 +435,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipelined chunk of the host path (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-steps", type=int, default=20, help="timed training steps (config 4: bf16, batch 32/GPU); 0 = skip")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="--impl reference: frame pairs per CPU step")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="--impl reference: frame pairs per CPU step (0 = the faster of 1 and 8)")
     ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--layers", action="store_true", help="print the per-launch table to stderr")
     args = ap.parse_args()
