@@ -356,16 +356,13 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
     if (d.block_n == 256 && d.Cout % 256 == 0) { bn = 256; mt = 1; }
   }
   GSD_CHECK(bkb == 128 || wres, "halo conv: first-layer path needs resident weights");
-  // CTA pairs (cta_group::2): only where there is more than one wave of pair items (small batches keep single CTAs)
-  {
-    const long mtl = (long)((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
-    const long pair_items = (((mtl + mt - 1) / mt + 1) / 2) * (d.Cout / bn);
-    // default (1): N >= 128 layers with at least a full wave of pair items; 0: never; 2: every 64-channel-block layer
-    // (tests).  Measured on B200, batch 64 (tools/exp_cta2.py): N = 128 / 256 layers gain 8-17 %, the resident-weight
-    // N = 64 layers lose 4-30 % (their UMMA is A-read-bound either way), so those keep single CTAs.
-    L->cta2 = (bkb == 128 && num_sms % 2 == 0 &&
-               (cta2_mode == 2 || (cta2_mode == 1 && (bn >= 128 || pair64) && pair_items >= num_sms / 2))) ? 1 : 0;
-  }
+  // CTA pairs (cta_group::2).  GSD_CTA2: 1 = the measured rule below (default), 0 = never, 2 = every 64-channel-block layer (tests).
+  // Measured on B200, batch 64 (tools/exp_cta2.py): streamed-weight layers gain 8-17 % as pairs, the resident-weight N = 64
+  // layers lose 4-30 % (their UMMA is A-read-bound either way), so those keep single CTAs.  Streamed-weight layers pair at
+  // every batch size: at batch 1-3 the grid is one partial wave either way and a pair reads each weight stage once for two
+  // M tiles (same-box A/B, tools/ab_forward.py: batch 1 0.362 -> 0.344 ms, batch 2 0.538 -> 0.506 ms, batch >= 4 unchanged).
+  L->cta2 = (bkb == 128 && num_sms % 2 == 0 &&
+             (cta2_mode == 2 || (cta2_mode == 1 && ((!wres && mtl_all >= 2) || pair64)))) ? 1 : 0;
   const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048 + (d.bias ? kBiasOnesBytes + 64 * 32 : 0);
   const int b_bytes = (L->cta2 ? bn / 2 : bn) * bkb;
   if (wres) {

@@ -16,8 +16,9 @@ plan = net.plan_for(B, 320, 427, dev)
 packed = net.packed_weights(plan)
 for _ in range(5):
     prof = plan.forward_profiled(x, base, pp, y, packed)
-names = ["prologue", "inc.0", "inc.3"] + [f"down.{i}.{j}" for i in range(4) for j in (0, 3)] + \
-        [f"up.{i}.{n}" for i in range(4) for n in ("up", "conv.0", "conv.3")] + ["head"]
+fused = len(prof) == 23      # 22 conv launches (prologue fused into the first) + the tail entry
+names = (["inc.0+prologue"] if fused else ["prologue", "inc.0"]) + ["inc.3"] + [f"down.{i}.{j}" for i in range(4) for j in (0, 3)] + \
+        [f"up.{i}.{n}" for i in range(4) for n in ("up", "conv.0", "conv.3")] + ["tail"]
 tot = 0
 for n, (ms, fl) in zip(names, prof):
     tot += ms
