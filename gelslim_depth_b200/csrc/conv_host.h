@@ -129,11 +129,15 @@ inline int build_conv_launch(const ConvDesc& d, int num_sms, ConvLaunch* L) {
   GSD_CHECK(!(bkb == 32 && bn != 64), "conv: first-layer path supports block_n 64 only");
   L->bn = bn; L->bkb = bkb;
   {
-    // CTA pairs for the tensor-bound 3x3 layers (the transposed convs are HBM / epilogue-bound: no operand to save)
+    // CTA pairs for the tensor-bound 3x3 layers (most transposed convs are HBM / epilogue-bound: no operand to save)
     const int mode = getenv("GSD_CTA2") ? atoi(getenv("GSD_CTA2")) : 1;
     const long pair_items = (long)((m_tiles + 1) / 2) * (ntot / bn);
-    L->cta2 = (bkb == 128 && num_sms % 2 == 0 && bn >= 128 && d.groups == 1 &&
-               (mode == 2 || (mode == 1 && d.ntaps == 9 && pair_items >= num_sms / 2))) ? 1 : 0;
+    // transposed convs: only the K = 1024 one (up.0.up) is tensor-bound enough to gain as pairs (same-box A/B at batch 64 with
+    // GSD_CTA2_CONVT = smallest paired K: up.0.up 0.166 -> 0.145 ms, up.1.up 0.187 -> 0.184, up.2.up 0.239 -> 0.264, up.3.up 0.382 -> 0.455)
+    const int convt_k = getenv("GSD_CTA2_CONVT") ? atoi(getenv("GSD_CTA2_CONVT")) : 1024;
+    const bool convt = mode >= 1 && d.groups == 4 && convt_k > 0 && d.C0 >= convt_k && pair_items >= num_sms / 2;
+    L->cta2 = (bkb == 128 && num_sms % 2 == 0 && bn >= 128 && (d.groups == 1 || convt) &&
+               (mode == 2 || convt || (mode == 1 && d.ntaps == 9 && pair_items >= num_sms / 2))) ? 1 : 0;
   }
   p.n_tiles = ntot / bn;
   p.cout_per_group = d.Cout;

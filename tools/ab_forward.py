@@ -38,6 +38,10 @@ for name, env in variants:
     plan.pack([p.detach() for p in net.parameters()], net._bn_buffers(), packed)
     plan.forward(x, base, pp, y, packed)           # binds under this environment
     torch.cuda.synchronize()
+    if plans and not torch.equal(y, y_first):
+        print(f"!! variant {name}: output differs from the first variant (max abs {(y - y_first).abs().max().item():.3e})")
+    if not plans:
+        y_first = y.clone()
     plans.append((name, env, plan, packed))
 rows = {name: [] for name, *_ in plans}
 steps = {name: [] for name, *_ in plans}
