@@ -16,6 +16,9 @@ struct F32Conv {
   float* out;                                     // (B,H,W,Cout) or (B,2H,2W,Cout) when groups == 4
   int B, H, W, Cout, groups, ntaps, relu;
   int8_t dy[9], dx[9];
+  // training-path extensions (0 = the inference defaults): leading dimension of w when only a column range of it is used,
+  // and a strided / offset sampling of src0: sample (in_stride * y + dy + s_oy, in_stride * x + dx + s_ox) of a (B, sH, sW, C0) tensor
+  int ldw = 0, in_stride = 0, sH = 0, sW = 0, s_oy = 0, s_ox = 0;
 };
 
 // 64 pixels x 64 channels per block, 256 threads, 4x4 outputs per thread, K walked in chunks of 16.
@@ -28,6 +31,8 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Conv p) {
   const long M = (long)p.B * p.H * p.W;
   const long m0 = (long)blockIdx.x * 64;
   const int n0 = blockIdx.y * 64;
+  const int ldw = p.ldw ? p.ldw : Ntot;
+  const int S = p.in_stride ? p.in_stride : 1, sH = p.sH ? p.sH : p.H, sW = p.sW ? p.sW : p.W;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx -> channels, ty -> pixels
   float acc[4][4];
 #pragma unroll
@@ -53,7 +58,8 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Conv p) {
           const long b = m / ((long)p.W * p.H);
           const int ys = y + p.dy[tap], xs = x + p.dx[tap];
           if (c < p.C0) {
-            if (ys >= 0 && ys < p.H && xs >= 0 && xs < p.W) v = __ldg(p.src0 + ((b * p.H + ys) * p.W + xs) * p.C0 + c);
+            const int y0 = S * y + p.dy[tap] + p.s_oy, x0 = S * x + p.dx[tap] + p.s_ox;
+            if (y0 >= 0 && y0 < sH && x0 >= 0 && x0 < sW) v = __ldg(p.src0 + ((b * sH + y0) * sW + x0) * p.C0 + c);
           } else {
             const int y1 = ys - p.off_y, x1 = xs - p.off_x;
             if (y1 >= 0 && y1 < p.H1 && x1 >= 0 && x1 < p.W1)
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Conv p) {
       for (int r = 0; r < 4; ++r) {
         const int kk = (threadIdx.x >> 6) + 4 * r;
         const int k = k0 + kk;
-        Bs[kk][nn] = (k < K && n0 + nn < Ntot) ? __ldg(p.w + (long)k * Ntot + n0 + nn) : 0.f;
+        Bs[kk][nn] = (k < K && n0 + nn < Ntot) ? __ldg(p.w + (long)k * ldw + n0 + nn) : 0.f;
       }
     }
     __syncthreads();
@@ -99,7 +105,10 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Conv p) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx + 16 * j;
       if (n >= Ntot) continue;
-      float v = acc[i][j] * p.scale[n] + p.shift[n];
+      float v = acc[i][j];
+      if (p.scale && p.shift) v = v * p.scale[n] + p.shift[n];
+      else if (p.scale) v *= p.scale[n];
+      else if (p.shift) v += p.shift[n];
       if (p.relu) v = fmaxf(v, 0.f);
       if (p.groups == 1) {
         p.out[((b * p.H + y) * p.W + x) * p.Cout + n] = v;

@@ -24,11 +24,13 @@ struct TrainUnit {          // conv3x3 -> BatchNorm2d -> ReLU (unet.py:11-13 / 1
   int p_w = 0, p_g = 0, p_b = 0, bn = 0, neg_off = 0;
   size_t z = 0, a = 0, pooled = 0, consts = 0, stats = 0, dz = 0, din0 = 0, din1 = 0, w_fwd = 0, w_dgrad = 0, dwk = 0;
   size_t src0 = 0, src1 = 0;      // workspace offsets of the conv inputs
+  size_t dstat = 0, dbwd = 0;     // fp32 parity path: double [2C] accumulators (batch statistics / their gradients)
 };
 
 struct TrainUp {            // ConvTranspose2d(k=2, s=2) of one decoder block (unet.py:36)
   int Cin = 0, Cout = 0, hs = 0, ws = 0, p_w = 0, p_b = 0;
   size_t u = 0, w_fwd = 0, w_dgrad = 0, bias4 = 0, din = 0, src = 0;
+  size_t dbias = 0;               // fp32 parity path: double [Cout]
 };
 
 struct PrepItem {           // dst[i] = src ? mul * src[i % csrc] : 0   (per-step constants and small zero fills, one launch)
@@ -101,6 +103,9 @@ struct gsd_train_plan {
   size_t ev_next = 0;
   bool forked = false;
   int overlap = 1;
+  bool f32 = false;      // geometry.dtype == GSD_DTYPE_FP32: the FFMA parity path (train_plan_f32.h), everything on the main stream
+  size_t dzero = 0, dzero_bytes = 0, dhead = 0, da_head = 0;   // fp32: double accumulator arena, OutConv gradient accumulators / input gradient
+  int launches_f32 = 0;  // launches of the last fp32 step (counted while enqueuing)
   bool dry = false;      // gsd_debug_train_plan_create: walk the step's structure (gradient order, bucket callbacks) without a GPU
   // per-call
   gsd_bucket_cb cb = nullptr;
@@ -158,6 +163,10 @@ void grad_done(gsd_train_plan* p, int pi) {
   const int b = p->bucket_of[pi];
   if (--p->pending[b] == 0 && p->cb) p->cb(p->cb_user, b, p->bucket_lo[b], p->bucket_hi[b], p->main, p->forked ? p->side : nullptr);
 }
+
+}  // namespace
+#include "train_plan_f32.h"
+namespace {
 
 int bn_bwd_launch(const void* da, const float* scale, const float* shift, const void* z, const float* mean, const float* rstd,
                   const float* gamma, double count, long npix, int C, float* dbeta, float* dgamma, void* dz, cudaStream_t st) {
@@ -258,7 +267,7 @@ int unit_backward(gsd_train_plan* p, TrainUnit& u, const void* da, const float* 
 
 extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g, int device) {
   GSD_CHECK(out && g, "gsd_train_plan_create: null argument");
-  GSD_CHECK(g->dtype == GSD_DTYPE_BF16, "gsd_train_plan_create: training runs the bf16 tensor-core path only");
+  GSD_CHECK(g->dtype == GSD_DTYPE_BF16 || g->dtype == GSD_DTYPE_FP32, "gsd_train_plan_create: geometry.dtype must be GSD_DTYPE_BF16 or GSD_DTYPE_FP32");
   GSD_CHECK(g->mode == GSD_MODE_TRAIN, "gsd_train_plan_create: geometry.mode must be GSD_MODE_TRAIN");
   GSD_CHECK(g->batch >= 1 && g->height >= 1 && g->width >= 1, "gsd_train_plan_create: bad shape");
   GSD_CHECK(g->in_channels >= 1 && g->in_channels <= 8, "gsd_train_plan_create: in_channels %d not in 1..8", g->in_channels);
@@ -282,6 +291,7 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
 
   gsd_train_plan* p = new gsd_train_plan();
   p->dry = dry;
+  p->f32 = g->dtype == GSD_DTYPE_FP32;
   p->g = *g;
   p->device = device;
   p->num_sms = sms;
@@ -296,7 +306,10 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
   const size_t B = g->batch;
   const int* dims = g->dims;
   size_t cur = 0;
-  p->in16 = tbump(&cur, B * g->height * g->width * 16 * 2);
+  const bool f32 = p->f32;
+  const size_t es = f32 ? 4 : 2;      // activation / packed operand element size
+  size_t dz_cur = 0;                  // fp32: double accumulators
+  p->in16 = tbump(&cur, f32 ? B * g->height * g->width * g->in_channels * 4 : B * g->height * g->width * 16 * 2);
   const size_t out_bytes = B * g->n_classes * g->height * g->width * 4;
   p->y = tbump(&cur, out_bytes);
   p->dy = tbump(&cur, out_bytes);
@@ -305,25 +318,28 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
   auto make_unit = [&](int l, int C0, int C1, int cin_real, int Cout, bool first, bool pool, bool apply, bool need_dx) {
     TrainUnit u;
     u.H = p->Hs[l]; u.W = p->Ws[l]; u.C0 = C0; u.C1 = C1; u.cin_real = cin_real; u.Cout = Cout;
-    u.first = first; u.pool = pool; u.apply = apply;
+    u.first = first; u.pool = pool; u.apply = apply || f32;
+    if (f32 && first) u.C0 = cin_real;       // no 16-channel padding on the FFMA path
+    apply = u.apply;
     u.p_w = pi++; u.p_g = pi++; u.p_b = pi++;
     u.bn = bn++;
     u.neg_off = neg; neg += Cout;
     const size_t px = B * u.H * u.W;
-    u.z = tbump(&cur, px * Cout * 2);
-    if (apply) u.a = tbump(&cur, px * Cout * 2);
-    if (pool) u.pooled = tbump(&cur, B * (u.H / 2) * (u.W / 2) * Cout * 2);
-    u.dz = tbump(&cur, px * Cout * 2);
+    u.z = tbump(&cur, px * Cout * es);
+    if (apply) u.a = tbump(&cur, px * Cout * es);
+    if (pool) u.pooled = tbump(&cur, B * (u.H / 2) * (u.W / 2) * Cout * es);
+    u.dz = tbump(&cur, px * Cout * es);
     if (need_dx) {
-      u.din0 = tbump(&cur, px * C0 * 2);
-      if (C1) u.din1 = tbump(&cur, px * C1 * 2);
+      u.din0 = tbump(&cur, px * C0 * es);
+      if (C1) u.din1 = tbump(&cur, px * C1 * es);
     }
+    if (f32) { u.dstat = dz_cur; dz_cur += 2 * (size_t)Cout * 8; u.dbwd = dz_cur; dz_cur += 2 * (size_t)Cout * 8; }
     u.consts = tbump(&cur, 4 * (size_t)Cout * 4);
     u.stats = zero_cur; zero_cur += align_up(2 * (size_t)Cout * 4, 256);
-    const size_t ktot = 9 * (size_t)(C0 + C1);
-    u.w_fwd = packed_cur; packed_cur += align_up(ktot * Cout * 2, 256);
-    if (!first) { u.w_dgrad = packed_cur; packed_cur += align_up(ktot * Cout * 2, 256); }
-    u.dwk = dwk_cur; dwk_cur += align_up(ktot * Cout * 4, 256);
+    const size_t ktot = 9 * (size_t)(u.C0 + C1);
+    u.w_fwd = packed_cur; packed_cur += align_up(ktot * Cout * es, 256);
+    if (!first) { u.w_dgrad = packed_cur; packed_cur += align_up(ktot * Cout * es, 256); }
+    if (!f32) { u.dwk = dwk_cur; dwk_cur += align_up(ktot * Cout * 4, 256); }
     p->param_numel.push_back((long long)Cout * cin_real * 9);
     p->param_numel.push_back(Cout);
     p->param_numel.push_back(Cout);
@@ -342,10 +358,11 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
     t.p_w = pi++; t.p_b = pi++;
     p->param_numel.push_back(4LL * t.Cin * t.Cout);
     p->param_numel.push_back(t.Cout);
-    t.u = tbump(&cur, B * (2 * t.hs) * (2 * t.ws) * t.Cout * 2);
-    t.din = tbump(&cur, B * t.hs * t.ws * t.Cin * 2);
-    t.w_fwd = packed_cur; packed_cur += align_up(4 * (size_t)t.Cin * t.Cout * 2, 256);
-    t.w_dgrad = packed_cur; packed_cur += align_up(4 * (size_t)t.Cin * t.Cout * 2, 256);
+    t.u = tbump(&cur, B * (2 * t.hs) * (2 * t.ws) * t.Cout * es);
+    t.din = tbump(&cur, B * t.hs * t.ws * t.Cin * es);
+    t.w_fwd = packed_cur; packed_cur += align_up(4 * (size_t)t.Cin * t.Cout * es, 256);
+    t.w_dgrad = packed_cur; packed_cur += align_up(4 * (size_t)t.Cin * t.Cout * es, 256);
+    if (f32) { t.dbias = dz_cur; dz_cur += (size_t)t.Cout * 8; }
     t.bias4 = tbump(&cur, 4 * (size_t)t.Cout * 4);
     p->ups.push_back(t);
     TrainUnit u1 = make_unit(l, dims[l], dims[l], 2 * dims[l], dims[l], false, false, true, true);
@@ -360,7 +377,13 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
   p->n_params = pi;
   p->n_bn = bn;
   p->neg_total = neg;
-  for (int l = 0; l < p->depth; ++l) p->dfull.push_back(tbump(&cur, B * p->Hs[l] * p->Ws[l] * dims[l] * 2));
+  for (int l = 0; l < p->depth; ++l) p->dfull.push_back(tbump(&cur, B * p->Hs[l] * p->Ws[l] * dims[l] * es));
+  if (f32) {
+    p->dhead = dz_cur; dz_cur += ((size_t)g->n_classes * dims[0] + g->n_classes) * 8;
+    p->dzero_bytes = dz_cur;
+    p->dzero = tbump(&cur, dz_cur);
+    p->da_head = tbump(&cur, B * g->height * g->width * dims[0] * 4);
+  }
   p->neg = tbump(&cur, (size_t)neg * 4);
   p->loss = zero_cur; zero_cur += 256;
   p->zero_bytes = zero_cur;
@@ -374,10 +397,14 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
   p->prep_bwd = tbump(&cur, 96 * sizeof(PrepItem));
   p->ws_bytes = align_up(cur, 1024);
   // resolve offsets that were relative to their arenas
-  auto fix = [&](TrainUnit& u) { u.stats += p->zero_arena; u.w_fwd += p->packed; if (!u.first) u.w_dgrad += p->packed; u.dwk += p->dwk0; };
+  auto fix = [&](TrainUnit& u) {
+    u.stats += p->zero_arena; u.w_fwd += p->packed; if (!u.first) u.w_dgrad += p->packed; u.dwk += p->dwk0;
+    u.dstat += p->dzero; u.dbwd += p->dzero;
+  };
   for (auto& u : p->enc) fix(u);
   for (auto& u : p->dec) fix(u);
-  for (auto& t : p->ups) { t.w_fwd += p->packed; t.w_dgrad += p->packed; }
+  for (auto& t : p->ups) { t.w_fwd += p->packed; t.w_dgrad += p->packed; t.dbias += p->dzero; }
+  p->dhead += p->dzero;
   p->loss += p->zero_arena;
   // conv inputs
   for (int l = 0; l <= p->depth; ++l) {
@@ -393,7 +420,7 @@ extern "C" int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g
   }
   // concat units: one split-output dgrad launch where the launch rules give it N >= 128 with streamed weights (small batches
   // plan N = 64 work items and the tap-streaming kernel has no split output: those keep two launches)
-  for (int i = 0; i < p->depth; ++i) {
+  for (int i = 0; i < p->depth && !f32; ++i) {
     TrainUnit& u = p->dec[2 * i];
     ConvDesc d;
     void* dummy = reinterpret_cast<void*>(static_cast<uintptr_t>(256));
@@ -446,6 +473,7 @@ extern "C" int gsd_train_plan_num_bn(const gsd_train_plan* p) { return p ? p->n_
 // kernel launches one gsd_train_step enqueues (bench.py's gpu_launches claim for the training leg)
 extern "C" int gsd_train_plan_launches(const gsd_train_plan* p) {
   if (!p) return 0;
+  if (p->f32) return p->launches_f32;       // counted while the last step was enqueued
   const int U = (int)(p->enc.size() + p->dec.size()), D = p->depth;
   int n = 3 + (3 * U - 1) + D + 1;            // pack, constants, prologue | conv + finalize (+ apply, not the last unit) | transposed convs | head
   n += 1;                                     // MSE
@@ -491,40 +519,46 @@ extern "C" int gsd_train_plan_bind(gsd_train_plan* p, const void* const* params,
     items.push_back(it);
   };
   auto add_unit = [&](const TrainUnit& u) {
+    if (p->f32) return;                       // the fp32 path packs its operands with its own kernels (train_plan_f32.h)
     add_item(0, p->params[u.p_w], p->ws + u.w_fwd, u.first ? nullptr : p->ws + u.w_dgrad, u.Cout, u.cin_real, u.first ? 16 : u.cin_real);
   };
   for (int l = 0; l <= p->depth; ++l) { add_unit(p->enc[2 * l]); add_unit(p->enc[2 * l + 1]); }
   for (int i = 0; i < p->depth; ++i) {
     const TrainUp& t = p->ups[i];
-    add_item(2, p->params[t.p_w], p->ws + t.w_fwd, nullptr, t.Cout, t.Cin, t.Cin);
-    add_item(3, p->params[t.p_w], p->ws + t.w_dgrad, nullptr, t.Cout, t.Cin, t.Cin);
+    if (!p->f32) {
+      add_item(2, p->params[t.p_w], p->ws + t.w_fwd, nullptr, t.Cout, t.Cin, t.Cin);
+      add_item(3, p->params[t.p_w], p->ws + t.w_dgrad, nullptr, t.Cout, t.Cin, t.Cin);
+    }
     add_unit(p->dec[2 * i]);
     add_unit(p->dec[2 * i + 1]);
   }
   GSD_CHECK(items.size() <= 64, "gsd_train_plan_bind: more than 64 pack items");
   p->n_pack = (int)items.size();
   p->pack_units = units;
-  GSD_CUDA(cudaMemcpy(p->ws + p->pack_table, items.data(), items.size() * sizeof(gsd_pack_item), cudaMemcpyHostToDevice));
+  if (!items.empty()) GSD_CUDA(cudaMemcpy(p->ws + p->pack_table, items.data(), items.size() * sizeof(gsd_pack_item), cudaMemcpyHostToDevice));
   std::vector<PrepItem> fwd, bwd;
   float* negp = wsp<float>(p, p->neg);
   auto all_units = [&](auto fn) { for (auto& u : p->enc) fn(u); for (auto& u : p->dec) fn(u); };
   all_units([&](TrainUnit& u) {
+    if (p->f32) return;                       // fp32: no centring, BatchNorm gradients are written, not accumulated
     fwd.push_back(PrepItem{p->bnbuf[2 * u.bn], negp + u.neg_off, u.Cout, u.Cout, -1.f});      // centring constant = -running_mean
     bwd.push_back(PrepItem{nullptr, p->grads[u.p_g], u.Cout, 1, 0.f});                          // BatchNorm gradients are accumulated
     bwd.push_back(PrepItem{nullptr, p->grads[u.p_b], u.Cout, 1, 0.f});
   });
   for (auto& t : p->ups) {
     fwd.push_back(PrepItem{p->params[t.p_b], wsp<float>(p, t.bias4), 4 * t.Cout, t.Cout, 1.f});   // bias for each of the 4 (dy,dx) groups
-    bwd.push_back(PrepItem{nullptr, p->grads[t.p_b], t.Cout, 1, 0.f});
+    if (!p->f32) bwd.push_back(PrepItem{nullptr, p->grads[t.p_b], t.Cout, 1, 0.f});
   }
-  bwd.push_back(PrepItem{nullptr, p->grads[p->n_params - 2], p->g.n_classes * p->g.dims[0], 1, 0.f});
-  bwd.push_back(PrepItem{nullptr, p->grads[p->n_params - 1], p->g.n_classes, 1, 0.f});
+  if (!p->f32) {
+    bwd.push_back(PrepItem{nullptr, p->grads[p->n_params - 2], p->g.n_classes * p->g.dims[0], 1, 0.f});
+    bwd.push_back(PrepItem{nullptr, p->grads[p->n_params - 1], p->g.n_classes, 1, 0.f});
+  }
   GSD_CHECK(fwd.size() <= 64 && bwd.size() <= 96, "gsd_train_plan_bind: too many per-step constant items");
   p->n_prep_fwd = (int)fwd.size();
   p->n_prep_bwd = (int)bwd.size();
-  GSD_CUDA(cudaMemcpy(p->ws + p->prep_fwd, fwd.data(), fwd.size() * sizeof(PrepItem), cudaMemcpyHostToDevice));
-  GSD_CUDA(cudaMemcpy(p->ws + p->prep_bwd, bwd.data(), bwd.size() * sizeof(PrepItem), cudaMemcpyHostToDevice));
-  GSD_CUDA(cudaMemset(p->ws + p->dwk0, 0, p->dwk_bytes));      // wgrad accumulators: zero once, the unpack kernel re-zeroes them
+  if (!fwd.empty()) GSD_CUDA(cudaMemcpy(p->ws + p->prep_fwd, fwd.data(), fwd.size() * sizeof(PrepItem), cudaMemcpyHostToDevice));
+  if (!bwd.empty()) GSD_CUDA(cudaMemcpy(p->ws + p->prep_bwd, bwd.data(), bwd.size() * sizeof(PrepItem), cudaMemcpyHostToDevice));
+  if (p->dwk_bytes) GSD_CUDA(cudaMemset(p->ws + p->dwk0, 0, p->dwk_bytes));      // wgrad accumulators: zero once, the unpack kernel re-zeroes them
   GSD_CUDA(cudaDeviceSynchronize());
   p->bound = true;
   return 0;
@@ -552,6 +586,7 @@ extern "C" int gsd_train_forward(gsd_train_plan* p, const float* x, float* y, vo
   GSD_CHECK(p->bound, "gsd_train_forward: call gsd_train_plan_bind first");
   GSD_DEVICE(p->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->f32) return f32_forward(p, x, y, st);
   const gsd_geometry& g = p->g;
   const int B = g.batch;
   GSD_TRY(gsd_op_pack_weights_batched(wsp<gsd_pack_item>(p, p->pack_table), p->n_pack, p->pack_units, st));   // every layer's bf16 operands
@@ -590,6 +625,11 @@ extern "C" int gsd_backward(gsd_train_plan* p, const float* dy, void* stream, gs
   p->forked = false;
   cudaStream_t st = p->main;
   const int B = p->g.batch, depth = p->depth;
+  if (p->f32 && !p->dry) {
+    const int rc = f32_backward(p, dy, st);
+    p->cb = nullptr;
+    return rc;
+  }
   if (!p->dry) {
     prep_kernel<<<p->n_prep_bwd, 256, 0, st>>>(wsp<PrepItem>(p, p->prep_bwd));
     GSD_CUDA(cudaGetLastError());

@@ -163,8 +163,9 @@ class UNet(nn.Module):
             raise ValueError(f"expected (N, {want_c}, H, W), got {tuple(x.shape)}")
         if self.training:
             # batch-statistics BatchNorm + autograd bridge to the backward kernels (train_unet.py:347,374)
-            if pp is not None or self.precision != "bf16":
-                raise NotImplementedError("train mode runs the plain bf16 network (no fused pre/post-processing, no fp32 mode)")
+            # precision 'fp32' selects the FFMA parity path of the training plan (csrc/train_plan_f32.h)
+            if pp is not None:
+                raise NotImplementedError("train mode runs the plain network (no fused pre/post-processing)")
             from ..train.engine import unet_train_forward
             return unet_train_forward(self, x.contiguous().float())
         if x.requires_grad and torch.is_grad_enabled():

@@ -42,7 +42,10 @@ class TrainPlan:
         g.n_dims = len(net.layer_dimensions)
         for i, d in enumerate(net.layer_dimensions):
             g.dims[i] = int(d)
-        g.dtype, g.mode = _lib.DTYPE_BF16, _lib.MODE_TRAIN
+        # 'fp32' (UNet.set_precision): the FFMA parity path -- same step, fp32 activations, ~1/50 of the speed (csrc/train_plan_f32.h)
+        g.dtype = _lib.DTYPE_FP32 if getattr(net, "precision", "bf16") == "fp32" else _lib.DTYPE_BF16
+        g.mode = _lib.MODE_TRAIN
+        self.precision = getattr(net, "precision", "bf16")
         self.shape = (batch, height, width)
         self.device = device
         self.handle = C.c_void_p()
@@ -121,7 +124,7 @@ class _BridgeState:
         self.plans = {}
 
     def plan_for(self, net, x):
-        key = (x.shape[0], x.shape[2], x.shape[3], x.device)
+        key = (x.shape[0], x.shape[2], x.shape[3], x.device, getattr(net, "precision", "bf16"))
         plan = self.plans.get(key)
         if plan is None:
             if len(self.plans) >= 2:
@@ -278,7 +281,7 @@ class FusedTrainer:
     # ------------------------------------------------------------------ plan
     def _plan_for(self, x):
         shape = (x.shape[0], x.shape[2], x.shape[3])
-        if self.plan is None or self.plan.shape != shape:
+        if self.plan is None or self.plan.shape != shape or self.plan.precision != getattr(self.net, "precision", "bf16"):
             if self._graph is not None:
                 raise RuntimeError("use_graph=True: the input shape is fixed once the step has been captured")
             if not self.overlap_wgrad:

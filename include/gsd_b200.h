@@ -329,7 +329,10 @@ typedef struct gsd_optimizer_state {
   long long* counter;   /* device int64[2]: Adam steps / EMA updates done so far (advanced on the device) */
   gsd_adam hp;
 } gsd_optimizer_state;
-/* Replaces: UNet(...).train() + the shape specialisation of the first step (train_unet.py:235,344). */
+/* Replaces: UNet(...).train() + the shape specialisation of the first step (train_unet.py:235,344).
+   g->mode = GSD_MODE_TRAIN; g->dtype = GSD_DTYPE_BF16 (tcgen05 path, the measured one) or GSD_DTYPE_FP32 (FFMA parity path:
+   the same entry points and protocol on fp32 activations, ~1/50 of the speed, for gradient / loss-curve comparisons with the
+   fp32 reference; csrc/train_plan_f32.h). */
 int gsd_train_plan_create(gsd_train_plan** out, const gsd_geometry* g, int device);
 void gsd_train_plan_destroy(gsd_train_plan* p);
 size_t gsd_train_plan_workspace_bytes(const gsd_train_plan* p);
