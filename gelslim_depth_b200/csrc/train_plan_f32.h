@@ -176,6 +176,9 @@ int f32_backward(gsd_train_plan* p, const float* dy, cudaStream_t st) {
   const gsd_geometry& G = p->g;
   const int B = G.batch, depth = p->depth, ncls = G.n_classes, C0 = G.dims[0];
   const long npix_img = (long)G.height * G.width;
+  // every double accumulator of the backward pass starts from zero, also when backward runs twice on one forward (the
+  // forward's batch-statistics sums in the same arena are dead by now)
+  GSD_CUDA(cudaMemsetAsync(p->ws + p->dzero, 0, p->dzero_bytes, st));
   // OutConv (unet.py:54-57)
   TrainUnit& last = p->dec.back();
   float* da_head = wsp<float>(p, p->da_head);

@@ -88,3 +88,39 @@ def test_normalisation_constants_match_reference_tables(golden_processing):
         scale, bias, den = depth_affine_constants(m, 0.9, dp)
         assert torch.allclose(d * (den / scale) + bias, golden_processing["denorm_depth_" + m], rtol=1e-5, atol=1e-6)
         assert torch.allclose(d * (scale / den) - scale * bias / den, golden_processing["norm_depth_" + m], rtol=1e-5, atol=1e-6)
+
+
+def test_training_plan_layouts_bf16_and_fp32_without_a_gpu():
+    """gsd_debug_train_plan_create (no GPU): the bf16 plan and the fp32 parity plan (geometry.dtype = GSD_DTYPE_FP32,
+    csrc/train_plan_f32.h) describe the same parameters in the same order; the fp32 workspace (fp32 activations and operand
+    copies, no split-K weight-gradient accumulators) is larger than the bf16 one but less than 2.5x; other dtypes are rejected."""
+    import ctypes as C
+    from gelslim_depth_b200 import _lib
+    from gelslim_depth_b200._lib import lib
+
+    def plan(dtype):
+        g = _lib.Geometry()
+        g.batch, g.in_channels, g.height, g.width, g.n_classes, g.n_dims = 2, 6, 40, 53, 2, 5
+        for i, d in enumerate((64, 128, 256, 512, 1024)):
+            g.dims[i] = d
+        g.dtype, g.mode = dtype, _lib.MODE_TRAIN
+        h = C.c_void_p()
+        rc = lib.gsd_debug_train_plan_create(C.byref(h), C.byref(g))
+        return rc, h
+
+    rc, hb = plan(_lib.DTYPE_BF16)
+    assert rc == 0, lib.gsd_last_error()
+    rc, hf = plan(_lib.DTYPE_FP32)
+    assert rc == 0, lib.gsd_last_error()
+    n = lib.gsd_train_plan_num_params(hb)
+    assert n == lib.gsd_train_plan_num_params(hf) == 18 * 3 + 4 * 2 + 2
+    assert lib.gsd_train_plan_num_bn(hb) == lib.gsd_train_plan_num_bn(hf) == 18
+    a, b = (C.c_longlong * n)(), (C.c_longlong * n)()
+    assert lib.gsd_train_plan_param_numel(hb, a, n) == n and lib.gsd_train_plan_param_numel(hf, b, n) == n
+    assert list(a) == list(b) and a[0] == 64 * 6 * 9
+    wb, wf = lib.gsd_train_plan_workspace_bytes(hb), lib.gsd_train_plan_workspace_bytes(hf)
+    assert wb < wf < 2.5 * wb, (wb, wf)
+    lib.gsd_train_plan_destroy(hb)
+    lib.gsd_train_plan_destroy(hf)
+    rc, _ = plan(7)
+    assert rc != 0 and b"dtype" in lib.gsd_last_error()
