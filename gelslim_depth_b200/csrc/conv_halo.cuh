@@ -58,6 +58,11 @@ struct HaloParams {
   FastDiv fd_ntiles, fd_tx, fd_ty;   // item -> (n tile, m group), m tile -> (tx, ty, b) without integer division
 };
 
+#ifndef GSD_ACC_BUFFERS_N64
+#define GSD_ACC_BUFFERS_N64 4
+#endif
+constexpr int kAccBuffersN64 = GSD_ACC_BUFFERS_N64;
+
 template <int BKB>
 struct HaloGeom {
   static constexpr int BOX_BYTES = kHaloRows * BKB;                       // bytes one TMA halo box delivers
@@ -85,8 +90,11 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
   constexpr int B_BYTES = BN_CTA * BKB;
   constexpr uint32_t NCTA = CTA2 ? 2 : 1;
   constexpr int KEL = BKB / 2;
-  constexpr int TMEM_COLS = (2 * MT * BN <= 128) ? 128 : (2 * MT * BN <= 256) ? 256 : 512;
-  static_assert(2 * MT * BN <= 512, "accumulators exceed TMEM");
+  // accumulator ring in TMEM: 2 buffers, 4 for the one-K-block N = 64 tiles (36 UMMAs ~ 2 000 cycles per tile: with two buffers
+  // the epilogue's round trip -- commit, tcgen05.ld, stores, arrive; across the cluster for a CTA pair -- is exposed)
+  constexpr int NACC = (BN == 64) ? ((kAccBuffersN64 * MT * BN <= 512) ? kAccBuffersN64 : 512 / (MT * BN)) : 2;
+  constexpr int TMEM_COLS = (NACC * MT * BN <= 128) ? 128 : (NACC * MT * BN <= 256) ? 256 : 512;
+  static_assert(NACC * MT * BN <= 512 && (NACC & (NACC - 1)) == 0, "accumulators exceed TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -110,9 +118,9 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
   const uint32_t bar_emptyA = bar_fullA + 8 * na;      // [na]
   const uint32_t bar_fullB = bar_emptyA + 8 * na;      // [nb] (or [1] = resident weights landed)
   const uint32_t bar_emptyB = bar_fullB + 8 * (WRES ? 1 : nb);
-  const uint32_t bar_acc_full = bar_emptyB + 8 * (WRES ? 1 : nb);   // [2]
-  const uint32_t bar_acc_empty = bar_acc_full + 16;                  // [2]
-  const uint32_t s_tmem_slot = bar_acc_empty + 16;
+  const uint32_t bar_acc_full = bar_emptyB + 8 * (WRES ? 1 : nb);   // [NACC]
+  const uint32_t bar_acc_empty = bar_acc_full + 8 * NACC;            // [NACC]
+  const uint32_t s_tmem_slot = bar_acc_empty + 8 * NACC;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (s_tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5;
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < na; ++i) { mbar_init(bar_fullA + 8 * i, 1); mbar_init(bar_emptyA + 8 * i, 1); }
     for (int i = 0; i < (WRES ? 1 : nb); ++i) { mbar_init(bar_fullB + 8 * i, 1); mbar_init(bar_emptyB + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4 * NCTA); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4 * NCTA); }
     fence_barrier_init();
   }
   if (warp == 2) { if (CTA2) tmem_alloc_2sm<TMEM_COLS>(s_tmem_slot); else tmem_alloc<TMEM_COLS>(s_tmem_slot); }
@@ -215,8 +223,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
     if (WRES) { mbar_wait(bar_fullB, 0); tc_fence_after(); }
     int it = 0;
     for (int item = first_item; item < total_items; item += item_stride, ++it) {
-      const int buf = it & 1;
-      mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1);
+      const int buf = it & (NACC - 1);
+      mbar_wait(bar_acc_empty + 8 * buf, ((it / NACC) & 1) ^ 1);
       tc_fence_after();
       const bool bias_mma = p.bias != nullptr;
       if (bias_mma) {          // D = 1 x bias^T first; every tap then accumulates
@@ -294,12 +302,12 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, (BKB == 32) ? 2 : 1) conv_halo
     int it = 0;
     pdl_wait();                 // no global write before the predecessor grid has finished (it may still read our output buffers' neighbours)
     for (int item = first_item; item < total_items; item += item_stride, ++it) {
-      const int buf = it & 1;
-      if (NEPI == 8 && buf != eset) continue;          // the other warp set owns this accumulator buffer
+      const int buf = it & (NACC - 1);
+      if (NEPI == 8 && (buf & 1) != eset) continue;    // the other warp set owns this accumulator buffer
       uint32_t mg, nt;
       fdivmod((uint32_t)item, p.fd_ntiles, mg, nt);
       if (CTA2) mg = 2 * mg + rank;
-      mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1);
+      mbar_wait(bar_acc_full + 8 * buf, (it / NACC) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < MT; ++j) {

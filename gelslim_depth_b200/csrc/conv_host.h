@@ -361,12 +361,16 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   }
   GSD_CHECK(bkb == 128 || wres, "halo conv: first-layer path needs resident weights");
   // CTA pairs (cta_group::2).  GSD_CTA2: 1 = the measured rule below (default), 0 = never, 2 = every 64-channel-block layer (tests).
-  // Measured on B200, batch 64 (tools/exp_cta2.py): streamed-weight layers gain 8-17 % as pairs, the resident-weight N = 64
-  // layers lose 4-30 % (their UMMA is A-read-bound either way), so those keep single CTAs.  Streamed-weight layers pair at
+  // Measured on B200, batch 64 (tools/exp_cta2.py): streamed-weight layers gain 8-17 % as pairs.  Streamed-weight layers pair at
   // every batch size: at batch 1-3 the grid is one partial wave either way and a pair reads each weight stage once for two
   // M tiles (same-box A/B, tools/ab_forward.py: batch 1 0.362 -> 0.344 ms, batch 2 0.538 -> 0.506 ms, batch >= 4 unchanged).
+  // Resident-weight N = 64 layers (inc.3, up.3.conv.3, their dgrads): slower as pairs with a 2-deep accumulator ring (the
+  // epilogue's round trip across the cluster is exposed behind 36-UMMA tiles: inc.3 0.82 -> 1.04 ms), faster with the 4-deep ring
+  // of conv_halo.cuh (same-box A/B at batch 64: inc.3 0.828 -> 0.784 ms, up.3.conv.3 0.828 -> 0.757; batch 16-32: 0-8 %; batch <= 8
+  // no difference), hence pairs from ~100 tiles per SM on.
+  const bool wres_pair = wres && bkb == 128 && d.Cout == 64 && mtl_all >= 100L * num_sms;
   L->cta2 = (bkb == 128 && num_sms % 2 == 0 &&
-             (cta2_mode == 2 || (cta2_mode == 1 && ((!wres && mtl_all >= 2) || pair64)))) ? 1 : 0;
+             (cta2_mode == 2 || (cta2_mode == 1 && ((!wres && mtl_all >= 2) || pair64 || wres_pair)))) ? 1 : 0;
   const int aux = 4 * d.Cout * 4 + 2048 + nepi * kEpiStageBytesPerWarp + 2048 + (d.bias ? kBiasOnesBytes + 64 * 32 : 0);
   const int b_bytes = (L->cta2 ? bn / 2 : bn) * bkb;
   if (wres) {
