@@ -1,7 +1,7 @@
 """Host logic of libgsd_b200.so that needs no GPU: which kernel / configuration every conv3x3 layer of the U-Net gets
 (csrc/conv_host.h: halo-resident vs tap-streaming kernel, UMMA width, resident weights, CTA pairs, ring depths, grid)
 and the chunk schedule of the host pipeline (csrc/plan.cu).  The expected batch-64 configurations are the kernels of
-the committed ncu launch list (profiles/r1_bench_launches.md), i.e. what was measured on the B200."""
+the committed ncu launch list (profiles/r2_fwd_launches.md, profiles/r2_ncu_full_convs.md), i.e. what was measured on the B200."""
 import ctypes as C
 import itertools
 
@@ -37,7 +37,7 @@ def unet_layers(H, W, dims=(64, 128, 256, 512, 1024)):
     return layers
 
 
-# (halo kernel, N, M tiles, resident weights, epilogue warps, CTA pair) measured at batch 64 -- profiles/r1_bench_launches.md
+# (halo kernel, N, M tiles, resident weights, epilogue warps, CTA pair) measured at batch 64 -- profiles/r2_ncu_full_convs.md
 EXPECTED_B64 = {
     "inc.3": (1, 64, 1, 1, 8, 1), "down.0.0": (1, 128, 2, 0, 8, 1), "down.0.3": (1, 128, 2, 0, 8, 1),
     "down.1.0": (1, 128, 2, 0, 8, 1), "down.1.3": (1, 128, 2, 0, 8, 1), "down.2.0": (1, 256, 1, 0, 8, 1),
