@@ -325,6 +325,7 @@ inline int build_halo_launch(const ConvDesc& d, int num_sms, HaloLaunch* L) {
   const long mtl_all = (long)((d.W + 7) / 8) * ((d.H + 15) / 16) * d.B;
   // 64 output channels with K >= 1152 (up.3.conv.0): as single CTAs the resident weights (144 KB) leave room for 4
   // epilogue warps only; a CTA pair with streamed weights (32 rows per CTA and stage) and M = 2 x 256 measured 7 % faster
+  // (round 2: resident in a pair -- 72 KB per CTA, eight epilogue warps, 4-deep accumulator ring -- measured 1.309 vs 1.222 ms: streamed stays)
   const bool pair64 = cta2_mode == 1 && bkb == 128 && d.Cout == 64 && cbt >= 2 && num_sms % 2 == 0 &&
                       ((mtl_all + 1) / 2 + 1) / 2 >= num_sms / 2;
   if (d.Cout == 64 && !pair64 && 9 * cbt * 64 * bkb <= 150 * 1024 && !(bkb == 128 && getenv("GSD_WRES0"))) { bn = 64; mt = 1; wres = 1; nepi = (9 * cbt * 64 * bkb > 80 * 1024) ? 4 : 8; }
