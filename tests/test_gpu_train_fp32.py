@@ -106,8 +106,8 @@ def test_fp32_loss_curve_200_steps_vs_reference():
     two runs share every rounding point except summation order: the first 20 losses agree to 3e-5 (bound 3e-4; the bf16 path's
     bound is 1e-2 on the first loss only).  After that training is chaotic and this path is not bit-reproducible (fp32 atomics
     in the weight gradients), so the rest of the curve is compared through the same robust statistics as the bf16 path's test
-    with tighter bounds -- six repetitions on B200 gave: 10-step-smoothed log10 distance max 0.05-0.27 (at the reference's own
-    loss spike around step 105-115), mean 0.010-0.064, median of the last 20 losses 1.01-1.13 x the reference's.  Bounds:
+    with tighter bounds -- fourteen repetitions on B200 gave: 10-step-smoothed log10 distance max 0.05-0.27 (at the reference's own
+    loss spike around step 105-115), mean 0.006-0.064, median of the last 20 losses 0.99-1.18 x the reference's.  Bounds:
     max <= 0.6 decade, mean <= 0.15, final level within [0.7, 1.4] (bf16 path: 1.0 / 0.25 / [0.25, 4])."""
     from gelslim_depth_b200.models.unet import UNet
     from gelslim_depth_b200.train.engine import FusedTrainer
