@@ -243,3 +243,54 @@ def test_fp32_train_step_through_the_c_abi_only():
     assert e_g < 3 * e_ref + 1e-5, (e_g, e_ref)
     assert lib.gsd_train_plan_launches(h) > 100          # counted while the step was enqueued
     lib.gsd_train_plan_destroy(h)
+
+
+def test_bf16_training_gradients_vs_fp32_mode_full_geometry():
+    """The measured (bf16 tensor-core) training path against the fp32 parity path ON THE GPU at the north-star geometry
+    (UNet(6,2), 6x320x427, batch 4, smooth learnable targets), at a point of the training trajectory (40 optimizer steps after
+    the trainer's init; at the init itself the output bias carries 99.9 % of the gradient and the deep levels 1e-9 of it): same
+    forward output to bf16 accuracy, same loss, and EVERY one of the 64 parameter tensors' gradients points the same way
+    (cosine > 0.99; measured 0.9973 .. 0.9997 for the worst tensor over four runs) with the same length (projection gain within 3 %; measured 0.992 .. 1.016 over all tensors) as the fp32
+    path's.  An implementation error in a backward kernel shows as bias (direction / gain); bf16 storage of activations and their
+    gradients as zero-mean noise."""
+    import copy
+    from gelslim_depth_b200.models.unet import UNet
+    from gelslim_depth_b200.train.engine import FusedTrainer
+    torch.manual_seed(11)
+    net = UNet(6, 2)
+    net.load_state_dict(oracle.trainer_init_state_dict(net.state_dict(), seed=12))
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(4, 6, 320, 427, generator=g)
+    k = torch.ones(1, 1, 9, 9) / 81.0
+    tgt = -0.9 * torch.nn.functional.conv2d(x.mean(1, keepdim=True), k, padding=4).repeat(1, 2, 1, 1)
+    xd, td = x.to(dev()), tgt.to(dev())
+    warm = copy.deepcopy(net).to(dev()).train()
+    ft = FusedTrainer(warm, use_graph=False)
+    for _ in range(40):
+        ft.step(xd, td)
+    ft.close()
+    res = {}
+    for prec in ("bf16", "fp32"):
+        n = copy.deepcopy(warm).set_precision(prec).train()
+        y = n(x=xd)
+        loss = torch.mean((y - td) ** 2)
+        loss.backward()
+        res[prec] = (n, y.detach(), float(loss.detach()))
+    (nb, yb, lb), (nf, yf, lf) = res["bf16"], res["fp32"]
+    fwd = rel_l2(yb, yf)
+    stats = {}
+    for (name, pb), (_, pf) in zip(nb.named_parameters(), nf.named_parameters()):
+        a, b = pb.grad.double().flatten(), pf.grad.double().flatten()
+        stats[name] = (float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300)), float(torch.dot(a, b) / (torch.dot(b, b) + 1e-300)))
+    fa = torch.cat([p_.grad.double().flatten() for p_ in nb.parameters()])
+    fb = torch.cat([p_.grad.double().flatten() for p_ in nf.parameters()])
+    whole_cos = float(torch.dot(fa, fb) / (fa.norm() * fb.norm()))
+    worst = min(stats, key=lambda n_: stats[n_][0])
+    gains = [v[1] for v in stats.values()]
+    print(f"bf16 vs fp32 path at 6x320x427 after 40 steps: forward rel-L2 {fwd:.2e}, loss {lb:.6f} vs {lf:.6f}, whole gradient cos {whole_cos:.6f}; "
+          f"{len(stats)} tensors: worst cos {stats[worst][0]:.4f} ({worst}), gain {min(gains):.3f} .. {max(gains):.3f}")
+    assert fwd < 3e-2, fwd
+    assert abs(lb - lf) < 1e-3 * lf, (lb, lf)
+    assert whole_cos > 0.99999, whole_cos
+    assert stats[worst][0] > 0.99, {n_: v for n_, v in stats.items() if v[0] < 0.998}
+    assert 0.97 < min(gains) and max(gains) < 1.03, {n_: v for n_, v in stats.items() if not 0.98 < v[1] < 1.02}
