@@ -1,5 +1,5 @@
 """Repeat the 200-step loss-curve run (tests/test_gpu_train.py::test_loss_curve_200_steps_vs_reference) N times and print the
-deviation statistics of every run: a race would show up as an outlier.  python tools/stress_train_curve.py [runs]"""
+deviation statistics of every run: a race would show up as an outlier.  python tests/stress_train_curve.py [runs]"""
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -237,7 +237,7 @@ def test_loss_curve_200_steps_vs_reference():
     (tests/golden/make_train_curve.py).  The B200 path (bf16, fused MSE + Adam + EMA) must follow it: same first-step
     loss, the same decades-long descent and the same final level.  Training is chaotic and the GPU path is not bit-
     reproducible (fp32 atomics in the BatchNorm statistics and the split-K weight gradients), so the criteria are robust
-    statistics; 50 repetitions (tools/stress_train_curve.py) gave: log10 distance of the 10-step-smoothed curves max
+    statistics; 50 repetitions (tests/stress_train_curve.py) gave: log10 distance of the 10-step-smoothed curves max
     0.04-0.39 (at the loss spike around step 105-115 that the reference has too, or at an isolated late spike), mean
     0.01-0.10, 90th percentile 0.02-0.29, median of the last 20 losses 0.83-2.05 x the reference's.  Thresholds (about
     2.5x the observed extremes): max <= 1.0 decade, mean <= 0.25, 90th percentile <= 0.6, median of the last 20 losses

@@ -12,23 +12,22 @@ from gelslim_depth_b200.engine import make_prepost
 
 
 def cpu_path_fps(seconds=12.0):
-    """the reference algorithm (oracle port) on this box's host cores: frames/s at batch 1 and batch 8"""
+    """the reference algorithm on this box's host cores (frames/s at batch 1 and batch 8): bench.py's `cpu_baseline` leg, the one
+    place outside tests/ that may execute oracle/"""
     import time
-    import oracle
+    import bench
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = oracle.random_init_state_dict(6, 2, seed=0)
     out = {"cores": os.cpu_count()}
     for b in (1, 8):
-        x = torch.rand(b, 6, 320, 427)
+        step = bench._cpu_step_fn(torch, b)
         ts, t_all = [], time.perf_counter()
-        with torch.no_grad():
-            for i in range(6):
-                t0 = time.perf_counter()
-                oracle.unet_forward(sd, x)
-                if i:
-                    ts.append(time.perf_counter() - t0)
-                if time.perf_counter() - t_all > seconds / 2 and len(ts) >= 2:
-                    break
+        for i in range(6):
+            t0 = time.perf_counter()
+            step()
+            if i:
+                ts.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_all > seconds / 2 and len(ts) >= 2:
+                break
         out[f"batch{b}_frames_per_s"] = b / sorted(ts)[len(ts) // 2]
     return out
 
